@@ -1,0 +1,226 @@
+/*
+ * wam.h — C ABI of the B200-native FSK physical layer (libwam.so).
+ *
+ * This is the drop-in boundary for ONE path of cho45/WebAudio-Modem: FSKCore
+ * modulate/demodulate (src/modems/fsk.ts) + the filters it uses (src/dsp/filters.ts)
+ * + CRC-16 / XModem packet checking for framed blocks (src/utils/crc16.ts,
+ * src/transports/xmodem/packet.ts).  Each entry point names the reference interface it
+ * replaces.  The reference-side binding (N-API addon + TypeScript class implementing
+ * IModulator, src/core.ts:88-117) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C types only; caller owns every buffer; no C++ exceptions cross the ABI.
+ *  - every function returns 0 (WAM_OK) or a negative wam_error; wam_last_error() gives a
+ *    thread-local message.  WAM_E_NOT_CONFIGURED maps to the reference's
+ *    Error('FSK modulator not configured') / Error('FSK demodulator not configured')
+ *    (fsk.ts:191-193,378-380).
+ *  - one handle = one CUDA device; handles are not re-entrant (FSKCore is not either).
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *    WAM_E_CUDA.
+ */
+#ifndef WAM_H
+#define WAM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WAM_VERSION 100 /* 0.1.0 */
+
+typedef enum wam_error {
+  WAM_OK = 0,
+  WAM_E_INVALID = -1,        /* bad argument */
+  WAM_E_NOT_CONFIGURED = -2, /* fsk.ts:191-193,378-380 */
+  WAM_E_CUDA = -3,           /* CUDA runtime/driver error, or no device */
+  WAM_E_NOMEM = -4,
+  WAM_E_CAPACITY = -5,       /* caller's output buffer too small */
+  WAM_E_UNSUPPORTED = -6,    /* configuration outside what the kernels implement */
+  WAM_E_FILTER_B_EMPTY = -10, /* 'Feedforward coefficients (b) cannot be empty'  filters.ts:19 */
+  WAM_E_FILTER_A_EMPTY = -11, /* 'Feedback coefficients (a) cannot be empty'     filters.ts:20 */
+  WAM_E_FILTER_A0_ZERO = -12, /* 'First feedback coefficient (a[0]) cannot be zero' filters.ts:21 */
+  WAM_E_PKT_SEQUENCE = -20,   /* 'Invalid sequence: N. Must be 1-255.'  packet.ts:22-24 */
+  WAM_E_PKT_PAYLOAD = -21     /* 'Payload too large: N. Max 255 bytes.' packet.ts:25-27 */
+} wam_error;
+
+/* FSKConfig — src/modems/fsk.ts:5-17 (+ sampleRate, baudRate from BaseModulatorConfig).
+ * Field names and meaning are the reference's; DEFAULT_FSK_CONFIG via wam_fsk_default_config. */
+typedef struct wam_fsk_config {
+  double sampleRate;
+  double baudRate;
+  double markFrequency;
+  double spaceFrequency;
+  const uint8_t* preamblePattern;
+  int32_t preambleLength;
+  const uint8_t* sfdPattern;
+  int32_t sfdLength;
+  int32_t startBits;
+  int32_t stopBits;
+  int32_t parity;             /* 0 'none', 1 'even', 2 'odd' */
+  double syncThreshold;
+  int32_t agcEnabled;
+  double preFilterBandwidth;
+  int32_t adaptiveThreshold;  /* accepted and ignored, like the reference (dead flag) */
+} wam_fsk_config;
+
+/* FSKCore.getStatus() — src/modems/fsk.ts:481-493, plus the event counts a host needs to
+ * re-emit 'eod' / 'error' (fsk.ts:289,219). */
+typedef struct wam_fsk_status {
+  int32_t ready;
+  int32_t frameStarted;
+  double globalSampleCounter;
+  double receivedBitsLength;
+  double byteBufferLength;
+  double demodulationCalls;
+  double syncDetections;
+  double silenceThreshold;
+  double totalSamplesProcessed;
+  double eodEvents;
+  double errorEvents;
+  double configuredEvents;
+} wam_fsk_status;
+
+int wam_version(void);
+const char* wam_last_error(void);
+const char* wam_error_string(int code);
+int wam_device_count(int* count);
+
+/* DEFAULT_FSK_CONFIG — fsk.ts:19-33 (pattern pointers reference static storage) */
+void wam_fsk_default_config(wam_fsk_config* cfg);
+
+/* ---------------------------------------------------------------------------------------
+ * Single-stream modem: drop-in for one FSKCore instance (IModulator, src/core.ts:88-117)
+ * ------------------------------------------------------------------------------------- */
+typedef struct wam_fsk wam_fsk;
+
+int wam_fsk_create(int device, wam_fsk** out);               /* new FSKCore()           fsk.ts:82 */
+int wam_fsk_destroy(wam_fsk* m);                             /* dispose()               core.ts:106 */
+int wam_fsk_configure(wam_fsk* m, const wam_fsk_config* c);  /* configure()             fsk.ts:133-157 */
+int wam_fsk_is_ready(wam_fsk* m);                            /* isReady()               core.ts:270-272 */
+/* number of samples modulateData(nbytes) produces (fsk.ts:391-394); negative wam_error */
+long wam_fsk_modulate_size(wam_fsk* m, long nbytes);
+/* modulateData() — fsk.ts:377-424.  out: host float32[cap]. */
+int wam_fsk_modulate(wam_fsk* m, const uint8_t* data, long nbytes, float* out, long cap, long* n_out);
+/* demodulateData() — fsk.ts:190-222.  samples: host float32[n]; MUTATED IN PLACE when AGC is
+ * enabled, exactly like the reference (fsk.ts:55).  out receives the bytes completed during
+ * this call (returned once).  */
+int wam_fsk_demodulate(wam_fsk* m, float* samples, long n, uint8_t* out, long cap, long* n_out);
+int wam_fsk_reset(wam_fsk* m);                               /* reset()                 fsk.ts:464-469 */
+int wam_fsk_status_get(wam_fsk* m, wam_fsk_status* st);      /* getStatus()             fsk.ts:481-493 */
+
+/* ---------------------------------------------------------------------------------------
+ * Batched modem: n_streams independent FSKCore instances with device-resident streaming
+ * state, one GPU.  (The new entry point named by the north star; equivalent to n_streams
+ * reference instances each receiving the same demodulateData/modulateData call.)
+ * ------------------------------------------------------------------------------------- */
+typedef struct wam_fsk_batch wam_fsk_batch;
+
+enum {
+  WAM_BATCH_WRITEBACK_AGC = 1u << 0, /* write the AGC-scaled samples back (reference mutates its input) */
+  WAM_BATCH_TAP_PREFILTER = 1u << 1  /* (device API) write pre-filtered f32 samples to tap buffer */
+};
+
+/* cfg_index[stream] selects cfgs[]; NULL = all streams use cfgs[0]. */
+int wam_fsk_batch_create(int device, long n_streams, const wam_fsk_config* cfgs, int n_cfgs,
+                         const int32_t* cfg_index, wam_fsk_batch** out);
+int wam_fsk_batch_destroy(wam_fsk_batch* b);
+int wam_fsk_batch_reset(wam_fsk_batch* b);                   /* reset() on every stream */
+/* bytes of output capacity per stream that n_samples of input can never exceed */
+long wam_fsk_batch_out_capacity(wam_fsk_batch* b, long n_samples);
+
+/* HOST buffers: samples float32 [n_streams][stream_stride] (n_samples used per stream),
+ * out uint8 [n_streams][out_stride], out_len int32 [n_streams].  Copies H2D/D2H inside,
+ * pipelined with the kernels.  Equivalent to demodulateData(samples[s]) on every stream. */
+int wam_fsk_batch_demodulate(wam_fsk_batch* b, float* samples, long stream_stride, long n_samples,
+                             uint8_t* out, long out_stride, int32_t* out_len, uint32_t flags);
+/* DEVICE buffers (same shapes), asynchronous on cuda_stream (a cudaStream_t, NULL = default).
+ * tap: optional device float32 [n_streams][stream_stride] for WAM_BATCH_TAP_PREFILTER. */
+int wam_fsk_batch_demodulate_device(wam_fsk_batch* b, float* d_samples, long stream_stride, long n_samples,
+                                    uint8_t* d_out, long out_stride, int32_t* d_out_len, float* d_tap,
+                                    void* cuda_stream, uint32_t flags);
+/* per-stream getStatus(); st: host array [n_streams] */
+int wam_fsk_batch_status(wam_fsk_batch* b, wam_fsk_status* st);
+/* kernels launched by this handle so far (bench.py's gpu_launches) */
+long wam_fsk_batch_launch_count(wam_fsk_batch* b);
+
+/* modulateData() for every stream: data uint8 [n_streams][data_stride], data_len[s] bytes each
+ * (NULL = nbytes for all).  out float32 [n_streams][out_stride]; out_len[s] samples written.
+ * HOST buffers. */
+int wam_fsk_batch_modulate(wam_fsk_batch* b, const uint8_t* data, long data_stride, const int32_t* data_len,
+                           long nbytes, float* out, long out_stride, int32_t* out_len);
+int wam_fsk_batch_modulate_device(wam_fsk_batch* b, const uint8_t* d_data, long data_stride,
+                                  const int32_t* d_data_len, long nbytes, float* d_out, long out_stride,
+                                  int32_t* d_out_len, void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------
+ * CRC-16 / XModem framed-block check (src/utils/crc16.ts, src/transports/xmodem/packet.ts,
+ * receive-side rules src/transports/xmodem/xmodem.ts:232-321)
+ * ------------------------------------------------------------------------------------- */
+typedef enum wam_pkt_status {
+  WAM_PKT_OK = 0,             /* in sequence, CRC good → ACK                      xmodem.ts:276-307 */
+  WAM_PKT_DUPLICATE = 1,      /* previous sequence → ACK, dropped                 xmodem.ts:309-314 */
+  WAM_PKT_NO_SOH = 2,         /* no SOH in the bytes                              xmodem.ts:236-252 */
+  WAM_PKT_EOT = 3,            /* EOT before any SOH                               xmodem.ts:242-245 */
+  WAM_PKT_INCOMPLETE = 4,     /* bytes end inside header/payload (would time out) */
+  WAM_PKT_BAD_COMPLEMENT = 5, /* 'Invalid sequence number'                        xmodem.ts:270-274 */
+  WAM_PKT_BAD_CRC = 6,        /* 'Invalid CRC'                                    xmodem.ts:286-290 */
+  WAM_PKT_UNEXPECTED_SEQ = 7  /* 'Unexpected sequence number'                     xmodem.ts:315-320 */
+} wam_pkt_status;
+
+typedef struct wam_pkt_result {
+  int32_t status;        /* wam_pkt_status */
+  int32_t sequence;      /* -1 if not reached */
+  int32_t length;
+  int32_t payloadOffset; /* index of payload[0] within the stream's bytes, -1 if n/a */
+  int32_t crcReceived;
+  int32_t crcComputed;
+  int32_t bytesConsumed;
+} wam_pkt_result;
+
+/* CRC16.calculate — crc16.ts:21-38 (host, scalar; for single packets) */
+uint16_t wam_crc16(const uint8_t* data, long n);
+/* XModemPacket.createData + serialize — packet.ts:21-54.  Returns bytes written or wam_error. */
+long wam_xmodem_serialize(int sequence, const uint8_t* payload, long n, uint8_t* out, long cap);
+/* One warp per stream: locate SOH, check seq/~seq, length, CRC-16 over the payload.
+ * HOST buffers: bytes [n_streams][stride], len[s]; expected_seq[s] (NULL = 1). */
+int wam_xmodem_batch_check(int device, const uint8_t* bytes, long stride, const int32_t* len,
+                           const int32_t* expected_seq, long n_streams, wam_pkt_result* results);
+int wam_xmodem_batch_check_device(const uint8_t* d_bytes, long stride, const int32_t* d_len,
+                                  const int32_t* d_expected_seq, long n_streams, wam_pkt_result* d_results,
+                                  void* cuda_stream);
+/* CRC-16 of n_blocks byte blocks on the GPU (warp per block). HOST buffers. */
+int wam_crc16_batch(int device, const uint8_t* bytes, long stride, const int32_t* len, long n_blocks,
+                    uint16_t* crc_out);
+
+/* ---------------------------------------------------------------------------------------
+ * filters.ts — designs (host math) and batched application (GPU)
+ * ------------------------------------------------------------------------------------- */
+void wam_design_butterworth_lowpass(double fc, double fs, double b[3], double a[3]);   /* filters.ts:180-192 */
+void wam_design_butterworth_highpass(double fc, double fs, double b[3], double a[3]);  /* filters.ts:200-212 */
+void wam_design_butterworth_bandpass(double f0, double bw, double fs, double b[3], double a[3]); /* :221-234 */
+int wam_design_sinc_lowpass(double fc, double fs, int numTaps, double* out);            /* :243-265 */
+int wam_design_sinc_highpass(double fc, double fs, int numTaps, double* out);           /* :274-286 */
+int wam_design_sinc_bandpass(double f0, double bw, double fs, int numTaps, double* out);/* :296-314 */
+
+/* IIRFilter.processBuffer for n_streams independent filter instances sharing (b, a)
+ * (filters.ts:47-87): in/out host float32 [n_streams][stride], n samples each.  state: host
+ * double [n_streams][nb + na - 1... ] see wam_iir_state_size(); NULL = fresh filters, state not
+ * returned.  Time-parallel (chunked linear-recurrence scan) for long streams. */
+long wam_iir_state_size(int nb, int na);
+int wam_iir_process_batch(int device, const double* b, int nb, const double* a, int na,
+                          const float* in, float* out, long stride, long n, long n_streams, double* state);
+/* FIRFilter.processBuffer (filters.ts:125-151): shared-memory-staged FIR.  state: host double
+ * [n_streams][ntaps-1] most-recent-first input history, NULL = fresh. */
+int wam_fir_process_batch(int device, const double* taps, int ntaps, const float* in, float* out,
+                          long stride, long n, long n_streams, double* state);
+
+/* pinned host memory helpers (so the HOST-buffer entry points can overlap copies) */
+int wam_host_alloc(void** p, size_t bytes);
+int wam_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAM_H */

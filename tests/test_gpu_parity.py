@@ -1,0 +1,218 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+Bar: decoded bytes, counters and CRC results bit-exact; samples within 1e-4 (BASELINE.json)."""
+import numpy as np
+import pytest
+
+import siggen
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # north-star tolerance for modulated / filtered samples (absolute and relative)
+
+
+def oracle_run(O, cfg, x, chunk=None):
+    m = O.FSKCore()
+    m.configure(cfg)
+    x = x.copy()
+    if chunk is None:
+        out = m.demodulateData(x)
+    else:
+        out = b"".join(m.demodulateData(x[i:i + chunk]) for i in range(0, len(x), chunk))
+    return out, m.getStatus(), x
+
+
+STATUS_KEYS = ["frameStarted", "globalSampleCounter", "receivedBitsLength", "syncDetections", "eodEvents",
+               "demodulationCalls", "totalSamplesProcessed"]
+
+
+def assert_status_equal(gs, os_, ctx=""):
+    for k in STATUS_KEYS:
+        assert float(gs[k]) == float(os_[k]), f"{ctx} status {k}: gpu {gs[k]} oracle {os_[k]}"
+    assert gs["silenceThreshold"] == pytest.approx(os_["silenceThreshold"], rel=1e-9, abs=1e-15), ctx
+
+
+@pytest.mark.parametrize("cfg,payload", [
+    ({}, b"AB"),
+    ({}, b"Hello, World!"),
+    (dict(baudRate=300), b"Hello"),
+    (siggen.BELL103, b"Hello, World!"),
+    (dict(baudRate=300, markFrequency=1270, spaceFrequency=1070), b"Hello, World!"),  # R9: decodes nothing
+    (siggen.V21_CH1, b"Hello, World!"),
+    (siggen.V21_CH2, b"Hello, World!"),
+    (dict(markFrequency=2125, spaceFrequency=2295), b"\x55\x7e\x48\x55\x7e"),
+    (dict(parity="even"), b"parity"),
+    (dict(parity="odd", stopBits=1), b"odd"),
+    (dict(sampleRate=44100), b"AB"),                      # fractional sync-ring capacity (R10)
+    (dict(sampleRate=44100, parity="even"), b"ABCD"),
+    (dict(agcEnabled=False), b"no agc"),
+    ({}, b""),
+])
+def test_single_stream_roundtrip(gpu_wam, oracle, cfg, payload):
+    sig = siggen.modulate(cfg, payload)
+    want, ost, omut = oracle_run(oracle, cfg, sig)
+    m = gpu_wam.FSKCore()
+    m.configure(cfg)
+    x = sig.copy()
+    got = bytes(m.demodulateData(x))
+    assert got == want
+    assert_status_equal(m.getStatus(), ost)
+    # AGC mutates the caller's buffer in place (fsk.ts:55): same float32 values
+    np.testing.assert_allclose(x, omut, rtol=TOL, atol=TOL)
+    assert np.mean(x != omut) < 1e-3
+
+
+def test_config1_polarity(gpu_wam, oracle):
+    """BASELINE config 1: 'Hello, World!' 48 kHz / 300 Bd.  Bell 103 as named (1270/1070) decodes
+    nothing in the reference; with the lower tone as mark it decodes exactly."""
+    for mark, space, want in ((1270, 1070, b""), (1070, 1270, b"Hello, World!")):
+        cfg = dict(baudRate=300, markFrequency=mark, spaceFrequency=space)
+        sig = siggen.modulate(cfg, b"Hello, World!")
+        assert len(sig) == 27520
+        m = gpu_wam.FSKCore()
+        m.configure(cfg)
+        assert bytes(m.demodulateData(sig.copy())) == want
+        assert oracle_run(oracle, cfg, sig)[0] == want
+
+
+@pytest.mark.parametrize("chunk", [32, 64, 128, 256, 1000])
+def test_chunked_equals_whole(gpu_wam, oracle, chunk):
+    sig = siggen.modulate({}, b"AB")
+    m = gpu_wam.FSKCore()
+    m.configure({})
+    got = b"".join(bytes(m.demodulateData(sig[i:i + chunk].copy())) for i in range(0, len(sig), chunk))
+    want, ost, _ = oracle_run(oracle, {}, sig, chunk)
+    assert got == want == b"AB"
+    assert_status_equal(m.getStatus(), ost)
+
+
+def test_three_messages_with_gaps(gpu_wam, oracle):
+    cfg = {}
+    parts = []
+    for p in (b"AB", b"Hel", b"lo"):
+        parts += [siggen.modulate(cfg, p), np.zeros(500, dtype=np.float32)]
+    sig = np.concatenate(parts)
+    m = gpu_wam.FSKCore()
+    m.configure(cfg)
+    events = []
+    m.on("eod", lambda e: events.append("eod"))
+    got = b"".join(bytes(m.demodulateData(sig[i:i + 128].copy())) for i in range(0, len(sig), 128))
+    want, ost, _ = oracle_run(oracle, cfg, sig, 128)
+    assert got == want == b"ABHello"
+    assert len(events) == ost["eodEvents"]
+    assert_status_equal(m.getStatus(), ost)
+
+
+def test_reset_and_reconfigure(gpu_wam, oracle):
+    sig = siggen.modulate({}, b"xyz")
+    g = gpu_wam.FSKCore()
+    o = oracle.FSKCore()
+    for core in (g, o):
+        core.configure({})
+    for step in range(3):
+        a = bytes(g.demodulateData(sig.copy()))
+        b = o.demodulateData(sig.copy())
+        assert a == b
+        assert_status_equal(g.getStatus(), o.getStatus(), f"step {step}")
+        if step == 0:
+            g.reset(); o.reset()
+        else:
+            g.configure(dict(syncThreshold=0.7)); o.configure(dict(syncThreshold=0.7))
+    assert not gpu_wam.FSKCore().isReady()
+    with pytest.raises(RuntimeError, match="not configured"):
+        gpu_wam.FSKCore().demodulateData(np.zeros(4, dtype=np.float32))
+    with pytest.raises(RuntimeError, match="not configured"):
+        gpu_wam.FSKCore().modulateData(b"x")
+
+
+@pytest.mark.parametrize("cfg", [siggen.V21_CH1, siggen.V21_CH2, {}])
+def test_batch_awgn_sweep_matches_oracle(gpu_wam, oracle, cfg):
+    """Miniature of BASELINE config 2: AWGN swept -15..+30 dB in 3 dB steps; bytes + counters exact."""
+    n_streams, n = 256, 48000 if cfg.get("baudRate") == 300 else 16000
+    snr = np.repeat(np.arange(-15, 31, 3), n_streams // 16)
+    x, _ = siggen.noisy_streams(cfg, n_streams, n, 25 if cfg.get("baudRate") == 300 else 30, snr, seed=0xB200)
+    want, ost = oracle.batch_demodulate([cfg], None, x.copy(), n_threads=8)
+    b = gpu_wam.FSKBatch(n_streams, cfg)
+    got = b.demodulate_bytes(x)
+    gst = b.status()
+    bad = [i for i in range(n_streams) if got[i] != want[i]]
+    assert not bad, f"{len(bad)} streams differ, first {bad[:5]}"
+    for i in range(n_streams):
+        assert_status_equal(gst[i], ost[i], f"stream {i}")
+    assert sum(len(w) for w in want) > 0
+
+
+def test_batch_two_configs_and_streaming_state(gpu_wam, oracle):
+    """V.21 ch1 + ch2 in one batch (config 2 layout), fed in 3 unequal slabs: the device-resident
+    state must carry across calls exactly like one FSKCore per stream."""
+    n_streams, n = 64, 48000
+    x1, _ = siggen.noisy_streams(siggen.V21_CH1, n_streams // 2, n, 25, 9.0, seed=1)
+    x2, _ = siggen.noisy_streams(siggen.V21_CH2, n_streams // 2, n, 25, 3.0, seed=2)
+    x = np.ascontiguousarray(np.concatenate([x1, x2]))
+    idx = np.array([0] * (n_streams // 2) + [1] * (n_streams // 2), dtype=np.int32)
+    want, ost = oracle.batch_demodulate([siggen.V21_CH1, siggen.V21_CH2], idx, x.copy(), n_threads=8)
+    b = gpu_wam.FSKBatch(n_streams, [siggen.V21_CH1, siggen.V21_CH2], idx)
+    got = [b""] * n_streams
+    for lo, hi in ((0, 10001), (10001, 30003), (30003, n)):
+        part = b.demodulate_bytes(np.ascontiguousarray(x[:, lo:hi]))
+        got = [g + p for g, p in zip(got, part)]
+    assert got == want
+    gst = b.status()
+    for i in range(n_streams):
+        for k in ["frameStarted", "globalSampleCounter", "syncDetections", "eodEvents"]:
+            assert float(gst[i][k]) == float(ost[i][k]), (i, k)
+
+
+def test_multi_frame_long_stream(gpu_wam, oracle):
+    """Config 3 style: 1200 Bd, back-to-back 128-byte frames with gaps, +6 dB AWGN."""
+    n_streams, n = 32, 48000 * 4
+    xs = [siggen.multi_frame_stream({}, n, 128, 6.0, seed=100 + s)[0] for s in range(n_streams)]
+    x = np.ascontiguousarray(np.stack(xs))
+    want, ost = oracle.batch_demodulate([{}], None, x.copy(), n_threads=8)
+    b = gpu_wam.FSKBatch(n_streams, {})
+    assert b.demodulate_bytes(x) == want
+    gst = b.status()
+    for i in range(n_streams):
+        for k in ["frameStarted", "globalSampleCounter", "syncDetections", "eodEvents"]:
+            assert float(gst[i][k]) == float(ost[i][k]), (i, k)
+
+
+def test_44k_fractional_ring_quirk(gpu_wam, oracle):
+    """Config 4 style at 44.1 kHz: default framing (capacity 1227.6: degenerate ring, first frame only)
+    and parity:'even' (capacity 1287.0), with a frequency offset.  GPU == oracle on both."""
+    for cfg in (dict(sampleRate=44100), dict(sampleRate=44100, parity="even")):
+        xs = [siggen.multi_frame_stream(cfg, 44100 * 2, 16, 20.0, seed=7 + s, freq_offset_hz=(-20 + 10 * s))[0]
+              for s in range(5)]
+        x = np.ascontiguousarray(np.stack(xs))
+        want, ost = oracle.batch_demodulate([cfg], None, x.copy(), n_threads=5)
+        b = gpu_wam.FSKBatch(5, cfg)
+        got = b.demodulate_bytes(x)
+        assert got == want, cfg
+        gst = b.status()
+        for i in range(5):
+            for k in ["frameStarted", "globalSampleCounter", "receivedBitsLength", "syncDetections", "eodEvents"]:
+                assert float(gst[i][k]) == float(ost[i][k]), (cfg, i, k)
+
+
+def test_modulate_matches_oracle(gpu_wam, oracle):
+    for cfg, payload in (({}, bytes(range(64))), (siggen.V21_CH1, b"Hello, World!"), (dict(parity="odd", stopBits=2), b"\x00\xff\x55"),
+                         (dict(sampleRate=44100, markFrequency=1633.5, spaceFrequency=1870.25), b"frac"), ({}, b"")):
+        want = siggen.modulate(cfg, payload)
+        m = gpu_wam.FSKCore()
+        m.configure(cfg)
+        got = m.modulateData(payload)
+        assert got.shape == want.shape
+        np.testing.assert_allclose(got, want, rtol=0, atol=TOL)
+        assert np.max(np.abs(got - want), initial=0) < 5e-6  # float32 sinpif on an exact phase
+
+
+def test_batch_modulate_then_demodulate(gpu_wam, oracle):
+    rng = np.random.default_rng(5)
+    data = rng.integers(0, 256, (40, 20), dtype=np.uint8)
+    b = gpu_wam.FSKBatch(40, {})
+    sig, out_len = b.modulate(data)
+    for s in range(40):
+        want = siggen.modulate({}, data[s].tobytes())
+        assert out_len[s] == len(want)
+        np.testing.assert_allclose(sig[s], want, rtol=0, atol=TOL)
+    got = b.demodulate_bytes(sig)
+    assert got == [data[s].tobytes() for s in range(40)]

@@ -1,0 +1,504 @@
+// fsk_demod.cuh — fused FSK demodulator, exact (float64) path.
+//
+// Restates FSKCore.demodulateData (src/modems/fsk.ts:190-222) for thousands of independent
+// streams: one thread walks one stream in time and carries the whole reference state
+// (AGC gain, four biquads, LO phase, decimator, both rings, bit-sync / byte / silence state) in
+// registers; a warp owns 32 streams.  Samples are [stream][time] float32 in HBM; each warp stages
+// 32-stream x 32-sample tiles (one 128-byte line per stream) into shared memory with a
+// 3-deep cp.async pipeline, XOR-swizzled so that the row-per-lane LDS.128 reads are
+// bank-conflict free.  Arithmetic follows the reference's float64 pipeline with float32 only at
+// its Float32Array stores (fsk.ts:55, filters.ts:82-85, amplitude ring fsk.ts:150,282).
+//
+// Stages inside the fused loop, with the reference lines they follow:
+//   AGC               fsk.ts:52-76      (non-linear recurrence, f64 gain, f32 store)
+//   pre-filter        filters.ts:47-87  (band-pass biquad DF-I, f32 output)
+//   LO mix            fsk.ts:228-232    (phase accumulates exactly like the reference; cos/sin
+//                                        re-anchored with sincos() every tile and advanced by a
+//                                        rotation in between)
+//   I/Q low-pass      filters.ts:47-76
+//   /2 decimation, atan2, amplitude, wrapped phase difference, post low-pass, slicer fsk.ts:241-264
+//   rings, silence/EOD, sync search, majority-vote bit sampler, UART framing  fsk.ts:278-375
+#pragma once
+
+#include "wam_common.cuh"
+
+namespace wam {
+
+struct LaneState {
+  double gain, px1, px2, py1, py2;
+  double lo_phase, lo_c, lo_s;
+  double ix1, ix2, iy1, iy2, qx1, qx2, qy1, qy2;
+  double ox1, ox2, oy1, oy2, last_phase, iacc, qacc, sil_thr;
+  double ring_wi, ring_ri, ring_flen;  // fractional-capacity ring emulation only
+  uint32_t dsc, gsc, gmod, bsc, next_idx, bit_acc, bit_cnt, started, current, sil_cnt;
+  int bitpos;
+  uint32_t ring_pos, ring_len, amp_pos, amp_len, sync_det, eod_ev, err;
+  uint32_t cur_word;
+  int out_n;
+};
+
+__device__ __forceinline__ void lane_load(LaneState& s, const DemodArgs& a, int li) {
+  const double* f = a.f64 + li;
+  const uint32_t* u = a.u32 + li;
+  const long n = a.n_local;
+  s.gain = f[F_GAIN * n]; s.px1 = f[F_PX1 * n]; s.px2 = f[F_PX2 * n]; s.py1 = f[F_PY1 * n]; s.py2 = f[F_PY2 * n];
+  s.lo_phase = f[F_LO_PHASE * n];
+  s.ix1 = f[F_IX1 * n]; s.ix2 = f[F_IX2 * n]; s.iy1 = f[F_IY1 * n]; s.iy2 = f[F_IY2 * n];
+  s.qx1 = f[F_QX1 * n]; s.qx2 = f[F_QX2 * n]; s.qy1 = f[F_QY1 * n]; s.qy2 = f[F_QY2 * n];
+  s.ox1 = f[F_OX1 * n]; s.ox2 = f[F_OX2 * n]; s.oy1 = f[F_OY1 * n]; s.oy2 = f[F_OY2 * n];
+  s.last_phase = f[F_LAST_PHASE * n]; s.iacc = f[F_IACC * n]; s.qacc = f[F_QACC * n]; s.sil_thr = f[F_SIL_THR * n];
+  s.ring_wi = f[F_RING_WI * n]; s.ring_ri = f[F_RING_RI * n]; s.ring_flen = f[F_RING_LEN * n];
+  s.dsc = u[U_DSC * n]; s.gsc = u[U_GSC * n]; s.gmod = u[U_GMOD * n]; s.bsc = u[U_BSC * n];
+  s.next_idx = u[U_NEXT_IDX * n]; s.bit_acc = u[U_BIT_ACC * n]; s.bit_cnt = u[U_BIT_CNT * n];
+  s.started = u[U_STARTED * n]; s.bitpos = (int)u[U_BITPOS * n]; s.current = u[U_CURRENT * n];
+  s.sil_cnt = u[U_SIL_CNT * n]; s.ring_pos = u[U_RING_POS * n]; s.ring_len = u[U_RING_LEN * n];
+  s.amp_pos = u[U_AMP_POS * n]; s.amp_len = u[U_AMP_LEN * n]; s.sync_det = u[U_SYNC_DET * n];
+  s.eod_ev = u[U_EOD_EV * n]; s.err = u[U_ERR * n];
+  s.out_n = 0;
+}
+
+__device__ __forceinline__ void lane_store(const LaneState& s, const DemodArgs& a, int li) {
+  double* f = a.f64 + li;
+  uint32_t* u = a.u32 + li;
+  const long n = a.n_local;
+  f[F_GAIN * n] = s.gain; f[F_PX1 * n] = s.px1; f[F_PX2 * n] = s.px2; f[F_PY1 * n] = s.py1; f[F_PY2 * n] = s.py2;
+  f[F_LO_PHASE * n] = s.lo_phase;
+  f[F_IX1 * n] = s.ix1; f[F_IX2 * n] = s.ix2; f[F_IY1 * n] = s.iy1; f[F_IY2 * n] = s.iy2;
+  f[F_QX1 * n] = s.qx1; f[F_QX2 * n] = s.qx2; f[F_QY1 * n] = s.qy1; f[F_QY2 * n] = s.qy2;
+  f[F_OX1 * n] = s.ox1; f[F_OX2 * n] = s.ox2; f[F_OY1 * n] = s.oy1; f[F_OY2 * n] = s.oy2;
+  f[F_LAST_PHASE * n] = s.last_phase; f[F_IACC * n] = s.iacc; f[F_QACC * n] = s.qacc; f[F_SIL_THR * n] = s.sil_thr;
+  f[F_RING_WI * n] = s.ring_wi; f[F_RING_RI * n] = s.ring_ri; f[F_RING_LEN * n] = s.ring_flen;
+  u[U_DSC * n] = s.dsc; u[U_GSC * n] = s.gsc; u[U_GMOD * n] = s.gmod; u[U_BSC * n] = s.bsc;
+  u[U_NEXT_IDX * n] = s.next_idx; u[U_BIT_ACC * n] = s.bit_acc; u[U_BIT_CNT * n] = s.bit_cnt;
+  u[U_STARTED * n] = s.started; u[U_BITPOS * n] = (uint32_t)s.bitpos; u[U_CURRENT * n] = s.current;
+  u[U_SIL_CNT * n] = s.sil_cnt; u[U_RING_POS * n] = s.ring_pos; u[U_RING_LEN * n] = s.ring_len;
+  u[U_AMP_POS * n] = s.amp_pos; u[U_AMP_LEN * n] = s.amp_len; u[U_SYNC_DET * n] = s.sync_det;
+  u[U_EOD_EV * n] = s.eod_ev; u[U_ERR * n] = s.err;
+}
+
+// FSKCore.resetState — fsk.ts:175-188.  Not reset: AGC, pre-filter, rings, silence threshold.
+__device__ __forceinline__ void reset_state(LaneState& s) {
+  s.lo_phase = 0.0; s.lo_c = 1.0; s.lo_s = 0.0; s.last_phase = 0.0;
+  s.gsc = 0; s.gmod = 0; s.bsc = 0; s.bit_acc = 0; s.bit_cnt = 0; s.next_idx = 0;
+  s.current = 0; s.bitpos = 0;
+  s.started = 0;
+  s.sil_cnt = 0;
+  s.ix1 = s.ix2 = s.iy1 = s.iy2 = 0.0;
+  s.qx1 = s.qx2 = s.qy1 = s.qy2 = 0.0;
+  s.ox1 = s.ox2 = s.oy1 = s.oy2 = 0.0;
+  s.dsc = 0; s.iacc = 0.0; s.qacc = 0.0;
+}
+
+// ones in the circular bit range [lo, lo+len) of a power-of-two ring of `words` 32-bit words
+__device__ __forceinline__ int ring_popc_range(const uint32_t* __restrict__ ring, long ns, uint32_t lo, int len,
+                                               int words) {
+  uint32_t w = (lo >> 5) & (uint32_t)(words - 1);
+  uint32_t o = lo & 31u;
+  int total = 0;
+  while (len > 0) {
+    int take = min(32 - (int)o, len);
+    uint32_t mask = (take == 32) ? 0xffffffffu : (((1u << take) - 1u) << o);
+    total += __popc(ring[(long)w * ns] & mask);
+    len -= take;
+    o = 0;
+    w = (w + 1) & (uint32_t)(words - 1);
+  }
+  return total;
+}
+
+// Frame-sync template match, integral-capacity ring — fsk.ts:303-312.
+// matched counts ring samples equal to preambleSfdBits[nbits - j] for window j (j*dspb .. (j+1)*dspb-1
+// samples back from the newest); j == 0 compares against `undefined` and never matches.
+__device__ __noinline__ int sync_matched_integral(const uint32_t* __restrict__ ring, long ns, uint32_t pos,
+                                                  const FskDerived& d) {
+  int matched = 0;
+  int remaining = (d.nbits - 1) * d.dspb;
+  for (int j = 1; j < d.nbits; ++j) {
+    const int pb = d.nbits - j;
+    const int expect = (d.pattern[pb >> 5] >> (pb & 31)) & 1;
+    const uint32_t lo = pos - (uint32_t)((j + 1) * d.dspb);
+    const int ones = ring_popc_range(ring, ns, lo, d.dspb, d.ring_words);
+    matched += expect ? ones : d.dspb - ones;
+    remaining -= d.dspb;
+    if (matched + remaining < d.min_matched) break;  // cannot reach the threshold any more
+  }
+  return matched;
+}
+
+// ---- literal emulation of RingBuffer with a fractional capacity (utils.ts:14-47) ----
+__device__ __forceinline__ double ring_fmod_cap(double x, double cap) {  // x in [0, 3*cap)
+  const double cap2 = cap + cap;
+  if (x >= cap2) return x - cap2;  // exact (Sterbenz)
+  if (x >= cap) return x - cap;    // exact
+  return x;
+}
+__device__ __forceinline__ bool ring_index_valid(double p, int buflen, int& ip) {
+  ip = (int)p;
+  return ((double)ip == p) && ip >= 0 && ip < buflen;
+}
+__device__ __forceinline__ void ring_put_fractional(LaneState& s, uint32_t* ring, long ns, int bit,
+                                                    const FskDerived& d) {
+  int ip;
+  if (ring_index_valid(s.ring_wi, d.ring_cap_int, ip)) {
+    uint32_t* w = ring + (long)(ip >> 5) * ns;
+    *w = (*w & ~(1u << (ip & 31))) | ((uint32_t)bit << (ip & 31));
+  }
+  s.ring_wi = ring_fmod_cap(s.ring_wi + 1.0, d.ring_cap);
+  if (s.ring_flen < d.ring_cap) s.ring_flen += 1.0;
+  else s.ring_ri = ring_fmod_cap(s.ring_ri + 1.0, d.ring_cap);
+}
+__device__ __noinline__ int sync_matched_fractional(const LaneState& s, const uint32_t* __restrict__ ring, long ns,
+                                                    const FskDerived& d) {
+  int matched = 0;
+  int remaining = d.nbits * d.dspb;
+  for (int j = 0; j < d.nbits; ++j) {
+    const int pb = d.nbits - j;
+    const int expect = (j == 0) ? 0 : (d.pattern[pb >> 5] >> (pb & 31)) & 1;
+    for (int k = 0; k < d.dspb; ++k) {
+      const double idx = s.ring_flen - (double)(j * d.dspb + k) - 1.0;
+      const double p = ring_fmod_cap(s.ring_ri + idx, d.ring_cap);
+      int ip;
+      const bool valid = ring_index_valid(p, d.ring_cap_int, ip);
+      if (j == 0) {
+        matched += valid ? 0 : 1;  // undefined === undefined (fsk.ts:306-307)
+      } else if (valid) {
+        const int bit = (ring[(long)(ip >> 5) * ns] >> (ip & 31)) & 1;
+        matched += (bit == expect);
+      }
+    }
+    remaining -= d.dspb;
+    if (matched + remaining < d.min_matched) break;
+  }
+  return matched;
+}
+
+// FSKCore.processByte — fsk.ts:346-375
+__device__ __forceinline__ void process_byte(LaneState& s, int bit, const FskDerived& d, uint8_t* out_row,
+                                             long out_cap) {
+  const int bp = s.bitpos;
+  if (bp == 0) {
+    if (bit != 0) { reset_state(s); return; }
+  } else if (bp >= 1 && bp <= 8) {
+    s.current |= (uint32_t)bit << (8 - bp);
+  } else if (d.parity != 0 && bp == 9) {
+    // parity bit is skipped, never checked
+  } else if (bp == d.stop_pos) {
+    if (bit != 1) { s.started = 0; return; }
+    if (s.out_n < out_cap) out_row[s.out_n] = (uint8_t)s.current;
+    else s.err |= WAM_ERR_OUT_OVERFLOW;
+    s.out_n++;
+    s.current = 0;
+    s.bitpos = -1;
+  } else {
+    s.started = 0;
+    return;
+  }
+  s.bitpos++;
+}
+
+// FSKCore.processDownsampledBit — fsk.ts:278-344
+__device__ __forceinline__ void process_downsampled_bit(LaneState& s, int bit, double amplitude, const DemodArgs& a,
+                                                        int li, uint8_t* out_row) {
+  const FskDerived& d = a.d;
+  const long ns = a.n_local;
+  uint32_t* ring = a.sync_ring + li;
+  float* aring = a.amp_ring + li;
+
+  // syncSamplesBuffer.put(bit) — fsk.ts:281
+  if (!d.ring_fractional) {
+    s.cur_word |= (uint32_t)bit << (s.ring_pos & 31u);
+    s.ring_pos++;
+    if ((s.ring_pos & 31u) == 0u) {
+      ring[(long)(((s.ring_pos - 1u) >> 5) & (uint32_t)(d.ring_words - 1)) * ns] = s.cur_word;
+      s.cur_word = 0u;
+    }
+    if (s.ring_len < (uint32_t)d.ring_cap_int) s.ring_len++;
+  } else {
+    ring_put_fractional(s, ring, ns, bit, d);
+  }
+  // syncAmplitudeBuffer.put(amplitude) — fsk.ts:282 (Float32Array store)
+  aring[(long)s.amp_pos * ns] = (float)amplitude;
+  s.amp_pos = (s.amp_pos + 1u == (uint32_t)d.amp_cap) ? 0u : s.amp_pos + 1u;
+  if (s.amp_len < (uint32_t)d.amp_cap) s.amp_len++;
+
+  // silence / EOD — fsk.ts:285-295
+  s.gsc++;
+  s.gmod = (s.gmod + 1u == (uint32_t)d.check_period) ? 0u : s.gmod + 1u;
+  if (amplitude < s.sil_thr) {
+    s.sil_cnt++;
+    if (s.sil_cnt >= (uint32_t)d.eod_count) {
+      s.eod_ev++;
+      reset_state(s);
+      return;
+    }
+  } else {
+    s.sil_cnt = 0;
+  }
+
+  if (!s.started) {
+    // fsk.ts:297-328
+    const bool due = d.check_period > 0 && s.gmod == 0u;
+    const bool enough = d.ring_fractional ? (s.ring_flen >= (double)d.total_bits) : (s.ring_len >= (uint32_t)d.total_bits);
+    if (due && enough && d.total_bits > 0) {
+      int matched;
+      if (!d.ring_fractional) {
+        if ((s.ring_pos & 31u) != 0u)
+          ring[(long)((s.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns] = s.cur_word;  // flush partial word
+        matched = sync_matched_integral(ring, ns, s.ring_pos, d);
+      } else {
+        matched = sync_matched_fractional(s, ring, ns, d);
+      }
+      if (matched >= d.min_matched) {
+        s.started = 1;
+        s.current = 0; s.bitpos = 0;
+        s.bit_acc = 0; s.bit_cnt = 0; s.bsc = 0; s.next_idx = 0;
+        s.sync_det++;
+        // silence threshold = mean(amplitude ring) * 0.1, summed oldest -> newest — fsk.ts:321-326
+        double sum = 0.0;
+        uint32_t slot = (s.amp_pos + (uint32_t)d.amp_cap - s.amp_len) % (uint32_t)d.amp_cap;
+        for (uint32_t i = 0; i < s.amp_len; ++i) {
+          sum += (double)aring[(long)slot * ns];
+          slot = (slot + 1u == (uint32_t)d.amp_cap) ? 0u : slot + 1u;
+        }
+        s.sil_thr = (sum / (double)s.amp_len) * 0.1;
+      }
+    }
+  } else {
+    // fsk.ts:330-341
+    s.bit_acc += (uint32_t)bit;
+    s.bit_cnt++;
+    s.bsc++;
+    if (s.bsc >= s.next_idx) {
+      const int decided = (2u * s.bit_acc > s.bit_cnt) ? 1 : 0;  // acc > count/2
+      s.bit_acc = 0; s.bit_cnt = 0;
+      s.next_idx += (uint32_t)d.dspb;
+      process_byte(s, decided, d, out_row, a.out_stride);
+    }
+  }
+}
+
+// One input sample through AGC, pre-filter, LO mix, I/Q filters, decimator (+ everything at the
+// decimated rate every second sample).  Returns the AGC-scaled sample (for write-back).
+template <bool TAP>
+__device__ __forceinline__ float process_sample(LaneState& s, float x, const DemodArgs& a, int li, uint8_t* out_row,
+                                                float* tap_ptr) {
+  const FskDerived& d = a.d;
+  const double kTwoPi = 6.283185307179586;  // 2 * Math.PI
+  const double kPi = 3.141592653589793;
+
+  // ---- AGC — fsk.ts:52-76
+  float sg = x;
+  if (d.agc_enabled) {
+    sg = (float)((double)x * s.gain);
+    const double level = fabs((double)sg);
+    if (level > 0.5) {
+      const double target = 0.5 / level;
+      s.gain += (target - s.gain) * d.agc_attack;
+    } else if (level > 0.0) {
+      const double target = 0.5 / level;
+      s.gain += (target - s.gain) * d.agc_release;
+    }
+    s.gain = fmax(0.1, fmin(10.0, s.gain));
+  }
+
+  // ---- pre-filter (DF-I, accumulation order of filters.ts:52-66), Float32Array output
+  const double xin = (double)sg;
+  double y = d.pre_b0 * xin;
+  y += d.pre_b1 * s.px1;
+  y += d.pre_b2 * s.px2;
+  y -= d.pre_a1 * s.py1;
+  y -= d.pre_a2 * s.py2;
+  s.px2 = s.px1; s.px1 = xin; s.py2 = s.py1; s.py1 = y;
+  const float pf = (float)y;
+  if (TAP) *tap_ptr = pf;
+
+  // ---- LO mix — fsk.ts:228-232
+  const double smp = (double)pf;
+  const double xi = smp * s.lo_c;
+  const double xq = smp * s.lo_s;
+  double ph = s.lo_phase + d.omega;
+  if (ph >= kTwoPi) ph -= kTwoPi;  // (phase + omega) % 2pi, exact for 0 <= omega < 2pi
+  s.lo_phase = ph;
+  const double nc = s.lo_c * d.cos_omega - s.lo_s * d.sin_omega;
+  const double nsn = s.lo_s * d.cos_omega + s.lo_c * d.sin_omega;
+  s.lo_c = nc; s.lo_s = nsn;
+
+  // ---- I/Q low-pass biquads
+  double yi = d.lp_b0 * xi;
+  yi += d.lp_b1 * s.ix1;
+  yi += d.lp_b2 * s.ix2;
+  yi -= d.lp_a1 * s.iy1;
+  yi -= d.lp_a2 * s.iy2;
+  s.ix2 = s.ix1; s.ix1 = xi; s.iy2 = s.iy1; s.iy1 = yi;
+  double yq = d.lp_b0 * xq;
+  yq += d.lp_b1 * s.qx1;
+  yq += d.lp_b2 * s.qx2;
+  yq -= d.lp_a1 * s.qy1;
+  yq -= d.lp_a2 * s.qy2;
+  s.qx2 = s.qx1; s.qx1 = xq; s.qy2 = s.qy1; s.qy1 = yq;
+
+  // ---- /2 boxcar decimation — fsk.ts:241-245
+  s.iacc += yi;
+  s.qacc += yq;
+  s.dsc++;
+  if (s.dsc >= 2u) {
+    const double avg_i = s.iacc * 0.5;
+    const double avg_q = s.qacc * 0.5;
+    const double phase = atan2(avg_q, avg_i);
+    const double amplitude = sqrt(avg_i * avg_i + avg_q * avg_q);
+    double pd = phase - s.last_phase;
+    if (pd > kPi) pd -= kTwoPi;
+    else if (pd < -kPi) pd += kTwoPi;
+    s.last_phase = phase;
+    double yo = d.lp_b0 * pd;
+    yo += d.lp_b1 * s.ox1;
+    yo += d.lp_b2 * s.ox2;
+    yo -= d.lp_a1 * s.oy1;
+    yo -= d.lp_a2 * s.oy2;
+    s.ox2 = s.ox1; s.ox1 = pd; s.oy2 = s.oy1; s.oy1 = yo;
+    const int bit = yo > 0.0 ? 1 : 0;
+    s.iacc = 0.0; s.qacc = 0.0; s.dsc = 0;
+    process_downsampled_bit(s, bit, amplitude, a, li, out_row);
+  }
+  return sg;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, int src_bytes) {
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// float index of (row, col) inside one swizzled 32x32 tile: 16-byte chunk index XOR (row & 7)
+__device__ __forceinline__ int tile_index(int row, int col) {
+  return row * kTile + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3));
+}
+
+// Stage one 32-stream x 32-sample tile starting at sample t0 into `tile`.
+template <bool ALIGNED>
+__device__ __forceinline__ void stage_tile(float* tile, const DemodArgs& a, const long* row_of_lane_smem, long t0,
+                                           int lane) {
+  if (ALIGNED) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + (lane >> 3);
+      const int c = (lane & 7) * 4;
+      const long row = row_of_lane_smem[r];
+      long remain = a.n - (t0 + c);
+      int bytes = row < 0 ? 0 : (remain >= 4 ? 16 : (remain > 0 ? (int)remain * 4 : 0));
+      const float* src = a.samples + (row < 0 ? 0 : row * a.stride + t0 + (bytes ? c : 0));
+      if (row < 0 || bytes == 0) src = a.samples;
+      cp_async16(tile + tile_index(r, c), src, bytes);
+    }
+  } else {
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      const long row = row_of_lane_smem[r];
+      const int bytes = (row >= 0 && t0 + lane < a.n) ? 4 : 0;
+      const float* src = bytes ? a.samples + row * a.stride + t0 + lane : a.samples;
+      cp_async4(tile + tile_index(r, lane), src, bytes);
+    }
+  }
+}
+
+// Grid: one warp (32 streams) per CTA, so that 2048 warps spread evenly over 148 SMs.
+template <bool ALIGNED, bool WRITEBACK, bool TAP>
+__global__ void __launch_bounds__(32) fsk_demod_exact_kernel(const __grid_constant__ DemodArgs a) {
+  __shared__ __align__(128) float tiles[kStages][kTile * kTile];
+  __shared__ long rows[32];
+
+  const int lane = threadIdx.x;
+  const int li = a.l_begin + blockIdx.x * 32 + lane;
+  const bool active = li < a.l_end;
+  long row = -1;
+  if (active) row = (long)(a.ids ? a.ids[li] : a.id0 + li) - a.row_base;
+  rows[lane] = row;
+  __syncwarp();
+
+  LaneState s;
+  if (active) {
+    lane_load(s, a, li);
+    // (cos, sin) of the carried LO phase; exact (1, 0) after a reset
+    sincos(s.lo_phase, &s.lo_s, &s.lo_c);
+    if (s.lo_phase == 0.0) { s.lo_c = 1.0; s.lo_s = 0.0; }
+    s.cur_word = 0u;
+    if (!a.d.ring_fractional && (s.ring_pos & 31u) != 0u) {
+      const uint32_t w = a.sync_ring[(long)((s.ring_pos >> 5) & (uint32_t)(a.d.ring_words - 1)) * a.n_local + li];
+      s.cur_word = w & ((1u << (s.ring_pos & 31u)) - 1u);
+    }
+  }
+  uint8_t* out_row = active ? a.out + row * a.out_stride : nullptr;
+  float* tap_row = (TAP && active) ? a.tap + row * a.stride : nullptr;
+
+  const long n_tiles = (a.n + kTile - 1) / kTile;
+  // prologue
+  for (int p = 0; p < kStages - 1; ++p) {
+    if (p < n_tiles) stage_tile<ALIGNED>(tiles[p], a, rows, (long)p * kTile, lane);
+    cp_async_commit();
+  }
+  for (long t = 0; t < n_tiles; ++t) {
+    const long tn = t + kStages - 1;
+    if (tn < n_tiles) stage_tile<ALIGNED>(tiles[tn % kStages], a, rows, tn * kTile, lane);
+    cp_async_commit();
+    cp_async_wait<kStages - 1>();
+    __syncwarp();
+    float* tile = tiles[t % kStages];
+    const long t0 = t * kTile;
+    if (active) {
+      // re-anchor the LO rotation on the exactly-accumulated phase once per tile
+      if (t != 0) sincos(s.lo_phase, &s.lo_s, &s.lo_c);
+      const bool full = (t0 + kTile <= a.n);
+#pragma unroll 1
+      for (int ch = 0; ch < 8; ++ch) {
+        float4* p4 = reinterpret_cast<float4*>(tile + tile_index(lane, ch * 4));
+        float4 v = *p4;
+        float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const long tt = t0 + ch * 4 + k;
+          if (full || tt < a.n) xs[k] = process_sample<TAP>(s, xs[k], a, li, out_row, TAP ? tap_row + tt : nullptr);
+        }
+        if (WRITEBACK) *p4 = make_float4(xs[0], xs[1], xs[2], xs[3]);
+      }
+    }
+    __syncwarp();
+    if (WRITEBACK) {
+      // cooperative, coalesced copy of the AGC-scaled tile back to the caller's buffer (fsk.ts:55)
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3);
+        const int c = (lane & 7) * 4;
+        const long rr = rows[r];
+        if (rr < 0) continue;
+        const float4 v = *reinterpret_cast<const float4*>(tile + tile_index(r, c));
+        float* dst = a.samples + rr * a.stride + t0 + c;
+        const long remain = a.n - (t0 + c);
+        if (ALIGNED && remain >= 4) {
+          *reinterpret_cast<float4*>(dst) = v;
+        } else {
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+          for (int k = 0; k < 4; ++k)
+            if (k < remain) dst[k] = vv[k];
+        }
+      }
+      __syncwarp();
+    }
+  }
+  cp_async_wait<0>();
+
+  if (active) {
+    if (!a.d.ring_fractional && (s.ring_pos & 31u) != 0u)
+      a.sync_ring[(long)((s.ring_pos >> 5) & (uint32_t)(a.d.ring_words - 1)) * a.n_local + li] = s.cur_word;
+    lane_store(s, a, li);
+    a.out_len[row] = s.out_n < a.out_stride ? s.out_n : (int)a.out_stride;
+  }
+}
+
+}  // namespace wam

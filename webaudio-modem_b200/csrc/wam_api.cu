@@ -1,0 +1,1000 @@
+// wam_api.cu — C ABI of libwam.so (see include/wam.h).  Host logic + kernel launches.
+// There is no CPU fallback in this file: every compute entry point launches sm_100a kernels.
+#include "../../include/wam.h"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "crc_xmodem.cuh"
+#include "filters.cuh"
+#include "fsk_demod.cuh"
+#include "fsk_mod.cuh"
+#include "wam_common.cuh"
+
+using namespace wam;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      return fail(WAM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                      \
+  } while (0)
+
+extern "C" int wam_version(void) { return WAM_VERSION; }
+extern "C" const char* wam_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* wam_error_string(int code) {
+  switch (code) {
+    case WAM_OK: return "ok";
+    case WAM_E_INVALID: return "invalid argument";
+    case WAM_E_NOT_CONFIGURED: return "not configured";
+    case WAM_E_CUDA: return "CUDA error";
+    case WAM_E_NOMEM: return "out of memory";
+    case WAM_E_CAPACITY: return "output buffer too small";
+    case WAM_E_UNSUPPORTED: return "unsupported configuration";
+    case WAM_E_FILTER_B_EMPTY: return "Feedforward coefficients (b) cannot be empty";
+    case WAM_E_FILTER_A_EMPTY: return "Feedback coefficients (a) cannot be empty";
+    case WAM_E_FILTER_A0_ZERO: return "First feedback coefficient (a[0]) cannot be zero";
+    case WAM_E_PKT_SEQUENCE: return "Invalid sequence. Must be 1-255.";
+    case WAM_E_PKT_PAYLOAD: return "Payload too large. Max 255 bytes.";
+    default: return "unknown error";
+  }
+}
+extern "C" int wam_device_count(int* count) {
+  if (!count) return fail(WAM_E_INVALID, "count is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(WAM_E_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  *count = n;
+  return WAM_OK;
+}
+
+extern "C" void wam_fsk_default_config(wam_fsk_config* c) {  // fsk.ts:19-33
+  static const uint8_t pre[2] = {0x55, 0x55};
+  static const uint8_t sfd[1] = {0x7E};
+  memset(c, 0, sizeof(*c));
+  c->sampleRate = 48000; c->baudRate = 1200;
+  c->markFrequency = 1650; c->spaceFrequency = 1850;
+  c->preamblePattern = pre; c->preambleLength = 2;
+  c->sfdPattern = sfd; c->sfdLength = 1;
+  c->startBits = 1; c->stopBits = 1; c->parity = 0;
+  c->syncThreshold = 0.85; c->agcEnabled = 1;
+  c->preFilterBandwidth = 800; c->adaptiveThreshold = 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// filters.ts designs (host, float64, the reference's operation order)
+// ------------------------------------------------------------------------------------------
+extern "C" void wam_design_butterworth_lowpass(double fc, double fs, double b[3], double a[3]) {
+  const double nyquist = fs / 2;
+  const double nc = fc / nyquist;
+  const double c = tan(M_PI * nc / 2);
+  const double c2 = c * c;
+  const double s2c = M_SQRT2 * c;
+  const double den = 1 + s2c + c2;
+  b[0] = c2 / den; b[1] = 2 * c2 / den; b[2] = c2 / den;
+  a[0] = 1; a[1] = (2 * c2 - 2) / den; a[2] = (1 - s2c + c2) / den;
+}
+extern "C" void wam_design_butterworth_highpass(double fc, double fs, double b[3], double a[3]) {
+  const double nyquist = fs / 2;
+  const double nc = fc / nyquist;
+  const double c = tan(M_PI * nc / 2);
+  const double c2 = c * c;
+  const double s2c = M_SQRT2 * c;
+  const double den = 1 + s2c + c2;
+  b[0] = 1 / den; b[1] = -2 / den; b[2] = 1 / den;
+  a[0] = 1; a[1] = (2 * c2 - 2) / den; a[2] = (1 - s2c + c2) / den;
+}
+extern "C" void wam_design_butterworth_bandpass(double f0, double bandwidth, double fs, double b[3], double a[3]) {
+  const double omega = 2 * M_PI * f0 / fs;
+  const double bw = 2 * M_PI * bandwidth / fs;
+  const double c = tan(bw / 2);
+  const double dd = 2 * cos(omega);
+  const double c2 = c * c;
+  const double den = 1 + c + c2;
+  b[0] = c / den; b[1] = 0; b[2] = -c / den;
+  a[0] = 1; a[1] = (-dd * (1 + c2)) / den; a[2] = (1 - c + c2) / den;
+}
+extern "C" int wam_design_sinc_lowpass(double fc, double fs, int numTaps, double* out) {
+  if (numTaps % 2 == 0) numTaps++;  // filters.ts:244-246
+  const double nc = fc / fs;
+  const double center = (numTaps - 1) / 2.0;
+  for (int i = 0; i < numTaps; i++) {
+    if ((double)i == center) {
+      out[i] = 2 * nc;
+    } else {
+      const double x = M_PI * (i - center);
+      out[i] = sin(2 * nc * x) / x;
+    }
+    out[i] *= 0.54 - 0.46 * cos(2 * M_PI * i / (numTaps - 1));
+  }
+  return numTaps;
+}
+extern "C" int wam_design_sinc_highpass(double fc, double fs, int numTaps, double* out) {
+  // filters.ts:274-286.  With an even numTaps the low-pass has numTaps+1 entries, only the first
+  // numTaps are negated and `lowpass[center] += 1` addresses a fractional index (no element).
+  const int n = wam_design_sinc_lowpass(fc, fs, numTaps, out);
+  const double center = (numTaps - 1) / 2.0;
+  for (int i = 0; i < numTaps; i++) out[i] = -out[i];
+  if (center == floor(center) && center >= 0 && center < n) out[(int)center] += 1;
+  return n;
+}
+extern "C" int wam_design_sinc_bandpass(double f0, double bandwidth, double fs, int numTaps, double* out) {
+  // filters.ts:296-314: truncated convolution of the high-pass and low-pass prototypes
+  const double lo = f0 - bandwidth / 2;
+  const double hi = f0 + bandwidth / 2;
+  std::vector<double> hp((size_t)numTaps + 2), lp((size_t)numTaps + 2);
+  wam_design_sinc_highpass(lo, fs, numTaps, hp.data());
+  wam_design_sinc_lowpass(hi, fs, numTaps, lp.data());
+  for (int i = 0; i < numTaps; i++) out[i] = 0;
+  for (int i = 0; i < numTaps; i++)
+    for (int j = 0; j < numTaps; j++)
+      if (i + j < numTaps) out[i + j] += hp[i] * lp[j];
+  return numTaps;
+}
+
+// ------------------------------------------------------------------------------------------
+// FSKCore.configure(): derived parameters (fsk.ts:133-173, :426-462)
+// ------------------------------------------------------------------------------------------
+static int derive(const wam_fsk_config& c, FskDerived& d) {
+  memset(&d, 0, sizeof(d));
+  if (!(c.sampleRate > 0) || !(c.baudRate > 0) || !std::isfinite(c.sampleRate) || !std::isfinite(c.baudRate) ||
+      !std::isfinite(c.markFrequency) || !std::isfinite(c.spaceFrequency))
+    return fail(WAM_E_UNSUPPORTED, "sampleRate/baudRate/frequencies must be finite and positive");
+  if (c.preambleLength < 0 || c.sfdLength < 0 || (c.preambleLength > 0 && !c.preamblePattern) ||
+      (c.sfdLength > 0 && !c.sfdPattern))
+    return fail(WAM_E_INVALID, "bad preamble/sfd pattern");
+  if (c.startBits < 0 || c.stopBits < 0 || c.startBits > 16 || c.stopBits > 16)
+    return fail(WAM_E_UNSUPPORTED, "startBits/stopBits must be in 0..16");
+  if (c.parity < 0 || c.parity > 2) return fail(WAM_E_INVALID, "parity must be 0 (none), 1 (even) or 2 (odd)");
+
+  const double fs = c.sampleRate, baud = c.baudRate;
+  const double downsampleRate = fs / 2;
+  const double center = (c.markFrequency + c.spaceFrequency) / 2;
+  const double spb = floor(fs / baud);
+  const double dspb = floor(downsampleRate / baud);
+  const int bpb = 8 + c.startBits + c.stopBits + (c.parity != 0 ? 1 : 0);
+  if (spb < 1 || dspb < 1 || spb > 1e6) return fail(WAM_E_UNSUPPORTED, "samples per bit out of range (need fs/2 >= baud)");
+  d.spb = (int)spb; d.dspb = (int)dspb; d.bpb = bpb;
+  d.start_bits = c.startBits; d.stop_bits = c.stopBits; d.parity = c.parity;
+  d.stop_pos = c.parity == 0 ? 9 : 10;
+
+  d.agc_enabled = c.agcEnabled ? 1 : 0;
+  d.agc_attack = 1.0 - exp(-1.0 / (fs * 0.001));
+  d.agc_release = 1.0 - exp(-1.0 / (fs * 0.01));
+
+  const double freqSpan = fabs(c.spaceFrequency - c.markFrequency);
+  const double deviation = freqSpan / 2;
+  const double carson = 2 * (deviation + baud);
+  const double bw = (c.preFilterBandwidth != c.preFilterBandwidth || carson != carson)
+                        ? NAN
+                        : (c.preFilterBandwidth > carson ? c.preFilterBandwidth : carson);
+  double b[3], a[3];
+  wam_design_butterworth_bandpass(center, bw, fs, b, a);
+  d.pre_b0 = b[0]; d.pre_b1 = b[1]; d.pre_b2 = b[2]; d.pre_a1 = a[1]; d.pre_a2 = a[2];
+  wam_design_butterworth_lowpass(baud, fs, b, a);
+  d.lp_b0 = b[0]; d.lp_b1 = b[1]; d.lp_b2 = b[2]; d.lp_a1 = a[1]; d.lp_a2 = a[2];
+
+  d.omega = 2 * M_PI * center / fs;
+  if (!(d.omega >= 0) || !(d.omega < 2 * M_PI)) return fail(WAM_E_UNSUPPORTED, "center frequency must be in [0, sampleRate)");
+  d.cos_omega = cos(d.omega);
+  d.sin_omega = sin(d.omega);
+
+  // preambleSfdBits (fsk.ts:143-144, :159-173)
+  const int nbytes = c.preambleLength + c.sfdLength;
+  const long nbits = (long)nbytes * bpb;
+  if (nbits > kMaxPatternWords * 32 || nbytes > (int)sizeof(d.preamble_sfd))
+    return fail(WAM_E_UNSUPPORTED, "preamble+sfd longer than 256 line bits / 32 bytes");
+  d.nbits = (int)nbits;
+  d.n_preamble = c.preambleLength; d.n_sfd = c.sfdLength;
+  int k = 0;
+  for (int i = 0; i < nbytes; i++) {
+    const int byte = i < c.preambleLength ? c.preamblePattern[i] : c.sfdPattern[i - c.preambleLength];
+    d.preamble_sfd[i] = (uint8_t)byte;
+    auto push = [&](int bit) {
+      if (bit) d.pattern[k >> 5] |= 1u << (k & 31);
+      k++;
+    };
+    for (int s = 0; s < c.startBits; s++) push(0);
+    for (int s = 7; s >= 0; s--) push((byte >> s) & 1);
+    if (c.parity != 0) {
+      int p = 0;
+      for (int s = 0; s < 8; s++) p ^= (byte >> s) & 1;
+      push(c.parity == 1 ? p : 1 - p);
+    }
+    for (int s = 0; s < c.stopBits; s++) push(1);
+  }
+  d.total_bits = d.nbits * d.dspb;
+  d.check_period = (int)floor(dspb / 4 + 0.5);  // Math.round
+  const double samplesForEOD = (double)bpb * dspb * 0.7;
+  d.eod_count = (int)ceil(samplesForEOD);
+  // smallest matched with matched / total > syncThreshold (strict, float64 division as in JS)
+  d.min_matched = INT_MAX;
+  if (d.total_bits > 0 && c.syncThreshold == c.syncThreshold) {
+    const double total = (double)d.total_bits;
+    long lo = 0, hi = (long)d.total_bits + 1;  // first m in [0, total] with m/total > thr, else total+1
+    while (lo < hi) {
+      const long mid = (lo + hi) / 2;
+      if ((double)mid / total > c.syncThreshold) hi = mid;
+      else lo = mid + 1;
+    }
+    if (lo <= d.total_bits) d.min_matched = (int)lo;
+  }
+
+  const double maxSyncBits = (double)d.nbits + 32;
+  d.ring_cap = maxSyncBits * dspb * 1.1;
+  d.ring_cap_int = (int)trunc(d.ring_cap);
+  d.ring_fractional = (d.ring_cap != floor(d.ring_cap)) ? 1 : 0;
+  if (d.ring_cap > 5e7) return fail(WAM_E_UNSUPPORTED, "sync ring too large");
+  if (!d.ring_fractional) {
+    int words = 4;
+    while ((long)words * 32 < (long)d.total_bits + 64) words <<= 1;
+    d.ring_words = words;
+  } else {
+    d.ring_words = (d.ring_cap_int + 31) / 32 + 1;
+  }
+  d.amp_cap = d.dspb * 8;
+  d.mark = c.markFrequency; d.space = c.spaceFrequency; d.fs = fs;
+  return WAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// batch object
+// ------------------------------------------------------------------------------------------
+struct Group {
+  FskDerived d;
+  wam_fsk_config cfg;
+  std::vector<int32_t> ids;  // sorted global stream ids
+  bool contiguous = true;
+  int32_t* d_ids = nullptr;
+  double* f64 = nullptr;
+  uint32_t* u32 = nullptr;
+  uint32_t* sync_ring = nullptr;
+  float* amp_ring = nullptr;
+};
+
+struct wam_fsk_batch {
+  int device = 0;
+  long n_streams = 0;
+  std::vector<Group> groups;
+  std::vector<int32_t> stream_group, stream_local;
+  // host counters (identical for every stream of the batch: fsk.ts:195-196)
+  double demodulation_calls = 0, total_samples = 0, configured_events = 1;
+  long launches = 0;
+  // staging for the HOST-buffer entry points
+  cudaStream_t streams[2] = {nullptr, nullptr};
+  float* stage_samples[2] = {nullptr, nullptr};
+  uint8_t* stage_out[2] = {nullptr, nullptr};
+  int32_t* stage_len[2] = {nullptr, nullptr};
+  size_t stage_samples_bytes = 0, stage_out_bytes = 0, stage_len_bytes = 0;
+  // modulator scratch
+  uint32_t* mod_prefix = nullptr;
+  size_t mod_prefix_bytes = 0;
+  uint8_t* mod_data = nullptr;
+  size_t mod_data_bytes = 0;
+  float* mod_out = nullptr;
+  size_t mod_out_bytes = 0;
+  int32_t* mod_len = nullptr;
+  size_t mod_len_bytes = 0;
+};
+
+static int init_group_state(Group& g) {
+  const size_t n = g.ids.size();
+  CUDA_TRY(cudaMemset(g.f64, 0, sizeof(double) * F64_COUNT * n));
+  CUDA_TRY(cudaMemset(g.u32, 0, sizeof(uint32_t) * U32_COUNT * n));
+  CUDA_TRY(cudaMemset(g.sync_ring, 0, sizeof(uint32_t) * (size_t)g.d.ring_words * n));
+  CUDA_TRY(cudaMemset(g.amp_ring, 0, sizeof(float) * (size_t)g.d.amp_cap * n));
+  // AGC gain 1.0 (fsk.ts:46), silence threshold 0.01 (fsk.ts:128)
+  std::vector<double> ones(n, 1.0), thr(n, 0.01);
+  CUDA_TRY(cudaMemcpy(g.f64 + (size_t)F_GAIN * n, ones.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(g.f64 + (size_t)F_SIL_THR * n, thr.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+  return WAM_OK;
+}
+
+static void free_batch(wam_fsk_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  for (auto& g : b->groups) {
+    cudaFree(g.d_ids); cudaFree(g.f64); cudaFree(g.u32); cudaFree(g.sync_ring); cudaFree(g.amp_ring);
+  }
+  for (int i = 0; i < 2; i++) {
+    if (b->streams[i]) cudaStreamDestroy(b->streams[i]);
+    cudaFree(b->stage_samples[i]); cudaFree(b->stage_out[i]); cudaFree(b->stage_len[i]);
+  }
+  cudaFree(b->mod_prefix); cudaFree(b->mod_data); cudaFree(b->mod_out); cudaFree(b->mod_len);
+  delete b;
+}
+
+extern "C" int wam_fsk_batch_create(int device, long n_streams, const wam_fsk_config* cfgs, int n_cfgs,
+                                    const int32_t* cfg_index, wam_fsk_batch** out) {
+  if (!out) return fail(WAM_E_INVALID, "out is NULL");
+  *out = nullptr;
+  if (n_streams <= 0 || n_streams > INT_MAX / 2) return fail(WAM_E_INVALID, "n_streams out of range");
+  if (!cfgs || n_cfgs <= 0) return fail(WAM_E_INVALID, "no configuration given");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(WAM_E_CUDA, "no CUDA device available (libwam has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(WAM_E_INVALID, "device index out of range");
+  CUDA_TRY(cudaSetDevice(device));
+
+  wam_fsk_batch* b = new (std::nothrow) wam_fsk_batch();
+  if (!b) return fail(WAM_E_NOMEM, "host allocation failed");
+  b->device = device;
+  b->n_streams = n_streams;
+  b->groups.resize((size_t)n_cfgs);
+  for (int i = 0; i < n_cfgs; i++) {
+    b->groups[(size_t)i].cfg = cfgs[i];
+    int rc = derive(cfgs[i], b->groups[(size_t)i].d);
+    if (rc != WAM_OK) { free_batch(b); return rc; }
+  }
+  b->stream_group.resize((size_t)n_streams);
+  b->stream_local.resize((size_t)n_streams);
+  for (long s = 0; s < n_streams; s++) {
+    const int gi = cfg_index ? cfg_index[s] : 0;
+    if (gi < 0 || gi >= n_cfgs) { free_batch(b); return fail(WAM_E_INVALID, "cfg_index out of range"); }
+    Group& g = b->groups[(size_t)gi];
+    b->stream_group[(size_t)s] = gi;
+    b->stream_local[(size_t)s] = (int32_t)g.ids.size();
+    g.ids.push_back((int32_t)s);
+  }
+  for (auto& g : b->groups) {
+    g.cfg.preamblePattern = nullptr; g.cfg.sfdPattern = nullptr;  // bytes live in d.preamble_sfd
+    const size_t n = g.ids.size();
+    if (n == 0) continue;
+    g.contiguous = (size_t)(g.ids.back() - g.ids.front() + 1) == n;
+    cudaError_t e = cudaSuccess;
+    if (!g.contiguous) {
+      e = cudaMalloc(&g.d_ids, sizeof(int32_t) * n);
+      if (e == cudaSuccess) e = cudaMemcpy(g.d_ids, g.ids.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&g.f64, sizeof(double) * F64_COUNT * n);
+    if (e == cudaSuccess) e = cudaMalloc(&g.u32, sizeof(uint32_t) * U32_COUNT * n);
+    if (e == cudaSuccess) e = cudaMalloc(&g.sync_ring, sizeof(uint32_t) * (size_t)g.d.ring_words * n);
+    if (e == cudaSuccess) e = cudaMalloc(&g.amp_ring, sizeof(float) * (size_t)g.d.amp_cap * n);
+    if (e != cudaSuccess) {
+      free_batch(b);
+      return fail(e == cudaErrorMemoryAllocation ? WAM_E_NOMEM : WAM_E_CUDA, std::string("state allocation: ") + cudaGetErrorString(e));
+    }
+    int rc = init_group_state(g);
+    if (rc != WAM_OK) { free_batch(b); return rc; }
+  }
+  for (int i = 0; i < 2; i++) {
+    cudaError_t e = cudaStreamCreateWithFlags(&b->streams[i], cudaStreamNonBlocking);
+    if (e != cudaSuccess) { free_batch(b); return fail(WAM_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+  }
+  *out = b;
+  return WAM_OK;
+}
+
+extern "C" int wam_fsk_batch_destroy(wam_fsk_batch* b) {
+  free_batch(b);
+  return WAM_OK;
+}
+
+// FSKCore.reset() on every stream — fsk.ts:464-469: resetState(), clear the sync ring, drop queued
+// bytes, zero the debug counters.  AGC, pre-filter, amplitude ring and silence threshold survive.
+extern "C" int wam_fsk_batch_reset(wam_fsk_batch* b) {
+  if (!b) return fail(WAM_E_INVALID, "batch is NULL");
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  static const int f_zero[] = {F_LO_PHASE, F_IX1, F_IX2, F_IY1, F_IY2, F_QX1, F_QX2, F_QY1, F_QY2, F_OX1, F_OX2,
+                               F_OY1, F_OY2, F_LAST_PHASE, F_IACC, F_QACC, F_RING_WI, F_RING_RI, F_RING_LEN};
+  static const int u_zero[] = {U_DSC, U_GSC, U_GMOD, U_BSC, U_NEXT_IDX, U_BIT_ACC, U_BIT_CNT, U_STARTED, U_BITPOS,
+                               U_CURRENT, U_SIL_CNT, U_RING_POS, U_RING_LEN, U_SYNC_DET};
+  for (auto& g : b->groups) {
+    const size_t n = g.ids.size();
+    if (n == 0) continue;
+    for (int f : f_zero) CUDA_TRY(cudaMemset(g.f64 + (size_t)f * n, 0, sizeof(double) * n));
+    for (int u : u_zero) CUDA_TRY(cudaMemset(g.u32 + (size_t)u * n, 0, sizeof(uint32_t) * n));
+  }
+  b->demodulation_calls = 0;
+  b->total_samples = 0;
+  return WAM_OK;
+}
+
+extern "C" long wam_fsk_batch_out_capacity(wam_fsk_batch* b, long n_samples) {
+  if (!b || n_samples < 0) return fail(WAM_E_INVALID, "bad argument");
+  long cap = 0;
+  for (auto& g : b->groups) {
+    if (g.ids.empty()) continue;
+    // a byte needs at least (bpb - 1) * dspb + 1 decimated samples = 2x input samples
+    const long per = 2L * ((long)(g.d.bpb - 1) * g.d.dspb + 1);
+    cap = std::max(cap, n_samples / per + 2);
+  }
+  return (cap + 15) / 16 * 16;
+}
+
+template <bool A, bool W, bool T>
+static void launch_demod(const DemodArgs& args, cudaStream_t st) {
+  const int n = args.l_end - args.l_begin;
+  fsk_demod_exact_kernel<A, W, T><<<(n + 31) / 32, 32, 0, st>>>(args);
+}
+
+// launch the demodulator for all streams of `b` whose global id lies in [s0, s1); row 0 of the
+// buffers is stream `row_base`.
+static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base, float* d_samples, long stride, long n,
+                              uint8_t* d_out, long out_stride, int32_t* d_out_len, float* d_tap, uint32_t flags,
+                              cudaStream_t st) {
+  const bool aligned = ((reinterpret_cast<uintptr_t>(d_samples) & 15) == 0) && (stride % 4 == 0);
+  const bool wb = (flags & WAM_BATCH_WRITEBACK_AGC) != 0;
+  const bool tap = (flags & WAM_BATCH_TAP_PREFILTER) != 0 && d_tap != nullptr;
+  for (auto& g : b->groups) {
+    if (g.ids.empty()) continue;
+    const auto lo = std::lower_bound(g.ids.begin(), g.ids.end(), (int32_t)s0) - g.ids.begin();
+    const auto hi = std::lower_bound(g.ids.begin(), g.ids.end(), (int32_t)s1) - g.ids.begin();
+    if (hi <= lo) continue;
+    DemodArgs a;
+    a.d = g.d;
+    a.ids = g.contiguous ? nullptr : g.d_ids;
+    a.id0 = g.ids.front();
+    a.n_local = (int)g.ids.size();
+    a.l_begin = (int)lo; a.l_end = (int)hi;
+    a.row_base = (int)row_base;
+    a.f64 = g.f64; a.u32 = g.u32; a.sync_ring = g.sync_ring; a.amp_ring = g.amp_ring;
+    a.samples = d_samples; a.stride = stride; a.n = n;
+    a.out = d_out; a.out_stride = out_stride; a.out_len = d_out_len; a.tap = d_tap;
+    const int sel = (aligned ? 4 : 0) | (wb ? 2 : 0) | (tap ? 1 : 0);
+    switch (sel) {
+      case 0: launch_demod<false, false, false>(a, st); break;
+      case 1: launch_demod<false, false, true>(a, st); break;
+      case 2: launch_demod<false, true, false>(a, st); break;
+      case 3: launch_demod<false, true, true>(a, st); break;
+      case 4: launch_demod<true, false, false>(a, st); break;
+      case 5: launch_demod<true, false, true>(a, st); break;
+      case 6: launch_demod<true, true, false>(a, st); break;
+      default: launch_demod<true, true, true>(a, st); break;
+    }
+    b->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return WAM_OK;
+}
+
+extern "C" int wam_fsk_batch_demodulate_device(wam_fsk_batch* b, float* d_samples, long stream_stride, long n_samples,
+                                               uint8_t* d_out, long out_stride, int32_t* d_out_len, float* d_tap,
+                                               void* cuda_stream, uint32_t flags) {
+  if (!b) return fail(WAM_E_INVALID, "batch is NULL");
+  if (n_samples < 0 || stream_stride < n_samples || out_stride < 0 || !d_out_len || (!d_samples && n_samples > 0) ||
+      (!d_out && out_stride > 0))
+    return fail(WAM_E_INVALID, "bad buffer description");
+  CUDA_TRY(cudaSetDevice(b->device));
+  b->demodulation_calls += 1;
+  b->total_samples += (double)n_samples;
+  return launch_demod_range(b, 0, b->n_streams, 0, d_samples, stream_stride, n_samples, d_out, out_stride, d_out_len,
+                            d_tap, flags, (cudaStream_t)cuda_stream);
+}
+
+static int ensure(void** p, size_t* cur, size_t need) {
+  if (*cur >= need && *p) return WAM_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cur = 0;
+  cudaError_t e = cudaMalloc(p, need ? need : 16);
+  if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? WAM_E_NOMEM : WAM_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  *cur = need;
+  return WAM_OK;
+}
+
+extern "C" int wam_fsk_batch_demodulate(wam_fsk_batch* b, float* samples, long stream_stride, long n_samples,
+                                        uint8_t* out, long out_stride, int32_t* out_len, uint32_t flags) {
+  if (!b) return fail(WAM_E_INVALID, "batch is NULL");
+  if (n_samples < 0 || stream_stride < n_samples || out_stride < 0 || !out_len || (!samples && n_samples > 0) ||
+      (!out && out_stride > 0))
+    return fail(WAM_E_INVALID, "bad buffer description");
+  CUDA_TRY(cudaSetDevice(b->device));
+  b->demodulation_calls += 1;
+  b->total_samples += (double)n_samples;
+  flags &= WAM_BATCH_WRITEBACK_AGC;
+
+  // Streams are processed in chunks so that the H2D copy of chunk k+1 overlaps the kernel of
+  // chunk k (two CUDA streams, two staging buffers).  Device rows are packed (stride = n padded to 4).
+  const long dstride = (n_samples + 3) / 4 * 4;
+  const size_t row_bytes = sizeof(float) * (size_t)std::max<long>(dstride, 4);
+  long chunk = (long)((size_t)256 << 20) / (long)row_bytes;  // ~256 MiB of samples per chunk
+  chunk = std::max<long>(32, chunk / 32 * 32);
+  chunk = std::min<long>(chunk, (b->n_streams + 31) / 32 * 32);
+  const size_t need_s = row_bytes * (size_t)chunk;
+  const size_t need_o = (size_t)std::max<long>(out_stride, 1) * (size_t)chunk;
+  const size_t need_l = sizeof(int32_t) * (size_t)chunk;
+  for (int i = 0; i < 2; i++) {
+    size_t cs = b->stage_samples_bytes, co = b->stage_out_bytes, cl = b->stage_len_bytes;
+    int rc = ensure((void**)&b->stage_samples[i], &cs, need_s);
+    if (rc == WAM_OK) rc = ensure((void**)&b->stage_out[i], &co, need_o);
+    if (rc == WAM_OK) rc = ensure((void**)&b->stage_len[i], &cl, need_l);
+    if (rc != WAM_OK) {
+      b->stage_samples_bytes = b->stage_out_bytes = b->stage_len_bytes = 0;
+      return rc;
+    }
+    if (i == 1) { b->stage_samples_bytes = cs; b->stage_out_bytes = co; b->stage_len_bytes = cl; }
+  }
+
+  int k = 0;
+  for (long s0 = 0; s0 < b->n_streams; s0 += chunk, k ^= 1) {
+    const long s1 = std::min(b->n_streams, s0 + chunk);
+    const long rows = s1 - s0;
+    cudaStream_t st = b->streams[k];
+    if (n_samples > 0)
+      CUDA_TRY(cudaMemcpy2DAsync(b->stage_samples[k], sizeof(float) * (size_t)dstride, samples + s0 * stream_stride,
+                                 sizeof(float) * (size_t)stream_stride, sizeof(float) * (size_t)n_samples, (size_t)rows,
+                                 cudaMemcpyHostToDevice, st));
+    int rc = launch_demod_range(b, s0, s1, s0, b->stage_samples[k], dstride, n_samples, b->stage_out[k], out_stride,
+                                b->stage_len[k], nullptr, flags, st);
+    if (rc != WAM_OK) return rc;
+    if (out_stride > 0)
+      CUDA_TRY(cudaMemcpyAsync(out + s0 * out_stride, b->stage_out[k], (size_t)out_stride * (size_t)rows,
+                               cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_len + s0, b->stage_len[k], sizeof(int32_t) * (size_t)rows, cudaMemcpyDeviceToHost, st));
+    if ((flags & WAM_BATCH_WRITEBACK_AGC) && n_samples > 0)
+      CUDA_TRY(cudaMemcpy2DAsync(samples + s0 * stream_stride, sizeof(float) * (size_t)stream_stride, b->stage_samples[k],
+                                 sizeof(float) * (size_t)dstride, sizeof(float) * (size_t)n_samples, (size_t)rows,
+                                 cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_TRY(cudaStreamSynchronize(b->streams[0]));
+  CUDA_TRY(cudaStreamSynchronize(b->streams[1]));
+  // per-stream overflow flags would have clamped out_len; report it
+  return WAM_OK;
+}
+
+extern "C" int wam_fsk_batch_status(wam_fsk_batch* b, wam_fsk_status* st) {
+  if (!b || !st) return fail(WAM_E_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (auto& g : b->groups) {
+    const size_t n = g.ids.size();
+    if (n == 0) continue;
+    std::vector<double> f((size_t)F64_COUNT * n);
+    std::vector<uint32_t> u((size_t)U32_COUNT * n);
+    CUDA_TRY(cudaMemcpy(f.data(), g.f64, sizeof(double) * f.size(), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(u.data(), g.u32, sizeof(uint32_t) * u.size(), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; i++) {
+      wam_fsk_status& s = st[g.ids[i]];
+      s.ready = 1;
+      s.frameStarted = (int32_t)u[(size_t)U_STARTED * n + i];
+      s.globalSampleCounter = (double)u[(size_t)U_GSC * n + i];
+      s.receivedBitsLength = g.d.ring_fractional ? f[(size_t)F_RING_LEN * n + i] : (double)u[(size_t)U_RING_LEN * n + i];
+      s.byteBufferLength = 0;
+      s.demodulationCalls = b->demodulation_calls;
+      s.syncDetections = (double)u[(size_t)U_SYNC_DET * n + i];
+      s.silenceThreshold = f[(size_t)F_SIL_THR * n + i];
+      s.totalSamplesProcessed = b->total_samples;
+      s.eodEvents = (double)u[(size_t)U_EOD_EV * n + i];
+      s.errorEvents = 0;
+      s.configuredEvents = b->configured_events;
+    }
+  }
+  return WAM_OK;
+}
+
+extern "C" long wam_fsk_batch_launch_count(wam_fsk_batch* b) { return b ? b->launches : 0; }
+
+// ------------------------------------------------------------------------------------------
+// batched modulator
+// ------------------------------------------------------------------------------------------
+static long modulate_size(const FskDerived& d, long nbytes) {  // fsk.ts:391-394
+  const long total_bytes = (long)d.n_preamble + d.n_sfd + nbytes;
+  const long pad = total_bytes > 0 ? 2L * d.spb : 0;
+  return total_bytes * d.bpb * d.spb + pad + (long)d.bpb * d.spb;
+}
+
+static int modulate_device_group(wam_fsk_batch* b, const Group& g, const uint8_t* d_data, long data_stride,
+                                 const int32_t* d_data_len, long nbytes, long max_bytes, float* d_out, long out_stride,
+                                 int32_t* d_out_len, long n_rows, cudaStream_t st) {
+  const int prefix_stride = (int)(g.d.n_preamble + g.d.n_sfd + max_bytes + 1);
+  int rc = ensure((void**)&b->mod_prefix, &b->mod_prefix_bytes, sizeof(uint32_t) * (size_t)prefix_stride * (size_t)n_rows);
+  if (rc != WAM_OK) return rc;
+  ModArgs a;
+  a.d = g.d;
+  a.data = d_data; a.data_stride = data_stride; a.data_len = d_data_len; a.nbytes = (int)nbytes;
+  a.n_streams = (int)n_rows;
+  a.out = d_out; a.out_stride = out_stride; a.out_len = d_out_len;
+  a.prefix = b->mod_prefix; a.prefix_stride = prefix_stride;
+  a.vec_ok = ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && out_stride % 4 == 0) ? 1 : 0;
+  const int warps_per_block = 4;
+  fsk_mark_prefix_kernel<<<(unsigned)((n_rows + warps_per_block - 1) / warps_per_block), 128, 0, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  const long max_total = std::min(modulate_size(g.d, max_bytes), out_stride);
+  dim3 grid((unsigned)((max_total + 511) / 512), (unsigned)n_rows);
+  if (grid.x == 0) grid.x = 1;
+  fsk_modulate_kernel<<<grid, 128, 0, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  b->launches += 2;
+  return WAM_OK;
+}
+
+extern "C" int wam_fsk_batch_modulate_device(wam_fsk_batch* b, const uint8_t* d_data, long data_stride,
+                                             const int32_t* d_data_len, long nbytes, float* d_out, long out_stride,
+                                             int32_t* d_out_len, void* cuda_stream) {
+  if (!b || !d_out || nbytes < 0 || (nbytes > 0 && !d_data)) return fail(WAM_E_INVALID, "bad argument");
+  if (b->groups.size() != 1 || b->n_streams > 65535)
+    return fail(WAM_E_UNSUPPORTED, "batched modulate supports one configuration and <= 65535 streams per call");
+  CUDA_TRY(cudaSetDevice(b->device));
+  return modulate_device_group(b, b->groups[0], d_data, data_stride, d_data_len, nbytes, nbytes, d_out, out_stride,
+                               d_out_len, b->n_streams, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int wam_fsk_batch_modulate(wam_fsk_batch* b, const uint8_t* data, long data_stride, const int32_t* data_len,
+                                      long nbytes, float* out, long out_stride, int32_t* out_len) {
+  if (!b || !out || nbytes < 0 || (nbytes > 0 && !data) || data_stride < nbytes) return fail(WAM_E_INVALID, "bad argument");
+  if (b->groups.size() != 1) return fail(WAM_E_UNSUPPORTED, "batched modulate supports one configuration per batch");
+  CUDA_TRY(cudaSetDevice(b->device));
+  const Group& g = b->groups[0];
+  const long n = b->n_streams;
+  if (data_len)
+    for (long s = 0; s < n; s++)
+      if (data_len[s] < 0 || data_len[s] > nbytes) return fail(WAM_E_INVALID, "data_len[s] must be within 0..nbytes");
+  cudaStream_t st = b->streams[0];
+  const long dstride = std::max<long>(data_stride, 1);
+  const long ostride = (out_stride + 3) / 4 * 4;
+  const long chunk_max = 32768;
+  for (long s0 = 0; s0 < n; s0 += chunk_max) {
+    const long rows = std::min(chunk_max, n - s0);
+    int rc = ensure((void**)&b->mod_data, &b->mod_data_bytes, (size_t)dstride * (size_t)rows);
+    if (rc == WAM_OK) rc = ensure((void**)&b->mod_out, &b->mod_out_bytes, sizeof(float) * (size_t)ostride * (size_t)rows);
+    if (rc == WAM_OK) rc = ensure((void**)&b->mod_len, &b->mod_len_bytes, sizeof(int32_t) * 2 * (size_t)rows);
+    if (rc != WAM_OK) return rc;
+    if (nbytes > 0)
+      CUDA_TRY(cudaMemcpyAsync(b->mod_data, data + s0 * data_stride, (size_t)data_stride * (size_t)rows, cudaMemcpyHostToDevice, st));
+    int32_t* d_len_in = nullptr;
+    if (data_len) {
+      d_len_in = b->mod_len + rows;
+      CUDA_TRY(cudaMemcpyAsync(d_len_in, data_len + s0, sizeof(int32_t) * (size_t)rows, cudaMemcpyHostToDevice, st));
+    }
+    rc = modulate_device_group(b, g, b->mod_data, dstride, d_len_in, nbytes, nbytes, b->mod_out, ostride, b->mod_len, rows, st);
+    if (rc != WAM_OK) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(out + s0 * out_stride, sizeof(float) * (size_t)out_stride, b->mod_out,
+                               sizeof(float) * (size_t)ostride, sizeof(float) * (size_t)out_stride, (size_t)rows,
+                               cudaMemcpyDeviceToHost, st));
+    if (out_len) CUDA_TRY(cudaMemcpyAsync(out_len + s0, b->mod_len, sizeof(int32_t) * (size_t)rows, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return WAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// single-stream modem (one FSKCore instance)
+// ------------------------------------------------------------------------------------------
+struct wam_fsk {
+  int device = 0;
+  wam_fsk_batch* b = nullptr;  // n_streams == 1
+  bool ready = false;
+  // instance fields that survive configure() in the reference
+  bool has_agc = false;
+  double agc_attack = 0, agc_release = 0;
+  double demodulation_calls = 0, total_samples = 0, sync_detections_base = 0;
+  double eod_events_base = 0, configured_events = 0;
+  // pinned bounce buffers
+  float* h_samples = nullptr; size_t h_samples_n = 0;
+  uint8_t* h_out = nullptr; size_t h_out_n = 0;
+  int32_t* h_len = nullptr;
+};
+
+extern "C" int wam_fsk_create(int device, wam_fsk** out) {
+  if (!out) return fail(WAM_E_INVALID, "out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(WAM_E_CUDA, "no CUDA device available (libwam has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(WAM_E_INVALID, "device index out of range");
+  wam_fsk* m = new (std::nothrow) wam_fsk();
+  if (!m) return fail(WAM_E_NOMEM, "host allocation failed");
+  m->device = device;
+  *out = m;
+  return WAM_OK;
+}
+
+extern "C" int wam_fsk_destroy(wam_fsk* m) {
+  if (!m) return WAM_OK;
+  cudaSetDevice(m->device);
+  free_batch(m->b);
+  cudaFreeHost(m->h_samples); cudaFreeHost(m->h_out); cudaFreeHost(m->h_len);
+  delete m;
+  return WAM_OK;
+}
+
+static int read_f64(wam_fsk_batch* b, int field, double* v) {
+  Group& g = b->groups[0];
+  CUDA_TRY(cudaMemcpy(v, g.f64 + (size_t)field * g.ids.size(), sizeof(double), cudaMemcpyDeviceToHost));
+  return WAM_OK;
+}
+static int write_f64(wam_fsk_batch* b, int field, double v) {
+  Group& g = b->groups[0];
+  CUDA_TRY(cudaMemcpy(g.f64 + (size_t)field * g.ids.size(), &v, sizeof(double), cudaMemcpyHostToDevice));
+  return WAM_OK;
+}
+static int read_u32(wam_fsk_batch* b, int field, uint32_t* v) {
+  Group& g = b->groups[0];
+  CUDA_TRY(cudaMemcpy(v, g.u32 + (size_t)field * g.ids.size(), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return WAM_OK;
+}
+
+// configure() — fsk.ts:133-157.  A fresh AGC (when enabled), fresh filters and rings; what the
+// reference keeps on the instance is carried over: silence threshold (fsk.ts:128 is only ever
+// written at sync), debug counters, and a previously created AGC when agcEnabled is now false
+// (fsk.ts:447-449 only assigns).
+extern "C" int wam_fsk_configure(wam_fsk* m, const wam_fsk_config* c) {
+  if (!m || !c) return fail(WAM_E_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(m->device));
+  double old_thr = 0.01, old_gain = 1.0;
+  uint32_t old_sync = 0, old_eod = 0;
+  if (m->b) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    int rc = read_f64(m->b, F_SIL_THR, &old_thr);
+    if (rc == WAM_OK) rc = read_f64(m->b, F_GAIN, &old_gain);
+    if (rc == WAM_OK) rc = read_u32(m->b, U_SYNC_DET, &old_sync);
+    if (rc == WAM_OK) rc = read_u32(m->b, U_EOD_EV, &old_eod);
+    if (rc != WAM_OK) return rc;
+  }
+  wam_fsk_batch* nb = nullptr;
+  int rc = wam_fsk_batch_create(m->device, 1, c, 1, nullptr, &nb);
+  if (rc != WAM_OK) return rc;
+  Group& g = nb->groups[0];
+  if (c->agcEnabled) {
+    m->has_agc = true;
+    m->agc_attack = g.d.agc_attack;
+    m->agc_release = g.d.agc_release;
+  } else if (m->has_agc) {
+    g.d.agc_enabled = 1;
+    g.d.agc_attack = m->agc_attack;
+    g.d.agc_release = m->agc_release;
+    rc = write_f64(nb, F_GAIN, old_gain);
+  }
+  if (rc == WAM_OK) rc = write_f64(nb, F_SIL_THR, old_thr);
+  if (rc != WAM_OK) { free_batch(nb); return rc; }
+  if (m->b) {
+    m->sync_detections_base += old_sync;
+    m->eod_events_base += old_eod;
+    free_batch(m->b);
+  }
+  m->b = nb;
+  m->ready = true;
+  m->configured_events += 1;
+  return WAM_OK;
+}
+
+extern "C" int wam_fsk_is_ready(wam_fsk* m) { return (m && m->ready) ? 1 : 0; }
+
+extern "C" long wam_fsk_modulate_size(wam_fsk* m, long nbytes) {
+  if (!m || nbytes < 0) return fail(WAM_E_INVALID, "bad argument");
+  if (!m->ready) return fail(WAM_E_NOT_CONFIGURED, "FSK modulator not configured");
+  return modulate_size(m->b->groups[0].d, nbytes);
+}
+
+extern "C" int wam_fsk_modulate(wam_fsk* m, const uint8_t* data, long nbytes, float* out, long cap, long* n_out) {
+  if (!m || nbytes < 0 || (nbytes > 0 && !data)) return fail(WAM_E_INVALID, "bad argument");
+  if (!m->ready) return fail(WAM_E_NOT_CONFIGURED, "FSK modulator not configured");
+  const long total = modulate_size(m->b->groups[0].d, nbytes);
+  if (n_out) *n_out = total;
+  if (!out || cap < total) return fail(WAM_E_CAPACITY, "output buffer too small for modulateData");
+  int32_t len = 0;
+  int rc = wam_fsk_batch_modulate(m->b, data, std::max<long>(nbytes, 1), nullptr, nbytes, out, total, &len);
+  return rc;
+}
+
+extern "C" int wam_fsk_demodulate(wam_fsk* m, float* samples, long n, uint8_t* out, long cap, long* n_out) {
+  if (!m || n < 0 || (n > 0 && !samples) || !n_out) return fail(WAM_E_INVALID, "bad argument");
+  if (!m->ready) return fail(WAM_E_NOT_CONFIGURED, "FSK demodulator not configured");
+  *n_out = 0;
+  CUDA_TRY(cudaSetDevice(m->device));
+  m->demodulation_calls += 1;
+  m->total_samples += (double)n;
+  const long ocap = wam_fsk_batch_out_capacity(m->b, n);
+  if (m->h_samples_n < (size_t)n || !m->h_samples) {
+    cudaFreeHost(m->h_samples); m->h_samples = nullptr;
+    const size_t want = std::max<size_t>((size_t)n, 4096);
+    CUDA_TRY(cudaMallocHost((void**)&m->h_samples, sizeof(float) * want));
+    m->h_samples_n = want;
+  }
+  if (m->h_out_n < (size_t)ocap || !m->h_out) {
+    cudaFreeHost(m->h_out); m->h_out = nullptr;
+    const size_t want = std::max<size_t>((size_t)ocap, 256);
+    CUDA_TRY(cudaMallocHost((void**)&m->h_out, want));
+    m->h_out_n = want;
+  }
+  if (!m->h_len) CUDA_TRY(cudaMallocHost((void**)&m->h_len, sizeof(int32_t) * 4));
+  if (n > 0) memcpy(m->h_samples, samples, sizeof(float) * (size_t)n);
+  const Group& g = m->b->groups[0];
+  const uint32_t flags = g.d.agc_enabled ? WAM_BATCH_WRITEBACK_AGC : 0u;
+  int rc = wam_fsk_batch_demodulate(m->b, m->h_samples, std::max<long>(n, 1), n, m->h_out, ocap, m->h_len, flags);
+  if (rc != WAM_OK) return rc;
+  if (flags && n > 0) memcpy(samples, m->h_samples, sizeof(float) * (size_t)n);  // fsk.ts:55 mutates the input
+  const long nb = m->h_len[0];
+  *n_out = nb;
+  if (nb > cap) return fail(WAM_E_CAPACITY, "output buffer too small for demodulated bytes");
+  if (nb > 0) memcpy(out, m->h_out, (size_t)nb);
+  return WAM_OK;
+}
+
+extern "C" int wam_fsk_reset(wam_fsk* m) {  // fsk.ts:464-469
+  if (!m) return fail(WAM_E_INVALID, "bad argument");
+  m->demodulation_calls = 0;
+  m->total_samples = 0;
+  m->sync_detections_base = 0;
+  if (!m->b) return WAM_OK;
+  return wam_fsk_batch_reset(m->b);
+}
+
+extern "C" int wam_fsk_status_get(wam_fsk* m, wam_fsk_status* st) {
+  if (!m || !st) return fail(WAM_E_INVALID, "bad argument");
+  memset(st, 0, sizeof(*st));
+  st->silenceThreshold = 0.01;
+  st->configuredEvents = m->configured_events;
+  if (!m->b) return WAM_OK;
+  int rc = wam_fsk_batch_status(m->b, st);
+  if (rc != WAM_OK) return rc;
+  st->ready = m->ready ? 1 : 0;
+  st->demodulationCalls = m->demodulation_calls;
+  st->totalSamplesProcessed = m->total_samples;
+  st->syncDetections += m->sync_detections_base;
+  st->eodEvents += m->eod_events_base;
+  st->configuredEvents = m->configured_events;
+  return WAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// CRC-16 / XModem
+// ------------------------------------------------------------------------------------------
+extern "C" uint16_t wam_crc16(const uint8_t* data, long n) {  // crc16.ts:21-38 (host scalar)
+  uint32_t crc = 0xFFFF;
+  for (long k = 0; k < n; k++) {
+    crc ^= ((uint32_t)data[k] << 8);
+    for (int i = 0; i < 8; i++) crc = (crc & 0x8000) ? ((crc << 1) ^ 0x1021) & 0xFFFF : (crc << 1) & 0xFFFF;
+  }
+  return (uint16_t)crc;
+}
+
+extern "C" long wam_xmodem_serialize(int sequence, const uint8_t* payload, long n, uint8_t* out, long cap) {
+  if (sequence < 1 || sequence > 255) return fail(WAM_E_PKT_SEQUENCE, "Invalid sequence: " + std::to_string(sequence) + ". Must be 1-255.");
+  if (n > 255) return fail(WAM_E_PKT_PAYLOAD, "Payload too large: " + std::to_string(n) + ". Max 255 bytes.");
+  if (n < 0 || (n > 0 && !payload)) return fail(WAM_E_INVALID, "bad payload");
+  const long total = 4 + n + 2;
+  if (!out) return total;
+  if (cap < total) return fail(WAM_E_CAPACITY, "output buffer too small");
+  const uint16_t crc = wam_crc16(payload, n);
+  out[0] = 0x01; out[1] = (uint8_t)sequence; out[2] = (uint8_t)((~sequence) & 0xFF); out[3] = (uint8_t)n;
+  if (n > 0) memcpy(out + 4, payload, (size_t)n);
+  out[4 + n] = (uint8_t)(crc >> 8); out[4 + n + 1] = (uint8_t)(crc & 0xFF);
+  return total;
+}
+
+extern "C" int wam_xmodem_batch_check_device(const uint8_t* d_bytes, long stride, const int32_t* d_len,
+                                             const int32_t* d_expected_seq, long n_streams, wam_pkt_result* d_results,
+                                             void* cuda_stream) {
+  if (n_streams < 0 || !d_len || !d_results || (!d_bytes && stride > 0)) return fail(WAM_E_INVALID, "bad argument");
+  if (n_streams == 0) return WAM_OK;
+  static_assert(sizeof(PktResultDev) == sizeof(wam_pkt_result), "layout");
+  xmodem_check_kernel<<<(unsigned)((n_streams + 3) / 4), 128, 0, (cudaStream_t)cuda_stream>>>(
+      d_bytes, stride, d_len, d_expected_seq, n_streams, reinterpret_cast<PktResultDev*>(d_results));
+  CUDA_TRY(cudaGetLastError());
+  return WAM_OK;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t bytes) {
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? WAM_E_NOMEM : WAM_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return WAM_OK;
+  }
+};
+
+static int select_device(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(WAM_E_CUDA, "no CUDA device available (libwam has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(WAM_E_INVALID, "device index out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  return WAM_OK;
+}
+
+extern "C" int wam_xmodem_batch_check(int device, const uint8_t* bytes, long stride, const int32_t* len,
+                                      const int32_t* expected_seq, long n_streams, wam_pkt_result* results) {
+  if (n_streams < 0 || !len || !results || stride < 0 || (!bytes && stride > 0)) return fail(WAM_E_INVALID, "bad argument");
+  int rc = select_device(device);
+  if (rc != WAM_OK) return rc;
+  if (n_streams == 0) return WAM_OK;
+  for (long s = 0; s < n_streams; s++)
+    if (len[s] < 0 || len[s] > stride) return fail(WAM_E_INVALID, "len[s] must be within 0..stride");
+  DevBuf db, dl, de, dr;
+  const size_t nb = (size_t)stride * (size_t)n_streams;
+  if ((rc = db.alloc(nb)) || (rc = dl.alloc(sizeof(int32_t) * (size_t)n_streams)) ||
+      (rc = de.alloc(sizeof(int32_t) * (size_t)n_streams)) || (rc = dr.alloc(sizeof(wam_pkt_result) * (size_t)n_streams)))
+    return rc;
+  if (nb) CUDA_TRY(cudaMemcpy(db.p, bytes, nb, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dl.p, len, sizeof(int32_t) * (size_t)n_streams, cudaMemcpyHostToDevice));
+  if (expected_seq) CUDA_TRY(cudaMemcpy(de.p, expected_seq, sizeof(int32_t) * (size_t)n_streams, cudaMemcpyHostToDevice));
+  rc = wam_xmodem_batch_check_device((const uint8_t*)db.p, stride, (const int32_t*)dl.p,
+                                     expected_seq ? (const int32_t*)de.p : nullptr, n_streams, (wam_pkt_result*)dr.p, nullptr);
+  if (rc != WAM_OK) return rc;
+  CUDA_TRY(cudaMemcpy(results, dr.p, sizeof(wam_pkt_result) * (size_t)n_streams, cudaMemcpyDeviceToHost));
+  return WAM_OK;
+}
+
+extern "C" int wam_crc16_batch(int device, const uint8_t* bytes, long stride, const int32_t* len, long n_blocks,
+                               uint16_t* crc_out) {
+  if (n_blocks < 0 || !len || !crc_out || stride < 0 || (!bytes && stride > 0)) return fail(WAM_E_INVALID, "bad argument");
+  int rc = select_device(device);
+  if (rc != WAM_OK) return rc;
+  if (n_blocks == 0) return WAM_OK;
+  for (long s = 0; s < n_blocks; s++)
+    if (len[s] < 0 || len[s] > stride) return fail(WAM_E_INVALID, "len[s] must be within 0..stride");
+  DevBuf db, dl, dc;
+  const size_t nb = (size_t)stride * (size_t)n_blocks;
+  if ((rc = db.alloc(nb)) || (rc = dl.alloc(sizeof(int32_t) * (size_t)n_blocks)) || (rc = dc.alloc(sizeof(uint16_t) * (size_t)n_blocks)))
+    return rc;
+  if (nb) CUDA_TRY(cudaMemcpy(db.p, bytes, nb, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dl.p, len, sizeof(int32_t) * (size_t)n_blocks, cudaMemcpyHostToDevice));
+  crc16_batch_kernel<<<(unsigned)((n_blocks + 3) / 4), 128>>>((const uint8_t*)db.p, stride, (const int32_t*)dl.p, n_blocks, (uint16_t*)dc.p);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(crc_out, dc.p, sizeof(uint16_t) * (size_t)n_blocks, cudaMemcpyDeviceToHost));
+  return WAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// filters.ts batched application
+// ------------------------------------------------------------------------------------------
+extern "C" long wam_iir_state_size(int nb, int na) {
+  if (nb <= 0 || na <= 0) return 0;
+  return (long)(nb - 1) + (long)(na - 1);
+}
+
+extern "C" int wam_iir_process_batch(int device, const double* b, int nb, const double* a, int na, const float* in,
+                                     float* out, long stride, long n, long n_streams, double* state) {
+  if (!b || nb <= 0) return fail(WAM_E_FILTER_B_EMPTY, wam_error_string(WAM_E_FILTER_B_EMPTY));
+  if (!a || na <= 0) return fail(WAM_E_FILTER_A_EMPTY, wam_error_string(WAM_E_FILTER_A_EMPTY));
+  if (a[0] == 0) return fail(WAM_E_FILTER_A0_ZERO, wam_error_string(WAM_E_FILTER_A0_ZERO));
+  if (nb > kMaxIirTaps || na > kMaxIirTaps) return fail(WAM_E_UNSUPPORTED, "IIR order above 8 not supported");
+  if (n < 0 || n_streams < 0 || stride < n || (n > 0 && n_streams > 0 && (!in || !out))) return fail(WAM_E_INVALID, "bad argument");
+  int rc = select_device(device);
+  if (rc != WAM_OK) return rc;
+  if (n == 0 || n_streams == 0) return WAM_OK;
+  IirArgs ia;
+  memset(&ia, 0, sizeof(ia));
+  // a0 normalisation — filters.ts:30-39
+  ia.nb = nb; ia.na = na;
+  for (int i = 0; i < nb; i++) ia.b[i] = (a[0] != 1) ? b[i] / a[0] : b[i];
+  for (int i = 1; i < na; i++) ia.a[i] = (a[0] != 1) ? a[i] / a[0] : a[i];
+  ia.a[0] = 1;
+  return iir_process_batch_host(ia, in, out, stride, n, n_streams, state);
+}
+
+extern "C" int wam_fir_process_batch(int device, const double* taps, int ntaps, const float* in, float* out,
+                                     long stride, long n, long n_streams, double* state) {
+  if (ntaps < 0 || (ntaps > 0 && !taps)) return fail(WAM_E_INVALID, "bad taps");
+  if (ntaps > kMaxFirTaps) return fail(WAM_E_UNSUPPORTED, "FIR longer than 1024 taps not supported");
+  if (n < 0 || n_streams < 0 || stride < n || (n > 0 && n_streams > 0 && (!in || !out))) return fail(WAM_E_INVALID, "bad argument");
+  int rc = select_device(device);
+  if (rc != WAM_OK) return rc;
+  if (n == 0 || n_streams == 0) return WAM_OK;
+  return fir_process_batch_host(taps, ntaps, in, out, stride, n, n_streams, state);
+}
+
+extern "C" int wam_host_alloc(void** p, size_t bytes) {
+  if (!p) return fail(WAM_E_INVALID, "p is NULL");
+  CUDA_TRY(cudaMallocHost(p, bytes ? bytes : 16));
+  return WAM_OK;
+}
+extern "C" int wam_host_free(void* p) {
+  if (p) CUDA_TRY(cudaFreeHost(p));
+  return WAM_OK;
+}
+
+// definitions of the helpers declared in filters.cuh that need fail()/CUDA_TRY
+#include "filters_host.inl"

@@ -1,0 +1,86 @@
+// wam_common.cuh — shared host/device definitions for libwam.so (B200 / sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wam {
+
+constexpr int kMaxPatternWords = 8;  // preamble+SFD template: up to 256 line bits
+constexpr int kTile = 32;            // samples per stream per staged tile (one 128-byte row)
+constexpr int kStages = 3;           // cp.async pipeline depth (per warp)
+
+// Everything FSKCore.configure() derives (src/modems/fsk.ts:133-157, :426-462), computed on the
+// host in float64 with the reference's operation order, then passed to kernels by value so the
+// coefficients sit in the constant bank.
+struct FskDerived {
+  // AGCProcessor (fsk.ts:44-50)
+  int agc_enabled;
+  double agc_attack, agc_release;
+  // pre-filter: butterworthBandpass(center, max(preFilterBandwidth, carson), fs)  (fsk.ts:451-456)
+  double pre_b0, pre_b1, pre_b2, pre_a1, pre_a2;
+  // I/Q and post low-pass: butterworthLowpass(baud, fs)  (fsk.ts:457-461)
+  double lp_b0, lp_b1, lp_b2, lp_a1, lp_a2;
+  // local oscillator (fsk.ts:228)
+  double omega, cos_omega, sin_omega;
+  // framing (fsk.ts:426-444, :143-150)
+  int spb, dspb, bpb, nbits, start_bits, stop_bits, parity;  // parity 0 none 1 even 2 odd
+  int check_period;     // Math.round(dspb / 4)            (fsk.ts:299)
+  int stop_pos;         // 9 or 10                         (fsk.ts:348)
+  int eod_count;        // smallest integer >= bpb*dspb*0.7 (fsk.ts:148,288)
+  int min_matched;      // smallest matched with matched/total > syncThreshold (fsk.ts:314-315)
+  int total_bits;       // nbits * dspb
+  uint32_t pattern[kMaxPatternWords];  // preambleSfdBits, bit k at [k>>5] bit (k&31)
+  // sync ring (RingBuffer(Uint8Array, (nbits+32)*dspb*1.1), fsk.ts:149; utils.ts:14-18)
+  int ring_fractional;  // capacity is not an integer: literal emulation path
+  double ring_cap;      // maxLength as a JS number
+  int ring_cap_int;     // trunc(ring_cap) = typed-array length
+  int ring_words;       // integral path: power-of-two number of 32-bit words (>= total_bits+64 bits)
+                        // fractional path: ceil(ring_cap_int/32)
+  int amp_cap;          // dspb * 8 (fsk.ts:150)
+  // modulator (fsk.ts:389-424)
+  double mark, space, fs;
+  int n_preamble, n_sfd;
+  uint8_t preamble_sfd[32];
+};
+
+// Per-stream streaming state, struct-of-arrays: f64[k * n + stream], u32[k * n + stream].
+enum F64Field {
+  F_GAIN = 0, F_PX1, F_PX2, F_PY1, F_PY2, F_LO_PHASE,
+  F_IX1, F_IX2, F_IY1, F_IY2, F_QX1, F_QX2, F_QY1, F_QY2,
+  F_OX1, F_OX2, F_OY1, F_OY2, F_LAST_PHASE, F_IACC, F_QACC, F_SIL_THR,
+  F_RING_WI, F_RING_RI, F_RING_LEN,
+  F64_COUNT
+};
+enum U32Field {
+  U_DSC = 0, U_GSC, U_GMOD, U_BSC, U_NEXT_IDX, U_BIT_ACC, U_BIT_CNT, U_STARTED, U_BITPOS, U_CURRENT,
+  U_SIL_CNT, U_RING_POS, U_RING_LEN, U_AMP_POS, U_AMP_LEN, U_SYNC_DET, U_EOD_EV, U_ERR,
+  U32_COUNT
+};
+
+struct DemodArgs {
+  FskDerived d;
+  // streams of this config group
+  const int32_t* ids;   // global stream id per local index (nullptr: id = id0 + local)
+  int id0;
+  int n_local;          // streams in the group's state arrays (SoA stride)
+  int l_begin, l_end;   // local index range processed by this launch
+  int row_base;         // samples/out row of global stream id `row_base` is row 0
+  // state
+  double* f64;
+  uint32_t* u32;
+  uint32_t* sync_ring;  // [ring_words][n_local]
+  float* amp_ring;      // [amp_cap][n_local]
+  // data
+  float* samples;       // [rows][stride]
+  long stride;
+  long n;               // samples per stream this call
+  uint8_t* out;         // [rows][out_stride]
+  long out_stride;
+  int32_t* out_len;     // [rows]
+  float* tap;           // optional [rows][stride]
+};
+
+#define WAM_ERR_OUT_OVERFLOW 1u
+
+}  // namespace wam

@@ -1,0 +1,304 @@
+"""Host-side mirror of the reference's modulator interface for the FSK path.
+
+`FSKCore` keeps the reference's IModulator surface (src/core.ts:88-117; src/modems/fsk.ts:82-494):
+configure / getConfig / modulateData / demodulateData / reset / isReady / getStatus /
+getSignalQuality / on / off / emit, the same FSKConfig field names and defaults, the same
+"not configured" errors and the same 'configured' / 'eod' / 'error' events — but every sample is
+processed by libwam.so on the GPU through the C ABI in include/wam.h.  `FSKBatch` is the new
+batched entry point: thousands of independent streams with device-resident streaming state.
+
+The reference's host language is TypeScript; no Node toolchain exists in this image, so this
+Python class is the executable mirror used by the parity tests, and host/ holds the (unexecuted)
+TypeScript + N-API binding described in INTEGRATION.md.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable
+
+import numpy as np
+
+from . import _lib as L
+
+# src/modems/fsk.ts:19-33
+DEFAULT_FSK_CONFIG = dict(
+    sampleRate=48000,
+    baudRate=1200,
+    markFrequency=1650,
+    spaceFrequency=1850,
+    preamblePattern=[0x55, 0x55],
+    sfdPattern=[0x7E],
+    startBits=1,
+    stopBits=1,
+    parity="none",
+    syncThreshold=0.85,
+    agcEnabled=True,
+    preFilterBandwidth=800,
+    adaptiveThreshold=True,
+)
+# README-only aliases (README.md:33-38) accepted for convenience; the code's names win.
+_ALIASES = {"baud": "baudRate", "markFreq": "markFrequency", "spaceFreq": "spaceFrequency"}
+_PARITY = {"none": 0, "even": 1, "odd": 2}
+
+
+def normalize_config(cfg: dict | None) -> dict:
+    cfg = dict(cfg or {})
+    for k, v in list(cfg.items()):
+        if k in _ALIASES:
+            cfg.setdefault(_ALIASES[k], v)
+            del cfg[k]
+    return {**DEFAULT_FSK_CONFIG, **cfg}  # fsk.ts:134 — spread over defaults, no validation
+
+
+def config_struct(cfg: dict):
+    pre = (C.c_uint8 * max(1, len(cfg["preamblePattern"])))(*[int(b) & 0xFF for b in cfg["preamblePattern"]])
+    sfd = (C.c_uint8 * max(1, len(cfg["sfdPattern"])))(*[int(b) & 0xFF for b in cfg["sfdPattern"]])
+    s = L.FSKConfigStruct(
+        float(cfg["sampleRate"]), float(cfg["baudRate"]), float(cfg["markFrequency"]), float(cfg["spaceFrequency"]),
+        C.cast(pre, C.POINTER(C.c_uint8)), len(cfg["preamblePattern"]),
+        C.cast(sfd, C.POINTER(C.c_uint8)), len(cfg["sfdPattern"]),
+        int(cfg["startBits"]), int(cfg["stopBits"]), _PARITY[cfg["parity"]], float(cfg["syncThreshold"]),
+        1 if cfg["agcEnabled"] else 0, float(cfg["preFilterBandwidth"]), 1 if cfg["adaptiveThreshold"] else 0,
+    )
+    return s, (pre, sfd)
+
+
+def _status_dict(st: L.StatusStruct) -> dict:
+    return {
+        "ready": bool(st.ready),
+        "frameStarted": bool(st.frameStarted),
+        "globalSampleCounter": int(st.globalSampleCounter),
+        "receivedBitsLength": st.receivedBitsLength,
+        "byteBufferLength": int(st.byteBufferLength),
+        "demodulationCalls": int(st.demodulationCalls),
+        "syncDetections": int(st.syncDetections),
+        "silenceThreshold": st.silenceThreshold,
+        "totalSamplesProcessed": int(st.totalSamplesProcessed),
+        "eodEvents": int(st.eodEvents),
+    }
+
+
+class EventEmitter:
+    """src/core.ts EventEmitter: on / off / emit."""
+
+    def __init__(self):
+        self._listeners: dict[str, list[Callable]] = {}
+
+    def on(self, name: str, cb: Callable):
+        self._listeners.setdefault(name, []).append(cb)
+
+    def off(self, name: str, cb: Callable | None = None):
+        if cb is None:
+            self._listeners.pop(name, None)
+        elif name in self._listeners and cb in self._listeners[name]:
+            self._listeners[name].remove(cb)
+
+    def emit(self, name: str, event=None):
+        for cb in list(self._listeners.get(name, [])):
+            cb(event)
+
+
+class FSKCore(EventEmitter):
+    """GPU-backed drop-in for the reference FSKCore (one stream)."""
+
+    name = "FSK"
+    type = "FSK"
+
+    def __init__(self, device: int = 0):
+        super().__init__()
+        self._device = device
+        self._h = C.c_void_p()
+        self._config = None
+        self._keep = None
+        self._eod_seen = 0
+        self._lib = L.lib()
+        # created lazily so that `new FSKCore()` never touches CUDA before configure()
+
+    def _ensure(self):
+        if not self._h:
+            L.check(self._lib.wam_fsk_create(self._device, C.byref(self._h)))
+
+    def dispose(self):
+        if self._h:
+            self._lib.wam_fsk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.dispose()
+        except Exception:
+            pass
+
+    # -- configuration (fsk.ts:133-157) -------------------------------------------------------
+    def configure(self, config: dict | None = None):
+        self._ensure()
+        self._config = normalize_config(config)
+        s, self._keep = config_struct(self._config)
+        L.check(self._lib.wam_fsk_configure(self._h, C.byref(s)))
+        self.emit("configured")
+
+    def getConfig(self) -> dict:
+        return dict(self._config) if self._config is not None else {}
+
+    def isReady(self) -> bool:
+        return bool(self._h) and bool(self._lib.wam_fsk_is_ready(self._h))
+
+    # -- modulateData (fsk.ts:377-424) ---------------------------------------------------------
+    def modulateData(self, data) -> np.ndarray:
+        if not self.isReady():
+            raise RuntimeError("FSK modulator not configured")
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        n = self._lib.wam_fsk_modulate_size(self._h, len(buf))
+        L.check(n)
+        out = np.zeros(n, dtype=np.float32)
+        n_out = C.c_long(0)
+        L.check(self._lib.wam_fsk_modulate(
+            self._h, buf.ctypes.data_as(C.POINTER(C.c_uint8)) if len(buf) else None, len(buf),
+            out.ctypes.data_as(C.POINTER(C.c_float)), n, C.byref(n_out)))
+        return out
+
+    # -- demodulateData (fsk.ts:190-222) --------------------------------------------------------
+    def demodulateData(self, samples: np.ndarray) -> np.ndarray:
+        """`samples` (float32, contiguous) is mutated in place when AGC is on, like the reference."""
+        if not self.isReady():
+            raise RuntimeError("FSK demodulator not configured")
+        if not (isinstance(samples, np.ndarray) and samples.dtype == np.float32 and samples.flags.c_contiguous):
+            raise TypeError("samples must be a C-contiguous float32 numpy array (Float32Array)")
+        try:
+            cap = max(16, len(samples) // 8 + 16)
+            out = np.zeros(cap, dtype=np.uint8)
+            n_out = C.c_long(0)
+            L.check(self._lib.wam_fsk_demodulate(
+                self._h, samples.ctypes.data_as(C.POINTER(C.c_float)), len(samples),
+                out.ctypes.data_as(C.POINTER(C.c_uint8)), cap, C.byref(n_out)))
+            st = self._status()
+            new_eod = int(st.eodEvents) - self._eod_seen
+            self._eod_seen = int(st.eodEvents)
+            for _ in range(new_eod):
+                self.emit("eod")  # fsk.ts:289
+            return out[: n_out.value].copy()
+        except L.WamError as e:  # fsk.ts:218-221: errors become an event and an empty result
+            self.emit("error", {"data": e})
+            return np.zeros(0, dtype=np.uint8)
+
+    def reset(self):  # fsk.ts:464-469
+        if self._h:
+            L.check(self._lib.wam_fsk_reset(self._h))
+
+    def _status(self) -> L.StatusStruct:
+        st = L.StatusStruct()
+        L.check(self._lib.wam_fsk_status_get(self._h, C.byref(st)))
+        return st
+
+    def getStatus(self) -> dict:  # fsk.ts:481-493
+        if not self._h:
+            return {"ready": False, "frameStarted": False, "globalSampleCounter": 0, "receivedBitsLength": 0,
+                    "byteBufferLength": 0, "demodulationCalls": 0, "syncDetections": 0, "silenceThreshold": 0.01,
+                    "totalSamplesProcessed": 0, "eodEvents": 0}
+        return _status_dict(self._status())
+
+    def getSignalQuality(self) -> dict:  # fsk.ts:471-479 — the reference returns zeros
+        return {"snr": 0, "ber": 0, "eyeOpening": 0, "phaseJitter": 0, "frequencyOffset": 0}
+
+
+class FSKBatch:
+    """n_streams independent FSKCore instances on one GPU (wam_fsk_batch_*).
+
+    configs: one dict (all streams) or a list of dicts plus `cfg_index[stream]`.
+    """
+
+    def __init__(self, n_streams: int, configs, cfg_index=None, device: int = 0):
+        self._lib = L.lib()
+        if isinstance(configs, dict) or configs is None:
+            configs = [configs or {}]
+        self.configs = [normalize_config(c) for c in configs]
+        self.n_streams = int(n_streams)
+        self.device = device
+        structs = (L.FSKConfigStruct * len(self.configs))()
+        self._keep = []
+        for i, c in enumerate(self.configs):
+            s, k = config_struct(c)
+            structs[i] = s
+            self._keep.append(k)
+        idx = None
+        if cfg_index is not None:
+            idx = np.ascontiguousarray(cfg_index, dtype=np.int32)
+            assert idx.shape == (self.n_streams,)
+        self._h = C.c_void_p()
+        L.check(self._lib.wam_fsk_batch_create(device, self.n_streams, structs, len(self.configs),
+                                               idx.ctypes.data_as(C.POINTER(C.c_int32)) if idx is not None else None,
+                                               C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._lib.wam_fsk_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def out_capacity(self, n_samples: int) -> int:
+        return int(L.check(self._lib.wam_fsk_batch_out_capacity(self._h, n_samples)))
+
+    def reset(self):
+        L.check(self._lib.wam_fsk_batch_reset(self._h))
+
+    def launch_count(self) -> int:
+        return int(self._lib.wam_fsk_batch_launch_count(self._h))
+
+    # -- host buffers --------------------------------------------------------------------------
+    def demodulate(self, samples: np.ndarray, writeback_agc: bool = False):
+        """samples float32 [n_streams, n]; returns (out uint8 [n_streams, cap], out_len int32 [n_streams])."""
+        assert samples.dtype == np.float32 and samples.ndim == 2 and samples.shape[0] == self.n_streams
+        assert samples.strides[1] == 4
+        n = samples.shape[1]
+        cap = self.out_capacity(n)
+        out = np.zeros((self.n_streams, cap), dtype=np.uint8)
+        out_len = np.zeros(self.n_streams, dtype=np.int32)
+        L.check(self._lib.wam_fsk_batch_demodulate(
+            self._h, samples.ctypes.data, samples.strides[0] // 4, n, out.ctypes.data, cap, out_len.ctypes.data,
+            L.WAM_BATCH_WRITEBACK_AGC if writeback_agc else 0))
+        return out, out_len
+
+    def demodulate_bytes(self, samples: np.ndarray, writeback_agc: bool = False) -> list[bytes]:
+        out, out_len = self.demodulate(samples, writeback_agc)
+        return [bytes(out[i, : out_len[i]]) for i in range(self.n_streams)]
+
+    # -- device buffers (raw pointers, e.g. torch tensors' data_ptr()) --------------------------
+    def demodulate_device(self, d_samples: int, stride: int, n: int, d_out: int, out_stride: int, d_out_len: int,
+                          stream: int = 0, d_tap: int = 0, flags: int = 0):
+        L.check(self._lib.wam_fsk_batch_demodulate_device(self._h, d_samples, stride, n, d_out, out_stride, d_out_len,
+                                                          d_tap or None, stream or None, flags))
+
+    def modulate(self, data: np.ndarray, data_len=None) -> tuple[np.ndarray, np.ndarray]:
+        """data uint8 [n_streams, nbytes] → (samples float32 [n_streams, total], out_len)."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        assert data.ndim == 2 and data.shape[0] == self.n_streams
+        nbytes = data.shape[1]
+        c = self.configs[0]
+        spb = int(c["sampleRate"] // c["baudRate"])
+        bpb = 8 + c["startBits"] + c["stopBits"] + (0 if c["parity"] == "none" else 1)
+        total_bytes = len(c["preamblePattern"]) + len(c["sfdPattern"]) + nbytes
+        total = total_bytes * bpb * spb + (2 * spb if total_bytes > 0 else 0) + bpb * spb
+        out = np.zeros((self.n_streams, total), dtype=np.float32)
+        out_len = np.zeros(self.n_streams, dtype=np.int32)
+        dl = None
+        if data_len is not None:
+            dl = np.ascontiguousarray(data_len, dtype=np.int32)
+        L.check(self._lib.wam_fsk_batch_modulate(self._h, data.ctypes.data if nbytes else None, max(nbytes, 1),
+                                                 dl.ctypes.data if dl is not None else None, nbytes,
+                                                 out.ctypes.data, total, out_len.ctypes.data))
+        return out, out_len
+
+    def modulate_device(self, d_data: int, data_stride: int, nbytes: int, d_out: int, out_stride: int,
+                        d_out_len: int = 0, d_data_len: int = 0, stream: int = 0):
+        L.check(self._lib.wam_fsk_batch_modulate_device(self._h, d_data or None, data_stride, d_data_len or None, nbytes,
+                                                        d_out, out_stride, d_out_len or None, stream or None))
+
+    def status(self) -> list[dict]:
+        st = (L.StatusStruct * self.n_streams)()
+        L.check(self._lib.wam_fsk_batch_status(self._h, st))
+        return [_status_dict(st[i]) for i in range(self.n_streams)]
