@@ -127,6 +127,9 @@ int wam_fsk_batch_create(int device, long n_streams, const wam_fsk_config* cfgs,
                          const int32_t* cfg_index, wam_fsk_batch** out);
 int wam_fsk_batch_destroy(wam_fsk_batch* b);
 int wam_fsk_batch_reset(wam_fsk_batch* b);                   /* reset() on every stream */
+/* new FSKCore() + configure() on every stream again (fresh AGC, filters, rings, counters);
+ * asynchronous on cuda_stream. */
+int wam_fsk_batch_renew(wam_fsk_batch* b, void* cuda_stream);
 /* bytes of output capacity per stream that n_samples of input can never exceed */
 long wam_fsk_batch_out_capacity(wam_fsk_batch* b, long n_samples);
 

@@ -84,6 +84,7 @@ SYMBOLS = {
     "wam_fsk_batch_create": (C.c_int, [C.c_int, C.c_long, _cfgp, C.c_int, _i32p, C.POINTER(_vp)]),
     "wam_fsk_batch_destroy": (C.c_int, [_vp]),
     "wam_fsk_batch_reset": (C.c_int, [_vp]),
+    "wam_fsk_batch_renew": (C.c_int, [_vp, _vp]),
     "wam_fsk_batch_out_capacity": (C.c_long, [_vp, C.c_long]),
     "wam_fsk_batch_demodulate": (C.c_int, [_vp, _vp, C.c_long, C.c_long, _vp, C.c_long, _vp, C.c_uint32]),
     "wam_fsk_batch_demodulate_device": (C.c_int, [_vp, _vp, C.c_long, C.c_long, _vp, C.c_long, _vp, _vp, _vp, C.c_uint32]),

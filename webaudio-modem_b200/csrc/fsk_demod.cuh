@@ -3,21 +3,25 @@
 // Restates FSKCore.demodulateData (src/modems/fsk.ts:190-222) for thousands of independent
 // streams: one thread walks one stream in time and carries the whole reference state
 // (AGC gain, four biquads, LO phase, decimator, both rings, bit-sync / byte / silence state) in
-// registers; a warp owns 32 streams.  Samples are [stream][time] float32 in HBM; each warp stages
-// 32-stream x 32-sample tiles (one 128-byte line per stream) into shared memory with a
-// 3-deep cp.async pipeline, XOR-swizzled so that the row-per-lane LDS.128 reads are
-// bank-conflict free.  Arithmetic follows the reference's float64 pipeline with float32 only at
-// its Float32Array stores (fsk.ts:55, filters.ts:82-85, amplitude ring fsk.ts:150,282).
+// registers; a warp owns 32 streams and is its own CTA.  Samples are [stream][time] float32 in
+// HBM; each warp stages 32-stream x 32-sample tiles (one 128-byte line per stream) into shared
+// memory with a double-buffered cp.async pipeline, XOR-swizzled so that the row-per-lane LDS.128
+// reads are bank-conflict free.  Arithmetic is the reference's float64 pipeline with float32
+// only at its Float32Array stores (fsk.ts:55, filters.ts:82-85, amplitude ring fsk.ts:150,282).
 //
-// Stages inside the fused loop, with the reference lines they follow:
-//   AGC               fsk.ts:52-76      (non-linear recurrence, f64 gain, f32 store)
-//   pre-filter        filters.ts:47-87  (band-pass biquad DF-I, f32 output)
-//   LO mix            fsk.ts:228-232    (phase accumulates exactly like the reference; cos/sin
-//                                        re-anchored with sincos() every tile and advanced by a
-//                                        rotation in between)
-//   I/Q low-pass      filters.ts:47-76
-//   /2 decimation, atan2, amplitude, wrapped phase difference, post low-pass, slicer fsk.ts:241-264
-//   rings, silence/EOD, sync search, majority-vote bit sampler, UART framing  fsk.ts:278-375
+// Every tile is processed in three phases so that the floating-point work is branch-free:
+//   A1  AGC (fsk.ts:52-76: non-linear gain recurrence, f64 gain, f32 store) and the band-pass
+//       pre-filter (filters.ts:47-87, f32 output) over the 32 samples -> pf[i][lane] in smem;
+//   A2  LO mix (fsk.ts:228-232), I/Q low-pass biquads, /2 boxcar decimation, atan2, wrapped phase
+//       difference, post low-pass and slicer (fsk.ts:241-264) -> 16 hard bits (a register mask)
+//       and 16 squared magnitudes in smem;
+//   B   the decimated-rate state machine (fsk.ts:278-375): ring puts, silence/EOD, sync search,
+//       majority-vote bit sampler, UART framing.
+// resetState() (fsk.ts:175-188; on EOD or a bad start bit) zeroes the A2 state from inside B.  It is
+// rare (about once per frame), so B reports the decimated index of the reset and A2 is REPLAYED
+// for the rest of the tile from the zeroed state; A1 (AGC, pre-filter) is never reset and never
+// replayed.  The result is the reference's exact causal order without a data-dependent branch in
+// the per-sample arithmetic.
 #pragma once
 
 #include "wam_common.cuh"
@@ -147,16 +151,16 @@ __device__ __forceinline__ void ring_put_fractional(LaneState& s, uint32_t* ring
   if (s.ring_flen < d.ring_cap) s.ring_flen += 1.0;
   else s.ring_ri = ring_fmod_cap(s.ring_ri + 1.0, d.ring_cap);
 }
-__device__ __noinline__ int sync_matched_fractional(const LaneState& s, const uint32_t* __restrict__ ring, long ns,
-                                                    const FskDerived& d) {
+__device__ __noinline__ int sync_matched_fractional(double ring_ri, double ring_flen, const uint32_t* __restrict__ ring,
+                                                    long ns, const FskDerived& d) {
   int matched = 0;
   int remaining = d.nbits * d.dspb;
   for (int j = 0; j < d.nbits; ++j) {
     const int pb = d.nbits - j;
     const int expect = (j == 0) ? 0 : (d.pattern[pb >> 5] >> (pb & 31)) & 1;
     for (int k = 0; k < d.dspb; ++k) {
-      const double idx = s.ring_flen - (double)(j * d.dspb + k) - 1.0;
-      const double p = ring_fmod_cap(s.ring_ri + idx, d.ring_cap);
+      const double idx = ring_flen - (double)(j * d.dspb + k) - 1.0;
+      const double p = ring_fmod_cap(ring_ri + idx, d.ring_cap);
       int ip;
       const bool valid = ring_index_valid(p, d.ring_cap_int, ip);
       if (j == 0) {
@@ -172,18 +176,18 @@ __device__ __noinline__ int sync_matched_fractional(const LaneState& s, const ui
   return matched;
 }
 
-// FSKCore.processByte — fsk.ts:346-375
-__device__ __forceinline__ void process_byte(LaneState& s, int bit, const FskDerived& d, uint8_t* out_row,
+// FSKCore.processByte — fsk.ts:346-375.  Returns true when resetState() ran.
+__device__ __forceinline__ bool process_byte(LaneState& s, int bit, const FskDerived& d, uint8_t* out_row,
                                              long out_cap) {
   const int bp = s.bitpos;
   if (bp == 0) {
-    if (bit != 0) { reset_state(s); return; }
+    if (bit != 0) { reset_state(s); return true; }
   } else if (bp >= 1 && bp <= 8) {
     s.current |= (uint32_t)bit << (8 - bp);
   } else if (d.parity != 0 && bp == 9) {
     // parity bit is skipped, never checked
   } else if (bp == d.stop_pos) {
-    if (bit != 1) { s.started = 0; return; }
+    if (bit != 1) { s.started = 0; return false; }
     if (s.out_n < out_cap) out_row[s.out_n] = (uint8_t)s.current;
     else s.err |= WAM_ERR_OUT_OVERFLOW;
     s.out_n++;
@@ -191,13 +195,26 @@ __device__ __forceinline__ void process_byte(LaneState& s, int bit, const FskDer
     s.bitpos = -1;
   } else {
     s.started = 0;
-    return;
+    return false;
   }
   s.bitpos++;
+  return false;
 }
 
-// FSKCore.processDownsampledBit — fsk.ts:278-344
-__device__ __forceinline__ void process_downsampled_bit(LaneState& s, int bit, double amplitude, const DemodArgs& a,
+// silence threshold = mean(amplitude ring) * 0.1, summed oldest -> newest in f64 — fsk.ts:321-326
+__device__ __noinline__ double amp_ring_threshold(const float* __restrict__ aring, long ns, uint32_t amp_pos,
+                                                  uint32_t amp_len, uint32_t amp_cap) {
+  double sum = 0.0;
+  uint32_t slot = (amp_pos + amp_cap - amp_len) % amp_cap;
+  for (uint32_t i = 0; i < amp_len; ++i) {
+    sum += (double)aring[(long)slot * ns];
+    slot = (slot + 1u == amp_cap) ? 0u : slot + 1u;
+  }
+  return (sum / (double)amp_len) * 0.1;
+}
+
+// FSKCore.processDownsampledBit — fsk.ts:278-344.  Returns true when resetState() ran.
+__device__ __forceinline__ bool process_downsampled_bit(LaneState& s, int bit, double amplitude, const DemodArgs& a,
                                                         int li, uint8_t* out_row) {
   const FskDerived& d = a.d;
   const long ns = a.n_local;
@@ -212,14 +229,14 @@ __device__ __forceinline__ void process_downsampled_bit(LaneState& s, int bit, d
       ring[(long)(((s.ring_pos - 1u) >> 5) & (uint32_t)(d.ring_words - 1)) * ns] = s.cur_word;
       s.cur_word = 0u;
     }
-    if (s.ring_len < (uint32_t)d.ring_cap_int) s.ring_len++;
+    s.ring_len = min(s.ring_len + 1u, (uint32_t)d.ring_cap_int);
   } else {
     ring_put_fractional(s, ring, ns, bit, d);
   }
   // syncAmplitudeBuffer.put(amplitude) — fsk.ts:282 (Float32Array store)
   aring[(long)s.amp_pos * ns] = (float)amplitude;
   s.amp_pos = (s.amp_pos + 1u == (uint32_t)d.amp_cap) ? 0u : s.amp_pos + 1u;
-  if (s.amp_len < (uint32_t)d.amp_cap) s.amp_len++;
+  s.amp_len = min(s.amp_len + 1u, (uint32_t)d.amp_cap);
 
   // silence / EOD — fsk.ts:285-295
   s.gsc++;
@@ -229,7 +246,7 @@ __device__ __forceinline__ void process_downsampled_bit(LaneState& s, int bit, d
     if (s.sil_cnt >= (uint32_t)d.eod_count) {
       s.eod_ev++;
       reset_state(s);
-      return;
+      return true;
     }
   } else {
     s.sil_cnt = 0;
@@ -246,121 +263,107 @@ __device__ __forceinline__ void process_downsampled_bit(LaneState& s, int bit, d
           ring[(long)((s.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns] = s.cur_word;  // flush partial word
         matched = sync_matched_integral(ring, ns, s.ring_pos, d);
       } else {
-        matched = sync_matched_fractional(s, ring, ns, d);
+        matched = sync_matched_fractional(s.ring_ri, s.ring_flen, ring, ns, d);
       }
       if (matched >= d.min_matched) {
         s.started = 1;
         s.current = 0; s.bitpos = 0;
         s.bit_acc = 0; s.bit_cnt = 0; s.bsc = 0; s.next_idx = 0;
         s.sync_det++;
-        // silence threshold = mean(amplitude ring) * 0.1, summed oldest -> newest — fsk.ts:321-326
-        double sum = 0.0;
-        uint32_t slot = (s.amp_pos + (uint32_t)d.amp_cap - s.amp_len) % (uint32_t)d.amp_cap;
-        for (uint32_t i = 0; i < s.amp_len; ++i) {
-          sum += (double)aring[(long)slot * ns];
-          slot = (slot + 1u == (uint32_t)d.amp_cap) ? 0u : slot + 1u;
-        }
-        s.sil_thr = (sum / (double)s.amp_len) * 0.1;
+        s.sil_thr = amp_ring_threshold(aring, ns, s.amp_pos, s.amp_len, (uint32_t)d.amp_cap);
       }
     }
-  } else {
-    // fsk.ts:330-341
-    s.bit_acc += (uint32_t)bit;
-    s.bit_cnt++;
-    s.bsc++;
-    if (s.bsc >= s.next_idx) {
-      const int decided = (2u * s.bit_acc > s.bit_cnt) ? 1 : 0;  // acc > count/2
-      s.bit_acc = 0; s.bit_cnt = 0;
-      s.next_idx += (uint32_t)d.dspb;
-      process_byte(s, decided, d, out_row, a.out_stride);
-    }
+    return false;
   }
+  // fsk.ts:330-341
+  s.bit_acc += (uint32_t)bit;
+  s.bit_cnt++;
+  s.bsc++;
+  if (s.bsc >= s.next_idx) {
+    const int decided = (2u * s.bit_acc > s.bit_cnt) ? 1 : 0;  // acc > count/2
+    s.bit_acc = 0; s.bit_cnt = 0;
+    s.next_idx += (uint32_t)d.dspb;
+    return process_byte(s, decided, d, out_row, a.out_stride);
+  }
+  return false;
 }
 
-// One input sample through AGC, pre-filter, LO mix, I/Q filters, decimator (+ everything at the
-// decimated rate every second sample).  Returns the AGC-scaled sample (for write-back).
-template <bool TAP>
-__device__ __forceinline__ float process_sample(LaneState& s, float x, const DemodArgs& a, int li, uint8_t* out_row,
-                                                float* tap_ptr) {
-  const FskDerived& d = a.d;
-  const double kTwoPi = 6.283185307179586;  // 2 * Math.PI
-  const double kPi = 3.141592653589793;
+// ---- phase A1: AGC + pre-filter for one sample -------------------------------------------------
+// 1 / (2 * level) to ~1e-14 relative: MUFU.RCP seed + one Newton step in f64.  (The reference
+// divides in f64; the gain recurrence is a contraction, so an error this size is invisible next to
+// the float32 store of fsk.ts:55 — see DESIGN.md "numerics".)
+__device__ __forceinline__ double agc_target(float level) {
+  const float l2 = fmaxf(level + level, 1e-30f);
+  float r0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(l2));
+  const double r = (double)r0;
+  const double e = fma(-(double)l2, r, 1.0);
+  return fma(r, e, r);
+}
 
-  // ---- AGC — fsk.ts:52-76
+__device__ __forceinline__ float phase_a1_sample(LaneState& s, float x, const FskDerived& d, float& agc_out) {
   float sg = x;
-  if (d.agc_enabled) {
+  if (d.agc_enabled) {  // fsk.ts:52-76
     sg = (float)((double)x * s.gain);
-    const double level = fabs((double)sg);
-    if (level > 0.5) {
-      const double target = 0.5 / level;
-      s.gain += (target - s.gain) * d.agc_attack;
-    } else if (level > 0.0) {
-      const double target = 0.5 / level;
-      s.gain += (target - s.gain) * d.agc_release;
-    }
-    s.gain = fmax(0.1, fmin(10.0, s.gain));
+    const float level = fabsf(sg);
+    const double target = agc_target(level);
+    const double rate = level > 0.5f ? d.agc_attack : d.agc_release;
+    double g = fma(target - s.gain, rate, s.gain);
+    g = g > 10.0 ? 10.0 : g;
+    g = g < 0.1 ? 0.1 : g;
+    s.gain = level > 0.0f ? g : s.gain;
   }
-
-  // ---- pre-filter (DF-I, accumulation order of filters.ts:52-66), Float32Array output
+  agc_out = sg;
+  // pre-filter: butterworthBandpass has b1 == 0 and b2 == -b0 exactly (filters.ts:230)
   const double xin = (double)sg;
-  double y = d.pre_b0 * xin;
-  y += d.pre_b1 * s.px1;
-  y += d.pre_b2 * s.px2;
-  y -= d.pre_a1 * s.py1;
-  y -= d.pre_a2 * s.py2;
+  double y = d.pre_b0 * (xin - s.px2);
+  y = fma(-d.pre_a1, s.py1, y);
+  y = fma(-d.pre_a2, s.py2, y);
   s.px2 = s.px1; s.px1 = xin; s.py2 = s.py1; s.py1 = y;
-  const float pf = (float)y;
-  if (TAP) *tap_ptr = pf;
+  return (float)y;  // Float32Array store of processBuffer (filters.ts:82-85)
+}
 
-  // ---- LO mix — fsk.ts:228-232
+// ---- phase A2: one input sample through LO mix and the I/Q low-pass filters --------------------
+// butterworthLowpass has b1 == 2*b0 and b2 == b0 exactly (filters.ts:188).
+__device__ __forceinline__ void phase_a2_half(LaneState& s, float pf, const FskDerived& d, double& yi, double& yq) {
   const double smp = (double)pf;
-  const double xi = smp * s.lo_c;
+  const double xi = smp * s.lo_c;  // fsk.ts:229-230 (cos/sin of the pre-increment phase)
   const double xq = smp * s.lo_s;
-  double ph = s.lo_phase + d.omega;
-  if (ph >= kTwoPi) ph -= kTwoPi;  // (phase + omega) % 2pi, exact for 0 <= omega < 2pi
-  s.lo_phase = ph;
   const double nc = s.lo_c * d.cos_omega - s.lo_s * d.sin_omega;
   const double nsn = s.lo_s * d.cos_omega + s.lo_c * d.sin_omega;
   s.lo_c = nc; s.lo_s = nsn;
-
-  // ---- I/Q low-pass biquads
-  double yi = d.lp_b0 * xi;
-  yi += d.lp_b1 * s.ix1;
-  yi += d.lp_b2 * s.ix2;
-  yi -= d.lp_a1 * s.iy1;
-  yi -= d.lp_a2 * s.iy2;
+  double ui = xi + s.ix2;
+  ui = fma(2.0, s.ix1, ui);
+  yi = d.lp_b0 * ui;
+  yi = fma(-d.lp_a1, s.iy1, yi);
+  yi = fma(-d.lp_a2, s.iy2, yi);
   s.ix2 = s.ix1; s.ix1 = xi; s.iy2 = s.iy1; s.iy1 = yi;
-  double yq = d.lp_b0 * xq;
-  yq += d.lp_b1 * s.qx1;
-  yq += d.lp_b2 * s.qx2;
-  yq -= d.lp_a1 * s.qy1;
-  yq -= d.lp_a2 * s.qy2;
+  double uq = xq + s.qx2;
+  uq = fma(2.0, s.qx1, uq);
+  yq = d.lp_b0 * uq;
+  yq = fma(-d.lp_a1, s.qy1, yq);
+  yq = fma(-d.lp_a2, s.qy2, yq);
   s.qx2 = s.qx1; s.qx1 = xq; s.qy2 = s.qy1; s.qy1 = yq;
+}
 
-  // ---- /2 boxcar decimation — fsk.ts:241-245
-  s.iacc += yi;
-  s.qacc += yq;
-  s.dsc++;
-  if (s.dsc >= 2u) {
-    const double avg_i = s.iacc * 0.5;
-    const double avg_q = s.qacc * 0.5;
-    const double phase = atan2(avg_q, avg_i);
-    const double amplitude = sqrt(avg_i * avg_i + avg_q * avg_q);
-    double pd = phase - s.last_phase;
-    if (pd > kPi) pd -= kTwoPi;
-    else if (pd < -kPi) pd += kTwoPi;
-    s.last_phase = phase;
-    double yo = d.lp_b0 * pd;
-    yo += d.lp_b1 * s.ox1;
-    yo += d.lp_b2 * s.ox2;
-    yo -= d.lp_a1 * s.oy1;
-    yo -= d.lp_a2 * s.oy2;
-    s.ox2 = s.ox1; s.ox1 = pd; s.oy2 = s.oy1; s.oy1 = yo;
-    const int bit = yo > 0.0 ? 1 : 0;
-    s.iacc = 0.0; s.qacc = 0.0; s.dsc = 0;
-    process_downsampled_bit(s, bit, amplitude, a, li, out_row);
-  }
-  return sg;
+// decimated-rate discriminator (fsk.ts:246-264) on the summed pair (2*avgI, 2*avgQ): returns the
+// hard bit, and the squared magnitude whose root is twice the reference amplitude.
+__device__ __forceinline__ int phase_a2_decim(LaneState& s, double si, double sq, const FskDerived& d, double& p) {
+  const double kTwoPi = 6.283185307179586;  // 2 * Math.PI
+  const double kPi = 3.141592653589793;
+  const double phase = atan2(sq, si);       // atan2(avgQ, avgI): scale invariant
+  p = __dadd_rn(__dmul_rn(si, si), __dmul_rn(sq, sq));
+  double pd = phase - s.last_phase;
+  if (pd > kPi) pd -= kTwoPi;
+  else if (pd < -kPi) pd += kTwoPi;
+  s.last_phase = phase;
+  double uo = pd + s.ox2;
+  uo = fma(2.0, s.ox1, uo);
+  double yo = d.lp_b0 * uo;
+  yo = fma(-d.lp_a1, s.oy1, yo);
+  yo = fma(-d.lp_a2, s.oy2, yo);
+  s.ox2 = s.ox1; s.ox1 = pd; s.oy2 = s.oy1; s.oy1 = yo;
+  return yo > 0.0 ? 1 : 0;
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
@@ -384,24 +387,22 @@ __device__ __forceinline__ int tile_index(int row, int col) {
 
 // Stage one 32-stream x 32-sample tile starting at sample t0 into `tile`.
 template <bool ALIGNED>
-__device__ __forceinline__ void stage_tile(float* tile, const DemodArgs& a, const long* row_of_lane_smem, long t0,
-                                           int lane) {
+__device__ __forceinline__ void stage_tile(float* tile, const DemodArgs& a, const long* rows, long t0, int lane) {
   if (ALIGNED) {
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int r = it * 4 + (lane >> 3);
       const int c = (lane & 7) * 4;
-      const long row = row_of_lane_smem[r];
-      long remain = a.n - (t0 + c);
-      int bytes = row < 0 ? 0 : (remain >= 4 ? 16 : (remain > 0 ? (int)remain * 4 : 0));
-      const float* src = a.samples + (row < 0 ? 0 : row * a.stride + t0 + (bytes ? c : 0));
-      if (row < 0 || bytes == 0) src = a.samples;
+      const long row = rows[r];
+      const long remain = a.n - (t0 + c);
+      const int bytes = (row < 0 || remain <= 0) ? 0 : (remain >= 4 ? 16 : (int)remain * 4);
+      const float* src = bytes ? a.samples + row * a.stride + t0 + c : a.samples;
       cp_async16(tile + tile_index(r, c), src, bytes);
     }
   } else {
 #pragma unroll 4
     for (int r = 0; r < 32; ++r) {
-      const long row = row_of_lane_smem[r];
+      const long row = rows[r];
       const int bytes = (row >= 0 && t0 + lane < a.n) ? 4 : 0;
       const float* src = bytes ? a.samples + row * a.stride + t0 + lane : a.samples;
       cp_async4(tile + tile_index(r, lane), src, bytes);
@@ -411,8 +412,11 @@ __device__ __forceinline__ void stage_tile(float* tile, const DemodArgs& a, cons
 
 // Grid: one warp (32 streams) per CTA, so that 2048 warps spread evenly over 148 SMs.
 template <bool ALIGNED, bool WRITEBACK, bool TAP>
-__global__ void __launch_bounds__(32) fsk_demod_exact_kernel(const __grid_constant__ DemodArgs a) {
+__global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kernel(const __grid_constant__ DemodArgs a) {
+  // stage buffers: input tile (swizzled f32 [32][32]); after A1 the same 4 KiB hold the squared
+  // magnitudes of the tile as f64 [16][32]
   __shared__ __align__(128) float tiles[kStages][kTile * kTile];
+  __shared__ __align__(128) float pfbuf[kTile * 32];  // pre-filtered samples [i][lane]
   __shared__ long rows[32];
 
   const int lane = threadIdx.x;
@@ -423,23 +427,24 @@ __global__ void __launch_bounds__(32) fsk_demod_exact_kernel(const __grid_consta
   rows[lane] = row;
   __syncwarp();
 
+  const FskDerived& d = a.d;
   LaneState s;
   if (active) {
     lane_load(s, a, li);
-    // (cos, sin) of the carried LO phase; exact (1, 0) after a reset
-    sincos(s.lo_phase, &s.lo_s, &s.lo_c);
-    if (s.lo_phase == 0.0) { s.lo_c = 1.0; s.lo_s = 0.0; }
+    sincos(s.lo_phase, &s.lo_s, &s.lo_c);  // exact (1, 0) for the post-reset phase 0
     s.cur_word = 0u;
-    if (!a.d.ring_fractional && (s.ring_pos & 31u) != 0u) {
-      const uint32_t w = a.sync_ring[(long)((s.ring_pos >> 5) & (uint32_t)(a.d.ring_words - 1)) * a.n_local + li];
+    if (!d.ring_fractional && (s.ring_pos & 31u) != 0u) {
+      const uint32_t w = a.sync_ring[(long)((s.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * a.n_local + li];
       s.cur_word = w & ((1u << (s.ring_pos & 31u)) - 1u);
     }
   }
   uint8_t* out_row = active ? a.out + row * a.out_stride : nullptr;
+  float* wb_row = ((WRITEBACK || TAP) && active) ? (WRITEBACK ? a.samples : a.tap) + row * a.stride : nullptr;
   float* tap_row = (TAP && active) ? a.tap + row * a.stride : nullptr;
+  (void)wb_row;
 
+  const double kTwoPi = 6.283185307179586;
   const long n_tiles = (a.n + kTile - 1) / kTile;
-  // prologue
   for (int p = 0; p < kStages - 1; ++p) {
     if (p < n_tiles) stage_tile<ALIGNED>(tiles[p], a, rows, (long)p * kTile, lane);
     cp_async_commit();
@@ -451,51 +456,90 @@ __global__ void __launch_bounds__(32) fsk_demod_exact_kernel(const __grid_consta
     cp_async_wait<kStages - 1>();
     __syncwarp();
     float* tile = tiles[t % kStages];
+    double* pbuf = reinterpret_cast<double*>(tile);  // [k][lane] after A1
     const long t0 = t * kTile;
+    const int len = (int)min((long)kTile, a.n - t0);
+
+    // ---------------- A1: AGC + pre-filter ----------------
     if (active) {
-      // re-anchor the LO rotation on the exactly-accumulated phase once per tile
-      if (t != 0) sincos(s.lo_phase, &s.lo_s, &s.lo_c);
-      const bool full = (t0 + kTile <= a.n);
 #pragma unroll 1
       for (int ch = 0; ch < 8; ++ch) {
-        float4* p4 = reinterpret_cast<float4*>(tile + tile_index(lane, ch * 4));
-        float4 v = *p4;
-        float xs[4] = {v.x, v.y, v.z, v.w};
+        const float4 v = *reinterpret_cast<const float4*>(tile + tile_index(lane, ch * 4));
+        const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const long tt = t0 + ch * 4 + k;
-          if (full || tt < a.n) xs[k] = process_sample<TAP>(s, xs[k], a, li, out_row, TAP ? tap_row + tt : nullptr);
+          const int i = ch * 4 + k;
+          if (i < len) {
+            float sg;
+            const float pf = phase_a1_sample(s, xs[k], d, sg);
+            pfbuf[i * 32 + lane] = pf;
+            if (WRITEBACK) a.samples[row * a.stride + t0 + i] = sg;  // fsk.ts:55 mutates the input
+            if (TAP) tap_row[t0 + i] = pf;
+          }
         }
-        if (WRITEBACK) *p4 = make_float4(xs[0], xs[1], xs[2], xs[3]);
+      }
+    }
+    __syncwarp();  // every lane is done with the input tile; its storage becomes pbuf
+
+    // ---------------- A2 + B with replay on resetState() ----------------
+    // virtual sample index v = i + dsc0; pair k = v >> 1; a pair's second half emits decimated k.
+    const int dsc0 = active ? (int)s.dsc : 0;
+    const int v_hi = dsc0 + len;
+    const int nk = v_hi >> 1;       // decimated outputs completed inside this tile
+    int k_from = 0;                 // first pair A2 has to (re)compute
+    int b_from = 0;                 // first decimated output B has to consume
+    int v_lo = dsc0;                // first virtual sample present
+    uint32_t bits = 0u;
+    bool redo = active;
+    while (__any_sync(0xffffffffu, redo)) {
+      if (redo) {
+        // re-anchor the LO rotation on the accumulated phase (start of tile / after a reset)
+        if (v_lo == dsc0 && t != 0) sincos(s.lo_phase, &s.lo_s, &s.lo_c);
+#pragma unroll 1
+        for (int k = k_from; 2 * k < v_hi; ++k) {
+          const int v0 = 2 * k, v1 = 2 * k + 1;
+          double yi, yq;
+          if (v0 >= v_lo) {
+            phase_a2_half(s, pfbuf[(v0 - dsc0) * 32 + lane], d, yi, yq);
+            s.iacc = yi; s.qacc = yq;  // 0 + y
+          }
+          if (v1 < v_hi) {
+            phase_a2_half(s, pfbuf[(v1 - dsc0) * 32 + lane], d, yi, yq);
+            double pp;
+            const int bit = phase_a2_decim(s, s.iacc + yi, s.qacc + yq, d, pp);
+            s.iacc = 0.0; s.qacc = 0.0;
+            bits = (bits & ~(1u << k)) | ((uint32_t)bit << k);
+            pbuf[k * 32 + lane] = pp;
+          }
+        }
+        // LO phase bookkeeping: (phase + omega) % 2pi per sample in the reference (fsk.ts:232)
+        {
+          double ph = s.lo_phase + (double)(v_hi - v_lo) * d.omega;
+          ph -= kTwoPi * floor(ph / kTwoPi);
+          s.lo_phase = ph;
+        }
+        s.dsc = (uint32_t)(v_hi & 1);
+        // ---------------- B ----------------
+        redo = false;
+#pragma unroll 1
+        for (int k = b_from; k < nk; ++k) {
+          const double amplitude = 0.5 * sqrt(pbuf[k * 32 + lane]);
+          if (process_downsampled_bit(s, (int)((bits >> k) & 1u), amplitude, a, li, out_row)) {
+            // resetState(): A2 restarts from the zeroed state at the next pair
+            k_from = k + 1; b_from = k + 1; v_lo = 2 * (k + 1);
+            redo = (v_lo < v_hi);
+            break;
+          }
+        }
       }
     }
     __syncwarp();
-    if (WRITEBACK) {
-      // cooperative, coalesced copy of the AGC-scaled tile back to the caller's buffer (fsk.ts:55)
-      for (int it = 0; it < 8; ++it) {
-        const int r = it * 4 + (lane >> 3);
-        const int c = (lane & 7) * 4;
-        const long rr = rows[r];
-        if (rr < 0) continue;
-        const float4 v = *reinterpret_cast<const float4*>(tile + tile_index(r, c));
-        float* dst = a.samples + rr * a.stride + t0 + c;
-        const long remain = a.n - (t0 + c);
-        if (ALIGNED && remain >= 4) {
-          *reinterpret_cast<float4*>(dst) = v;
-        } else {
-          const float vv[4] = {v.x, v.y, v.z, v.w};
-          for (int k = 0; k < 4; ++k)
-            if (k < remain) dst[k] = vv[k];
-        }
-      }
-      __syncwarp();
-    }
   }
   cp_async_wait<0>();
 
   if (active) {
-    if (!a.d.ring_fractional && (s.ring_pos & 31u) != 0u)
-      a.sync_ring[(long)((s.ring_pos >> 5) & (uint32_t)(a.d.ring_words - 1)) * a.n_local + li] = s.cur_word;
+    if (!d.ring_fractional && (s.ring_pos & 31u) != 0u)
+      a.sync_ring[(long)((s.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * a.n_local + li] = s.cur_word;
     lane_store(s, a, li);
     a.out_len[row] = s.out_n < a.out_stride ? s.out_n : (int)a.out_stride;
   }

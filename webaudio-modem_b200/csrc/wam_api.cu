@@ -280,6 +280,10 @@ struct wam_fsk_batch {
   long launches = 0;
   // staging for the HOST-buffer entry points
   cudaStream_t streams[2] = {nullptr, nullptr};
+  // concurrent launch of the per-configuration groups: fork/join around auxiliary streams
+  std::vector<cudaStream_t> aux_streams;
+  std::vector<cudaEvent_t> aux_done;
+  cudaEvent_t fork_ev = nullptr;
   float* stage_samples[2] = {nullptr, nullptr};
   uint8_t* stage_out[2] = {nullptr, nullptr};
   int32_t* stage_len[2] = {nullptr, nullptr};
@@ -295,16 +299,23 @@ struct wam_fsk_batch {
   size_t mod_len_bytes = 0;
 };
 
-static int init_group_state(Group& g) {
+__global__ void fill_f64_kernel(double* p, double v, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// State of freshly constructed + configured FSKCore instances, stream-ordered.
+static int init_group_state(Group& g, cudaStream_t st) {
   const size_t n = g.ids.size();
-  CUDA_TRY(cudaMemset(g.f64, 0, sizeof(double) * F64_COUNT * n));
-  CUDA_TRY(cudaMemset(g.u32, 0, sizeof(uint32_t) * U32_COUNT * n));
-  CUDA_TRY(cudaMemset(g.sync_ring, 0, sizeof(uint32_t) * (size_t)g.d.ring_words * n));
-  CUDA_TRY(cudaMemset(g.amp_ring, 0, sizeof(float) * (size_t)g.d.amp_cap * n));
+  CUDA_TRY(cudaMemsetAsync(g.f64, 0, sizeof(double) * F64_COUNT * n, st));
+  CUDA_TRY(cudaMemsetAsync(g.u32, 0, sizeof(uint32_t) * U32_COUNT * n, st));
+  CUDA_TRY(cudaMemsetAsync(g.sync_ring, 0, sizeof(uint32_t) * (size_t)g.d.ring_words * n, st));
+  CUDA_TRY(cudaMemsetAsync(g.amp_ring, 0, sizeof(float) * (size_t)g.d.amp_cap * n, st));
   // AGC gain 1.0 (fsk.ts:46), silence threshold 0.01 (fsk.ts:128)
-  std::vector<double> ones(n, 1.0), thr(n, 0.01);
-  CUDA_TRY(cudaMemcpy(g.f64 + (size_t)F_GAIN * n, ones.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(g.f64 + (size_t)F_SIL_THR * n, thr.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  fill_f64_kernel<<<blocks, 256, 0, st>>>(g.f64 + (size_t)F_GAIN * n, 1.0, (long)n);
+  fill_f64_kernel<<<blocks, 256, 0, st>>>(g.f64 + (size_t)F_SIL_THR * n, 0.01, (long)n);
+  CUDA_TRY(cudaGetLastError());
   return WAM_OK;
 }
 
@@ -314,6 +325,9 @@ static void free_batch(wam_fsk_batch* b) {
   for (auto& g : b->groups) {
     cudaFree(g.d_ids); cudaFree(g.f64); cudaFree(g.u32); cudaFree(g.sync_ring); cudaFree(g.amp_ring);
   }
+  for (auto st : b->aux_streams) cudaStreamDestroy(st);
+  for (auto ev : b->aux_done) cudaEventDestroy(ev);
+  if (b->fork_ev) cudaEventDestroy(b->fork_ev);
   for (int i = 0; i < 2; i++) {
     if (b->streams[i]) cudaStreamDestroy(b->streams[i]);
     cudaFree(b->stage_samples[i]); cudaFree(b->stage_out[i]); cudaFree(b->stage_len[i]);
@@ -372,14 +386,41 @@ extern "C" int wam_fsk_batch_create(int device, long n_streams, const wam_fsk_co
       free_batch(b);
       return fail(e == cudaErrorMemoryAllocation ? WAM_E_NOMEM : WAM_E_CUDA, std::string("state allocation: ") + cudaGetErrorString(e));
     }
-    int rc = init_group_state(g);
+    int rc = init_group_state(g, nullptr);
     if (rc != WAM_OK) { free_batch(b); return rc; }
   }
+  CUDA_TRY(cudaDeviceSynchronize());
   for (int i = 0; i < 2; i++) {
     cudaError_t e = cudaStreamCreateWithFlags(&b->streams[i], cudaStreamNonBlocking);
     if (e != cudaSuccess) { free_batch(b); return fail(WAM_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
   }
+  {
+    size_t live = 0;
+    for (auto& g : b->groups) live += g.ids.empty() ? 0 : 1;
+    cudaError_t e = cudaEventCreateWithFlags(&b->fork_ev, cudaEventDisableTiming);
+    for (size_t i = 1; i < live && e == cudaSuccess; i++) {
+      cudaStream_t st; cudaEvent_t ev;
+      e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+      if (e == cudaSuccess) { b->aux_streams.push_back(st); e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); }
+      if (e == cudaSuccess) b->aux_done.push_back(ev);
+    }
+    if (e != cudaSuccess) { free_batch(b); return fail(WAM_E_CUDA, std::string("stream/event creation: ") + cudaGetErrorString(e)); }
+  }
   *out = b;
+  return WAM_OK;
+}
+
+// new FSKCore() + configure(cfg) on every stream again: fresh AGC, filters, rings, counters.
+extern "C" int wam_fsk_batch_renew(wam_fsk_batch* b, void* cuda_stream) {
+  if (!b) return fail(WAM_E_INVALID, "batch is NULL");
+  CUDA_TRY(cudaSetDevice(b->device));
+  for (auto& g : b->groups) {
+    if (g.ids.empty()) continue;
+    int rc = init_group_state(g, (cudaStream_t)cuda_stream);
+    if (rc != WAM_OK) return rc;
+  }
+  b->demodulation_calls = 0;
+  b->total_samples = 0;
   return WAM_OK;
 }
 
@@ -435,11 +476,22 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
   const bool aligned = ((reinterpret_cast<uintptr_t>(d_samples) & 15) == 0) && (stride % 4 == 0);
   const bool wb = (flags & WAM_BATCH_WRITEBACK_AGC) != 0;
   const bool tap = (flags & WAM_BATCH_TAP_PREFILTER) != 0 && d_tap != nullptr;
+  // The groups (one per configuration) are independent: group 0 runs on the caller's stream, the
+  // others on auxiliary streams forked from / joined back into it, so their CTAs share the SMs.
+  size_t live = 0;
+  bool forked = false;
   for (auto& g : b->groups) {
     if (g.ids.empty()) continue;
+    const size_t slot = live++;
     const auto lo = std::lower_bound(g.ids.begin(), g.ids.end(), (int32_t)s0) - g.ids.begin();
     const auto hi = std::lower_bound(g.ids.begin(), g.ids.end(), (int32_t)s1) - g.ids.begin();
     if (hi <= lo) continue;
+    cudaStream_t gst = st;
+    if (slot > 0) {
+      if (!forked) { CUDA_TRY(cudaEventRecord(b->fork_ev, st)); forked = true; }
+      gst = b->aux_streams[slot - 1];
+      CUDA_TRY(cudaStreamWaitEvent(gst, b->fork_ev, 0));
+    }
     DemodArgs a;
     a.d = g.d;
     a.ids = g.contiguous ? nullptr : g.d_ids;
@@ -452,17 +504,21 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
     a.out = d_out; a.out_stride = out_stride; a.out_len = d_out_len; a.tap = d_tap;
     const int sel = (aligned ? 4 : 0) | (wb ? 2 : 0) | (tap ? 1 : 0);
     switch (sel) {
-      case 0: launch_demod<false, false, false>(a, st); break;
-      case 1: launch_demod<false, false, true>(a, st); break;
-      case 2: launch_demod<false, true, false>(a, st); break;
-      case 3: launch_demod<false, true, true>(a, st); break;
-      case 4: launch_demod<true, false, false>(a, st); break;
-      case 5: launch_demod<true, false, true>(a, st); break;
-      case 6: launch_demod<true, true, false>(a, st); break;
-      default: launch_demod<true, true, true>(a, st); break;
+      case 0: launch_demod<false, false, false>(a, gst); break;
+      case 1: launch_demod<false, false, true>(a, gst); break;
+      case 2: launch_demod<false, true, false>(a, gst); break;
+      case 3: launch_demod<false, true, true>(a, gst); break;
+      case 4: launch_demod<true, false, false>(a, gst); break;
+      case 5: launch_demod<true, false, true>(a, gst); break;
+      case 6: launch_demod<true, true, false>(a, gst); break;
+      default: launch_demod<true, true, true>(a, gst); break;
     }
     b->launches++;
     CUDA_TRY(cudaGetLastError());
+    if (slot > 0) {
+      CUDA_TRY(cudaEventRecord(b->aux_done[slot - 1], gst));
+      CUDA_TRY(cudaStreamWaitEvent(st, b->aux_done[slot - 1], 0));
+    }
   }
   return WAM_OK;
 }

@@ -8,7 +8,14 @@ namespace wam {
 
 constexpr int kMaxPatternWords = 8;  // preamble+SFD template: up to 256 line bits
 constexpr int kTile = 32;            // samples per stream per staged tile (one 128-byte row)
-constexpr int kStages = 3;           // cp.async pipeline depth (per warp)
+constexpr int kStages = 2;           // cp.async pipeline depth (per warp)
+
+// Resident one-warp CTAs per SM the demodulator is compiled for.  BASELINE config 2 is 2048 warps
+// over 148 SMs = 13.84 per SM: all of them must be resident at once (one wave), which needs
+// <= 65536 / (14 * 32) = 146 registers per thread.
+#ifndef WAM_DEMOD_MIN_BLOCKS
+#define WAM_DEMOD_MIN_BLOCKS 14
+#endif
 
 // Everything FSKCore.configure() derives (src/modems/fsk.ts:133-157, :426-462), computed on the
 // host in float64 with the reference's operation order, then passed to kernels by value so the

@@ -246,6 +246,10 @@ class FSKBatch:
     def reset(self):
         L.check(self._lib.wam_fsk_batch_reset(self._h))
 
+    def renew(self, stream: int = 0):
+        """new FSKCore() + configure() on every stream (stream-ordered)."""
+        L.check(self._lib.wam_fsk_batch_renew(self._h, stream or None))
+
     def launch_count(self) -> int:
         return int(self._lib.wam_fsk_batch_launch_count(self._h))
 
