@@ -219,6 +219,11 @@ int wam_iir_process_batch(int device, const double* b, int nb, const double* a, 
 int wam_fir_process_batch(int device, const double* taps, int ntaps, const float* in, float* out,
                           long stride, long n, long n_streams, double* state);
 
+/* test hook: the device float64 primitives of the discriminator (fast_atan2 / fast_sqrt / fast_rcp)
+ * evaluated on host arrays; used by tests/test_gpu_fastmath.py to bound their error against libm. */
+int wam_debug_fastmath(int device, const double* y, const double* x, long n, double* out_atan2,
+                       double* out_sqrt, double* out_rcp);
+
 /* pinned host memory helpers (so the HOST-buffer entry points can overlap copies) */
 int wam_host_alloc(void** p, size_t bytes);
 int wam_host_free(void* p);

@@ -106,6 +106,7 @@ SYMBOLS = {
     "wam_iir_state_size": (C.c_long, [C.c_int, C.c_int]),
     "wam_iir_process_batch": (C.c_int, [C.c_int, _dp, C.c_int, _dp, C.c_int, _vp, _vp, C.c_long, C.c_long, C.c_long, _vp]),
     "wam_fir_process_batch": (C.c_int, [C.c_int, _dp, C.c_int, _vp, _vp, C.c_long, C.c_long, C.c_long, _vp]),
+    "wam_debug_fastmath": (C.c_int, [C.c_int, _dp, _dp, C.c_long, _dp, _dp, _dp]),
     "wam_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "wam_host_free": (C.c_int, [_vp]),
 }

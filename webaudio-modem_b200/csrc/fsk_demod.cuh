@@ -24,6 +24,7 @@
 // the per-sample arithmetic.
 #pragma once
 
+#include "fastmath.cuh"
 #include "wam_common.cuh"
 
 namespace wam {
@@ -93,40 +94,36 @@ __device__ __forceinline__ void reset_state(LaneState& s) {
   s.dsc = 0; s.iacc = 0.0; s.qacc = 0.0;
 }
 
-// ones in the circular bit range [lo, lo+len) of a power-of-two ring of `words` 32-bit words
-__device__ __forceinline__ int ring_popc_range(const uint32_t* __restrict__ ring, long ns, uint32_t lo, int len,
-                                               int words) {
-  uint32_t w = (lo >> 5) & (uint32_t)(words - 1);
-  uint32_t o = lo & 31u;
-  int total = 0;
-  while (len > 0) {
-    int take = min(32 - (int)o, len);
-    uint32_t mask = (take == 32) ? 0xffffffffu : (((1u << take) - 1u) << o);
-    total += __popc(ring[(long)w * ns] & mask);
-    len -= take;
-    o = 0;
-    w = (w + 1) & (uint32_t)(words - 1);
-  }
-  return total;
-}
-
 // Frame-sync template match, integral-capacity ring — fsk.ts:303-312.
-// matched counts ring samples equal to preambleSfdBits[nbits - j] for window j (j*dspb .. (j+1)*dspb-1
-// samples back from the newest); j == 0 compares against `undefined` and never matches.
-__device__ __noinline__ int sync_matched_integral(const uint32_t* __restrict__ ring, long ns, uint32_t pos,
-                                                  const FskDerived& d) {
-  int matched = 0;
-  int remaining = (d.nbits - 1) * d.dspb;
-  for (int j = 1; j < d.nbits; ++j) {
-    const int pb = d.nbits - j;
-    const int expect = (d.pattern[pb >> 5] >> (pb & 31)) & 1;
-    const uint32_t lo = pos - (uint32_t)((j + 1) * d.dspb);
-    const int ones = ring_popc_range(ring, ns, lo, d.dspb, d.ring_words);
-    matched += expect ? ones : d.dspb - ones;
-    remaining -= d.dspb;
-    if (matched + remaining < d.min_matched) break;  // cannot reach the threshold any more
+// The reference compares the newest nbits*dspb ring samples with preambleSfdBits[nbits - j] for
+// window j (j*dspb .. (j+1)*dspb-1 samples back); j == 0 compares against `undefined` and never
+// matches.  Here the ring is bit-packed, and the expected bits / compare masks are precomputed on
+// the host for each of the 32 possible bit offsets of the window start inside a ring word, so the
+// match is one XOR + AND + POPC per 32 samples.  Returns the number of mismatches among the
+// compared (j >= 1) samples, or a value > max_mismatch as soon as the threshold is out of reach.
+__device__ __noinline__ int sync_mismatches(const uint32_t* __restrict__ ring, long ns, uint32_t pos,
+                                            const FskDerived& d) {
+  const uint32_t lo = pos - (uint32_t)d.total_bits;
+  const uint32_t o = lo & 31u;
+  const uint32_t wmask = (uint32_t)(d.ring_words - 1);
+  uint32_t w = (lo >> 5) & wmask;
+  const uint32_t* __restrict__ ex = d.tmpl_expect + (long)o * d.tmpl_words;
+  const uint32_t* __restrict__ mk = d.tmpl_mask + (long)o * d.tmpl_words;
+  int mism = 0;
+  int i = 0;
+  for (; i + 4 <= d.tmpl_words; i += 4) {
+    const uint32_t r0 = ring[(long)((w + 0) & wmask) * ns], r1 = ring[(long)((w + 1) & wmask) * ns];
+    const uint32_t r2 = ring[(long)((w + 2) & wmask) * ns], r3 = ring[(long)((w + 3) & wmask) * ns];
+    mism += __popc((r0 ^ __ldg(ex + i)) & __ldg(mk + i)) + __popc((r1 ^ __ldg(ex + i + 1)) & __ldg(mk + i + 1)) +
+            __popc((r2 ^ __ldg(ex + i + 2)) & __ldg(mk + i + 2)) + __popc((r3 ^ __ldg(ex + i + 3)) & __ldg(mk + i + 3));
+    w += 4;
+    if (mism > d.max_mismatch) return mism;  // cannot reach the threshold any more
   }
-  return matched;
+  for (; i < d.tmpl_words; ++i) {
+    mism += __popc((ring[(long)(w & wmask) * ns] ^ __ldg(ex + i)) & __ldg(mk + i));
+    ++w;
+  }
+  return mism;
 }
 
 // ---- literal emulation of RingBuffer with a fractional capacity (utils.ts:14-47) ----
@@ -261,7 +258,7 @@ __device__ __forceinline__ bool process_downsampled_bit(LaneState& s, int bit, d
       if (!d.ring_fractional) {
         if ((s.ring_pos & 31u) != 0u)
           ring[(long)((s.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns] = s.cur_word;  // flush partial word
-        matched = sync_matched_integral(ring, ns, s.ring_pos, d);
+        matched = (d.total_bits - d.dspb) - sync_mismatches(ring, ns, s.ring_pos, d);
       } else {
         matched = sync_matched_fractional(s.ring_ri, s.ring_flen, ring, ns, d);
       }
@@ -348,10 +345,11 @@ __device__ __forceinline__ void phase_a2_half(LaneState& s, float pf, const FskD
 
 // decimated-rate discriminator (fsk.ts:246-264) on the summed pair (2*avgI, 2*avgQ): returns the
 // hard bit, and the squared magnitude whose root is twice the reference amplitude.
-__device__ __forceinline__ int phase_a2_decim(LaneState& s, double si, double sq, const FskDerived& d, double& p) {
+__device__ __forceinline__ int phase_a2_decim(LaneState& s, double si, double sq, const FskDerived& d,
+                                              const double* __restrict__ atan_tab, double& p) {
   const double kTwoPi = 6.283185307179586;  // 2 * Math.PI
   const double kPi = 3.141592653589793;
-  const double phase = atan2(sq, si);       // atan2(avgQ, avgI): scale invariant
+  const double phase = fast_atan2(sq, si, atan_tab);  // atan2(avgQ, avgI): scale invariant
   p = __dadd_rn(__dmul_rn(si, si), __dmul_rn(sq, sq));
   double pd = phase - s.last_phase;
   if (pd > kPi) pd -= kTwoPi;
@@ -412,19 +410,26 @@ __device__ __forceinline__ void stage_tile(float* tile, const DemodArgs& a, cons
 
 // Grid: one warp (32 streams) per CTA, so that 2048 warps spread evenly over 148 SMs.
 template <bool ALIGNED, bool WRITEBACK, bool TAP>
-__global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kernel(const __grid_constant__ DemodArgs a) {
+__global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kernel(const __grid_constant__ DemodLaunch L) {
+  int gi = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxGroupsPerLaunch; ++i)
+    if (i < L.n_groups && (int)blockIdx.x >= L.block_begin[i]) gi = i;
+  const DemodArgs& a = L.g[gi];
   // stage buffers: input tile (swizzled f32 [32][32]); after A1 the same 4 KiB hold the squared
   // magnitudes of the tile as f64 [16][32]
   __shared__ __align__(128) float tiles[kStages][kTile * kTile];
   __shared__ __align__(128) float pfbuf[kTile * 32];  // pre-filtered samples [i][lane]
   __shared__ long rows[32];
+  __shared__ double atan_tab[kAtanTableSize];
 
   const int lane = threadIdx.x;
-  const int li = a.l_begin + blockIdx.x * 32 + lane;
+  const int li = a.l_begin + ((int)blockIdx.x - L.block_begin[gi]) * 32 + lane;
   const bool active = li < a.l_end;
   long row = -1;
   if (active) row = (long)(a.ids ? a.ids[li] : a.id0 + li) - a.row_base;
   rows[lane] = row;
+  for (int i = lane; i < kAtanTableSize; i += 32) atan_tab[i] = a.d.atan_tab[i];
   __syncwarp();
 
   const FskDerived& d = a.d;
@@ -506,7 +511,7 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
           if (v1 < v_hi) {
             phase_a2_half(s, pfbuf[(v1 - dsc0) * 32 + lane], d, yi, yq);
             double pp;
-            const int bit = phase_a2_decim(s, s.iacc + yi, s.qacc + yq, d, pp);
+            const int bit = phase_a2_decim(s, s.iacc + yi, s.qacc + yq, d, atan_tab, pp);
             s.iacc = 0.0; s.qacc = 0.0;
             bits = (bits & ~(1u << k)) | ((uint32_t)bit << k);
             pbuf[k * 32 + lane] = pp;
@@ -523,7 +528,7 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
         redo = false;
 #pragma unroll 1
         for (int k = b_from; k < nk; ++k) {
-          const double amplitude = 0.5 * sqrt(pbuf[k * 32 + lane]);
+          const double amplitude = 0.5 * fast_sqrt(pbuf[k * 32 + lane]);
           if (process_downsampled_bit(s, (int)((bits >> k) & 1u), amplitude, a, li, out_row)) {
             // resetState(): A2 restarts from the zeroed state at the next pair
             k_from = k + 1; b_from = k + 1; v_lo = 2 * (k + 1);

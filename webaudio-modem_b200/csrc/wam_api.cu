@@ -268,6 +268,7 @@ struct Group {
   uint32_t* u32 = nullptr;
   uint32_t* sync_ring = nullptr;
   float* amp_ring = nullptr;
+  uint32_t* tmpl = nullptr;  // expect[32][W] then mask[32][W]
 };
 
 struct wam_fsk_batch {
@@ -280,10 +281,6 @@ struct wam_fsk_batch {
   long launches = 0;
   // staging for the HOST-buffer entry points
   cudaStream_t streams[2] = {nullptr, nullptr};
-  // concurrent launch of the per-configuration groups: fork/join around auxiliary streams
-  std::vector<cudaStream_t> aux_streams;
-  std::vector<cudaEvent_t> aux_done;
-  cudaEvent_t fork_ev = nullptr;
   float* stage_samples[2] = {nullptr, nullptr};
   uint8_t* stage_out[2] = {nullptr, nullptr};
   int32_t* stage_len[2] = {nullptr, nullptr};
@@ -298,6 +295,50 @@ struct wam_fsk_batch {
   int32_t* mod_len = nullptr;
   size_t mod_len_bytes = 0;
 };
+
+// atan(k / 64) table shared by every kernel launch on a device
+static int atan_table_device(int device, const double** out) {
+  static double* tabs[64] = {nullptr};
+  if (device < 0 || device >= 64) return fail(WAM_E_INVALID, "device index out of range");
+  if (!tabs[device]) {
+    double h[kAtanTableSize];
+    for (int k = 0; k < kAtanTableSize; k++) h[k] = atan((double)k / 64.0);
+    double* dptr = nullptr;
+    CUDA_TRY(cudaMalloc(&dptr, sizeof(h)));
+    CUDA_TRY(cudaMemcpy(dptr, h, sizeof(h), cudaMemcpyHostToDevice));
+    tabs[device] = dptr;
+  }
+  *out = tabs[device];
+  return WAM_OK;
+}
+
+// Word-aligned frame-sync templates (see sync_mismatches in fsk_demod.cuh).
+static int build_sync_templates(Group& g) {
+  FskDerived& d = g.d;
+  d.tmpl_expect = nullptr; d.tmpl_mask = nullptr; d.tmpl_words = 0; d.max_mismatch = -1;
+  if (d.ring_fractional || d.total_bits <= 0) return WAM_OK;
+  const int care = d.total_bits - d.dspb;  // the newest dspb samples (j == 0) never match
+  const int W = (31 + care + 31) / 32;
+  std::vector<uint32_t> h((size_t)2 * 32 * W, 0u);
+  for (int o = 0; o < 32; o++) {
+    for (int idx = 0; idx < care; idx++) {
+      const int back = d.total_bits - 1 - idx;  // samples back from the newest
+      const int j = back / d.dspb;              // 1 .. nbits-1
+      const int pb = d.nbits - j;
+      const uint32_t expect = (d.pattern[pb >> 5] >> (pb & 31)) & 1u;
+      const int bitpos = o + idx;
+      h[(size_t)o * W + (bitpos >> 5)] |= expect << (bitpos & 31);
+      h[(size_t)(32 + o) * W + (bitpos >> 5)] |= 1u << (bitpos & 31);
+    }
+  }
+  CUDA_TRY(cudaMalloc(&g.tmpl, sizeof(uint32_t) * h.size()));
+  CUDA_TRY(cudaMemcpy(g.tmpl, h.data(), sizeof(uint32_t) * h.size(), cudaMemcpyHostToDevice));
+  d.tmpl_expect = g.tmpl;
+  d.tmpl_mask = g.tmpl + (size_t)32 * W;
+  d.tmpl_words = W;
+  d.max_mismatch = (d.min_matched == INT_MAX) ? -1 : care - d.min_matched;
+  return WAM_OK;
+}
 
 __global__ void fill_f64_kernel(double* p, double v, long n) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -323,11 +364,8 @@ static void free_batch(wam_fsk_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   for (auto& g : b->groups) {
-    cudaFree(g.d_ids); cudaFree(g.f64); cudaFree(g.u32); cudaFree(g.sync_ring); cudaFree(g.amp_ring);
+    cudaFree(g.d_ids); cudaFree(g.f64); cudaFree(g.u32); cudaFree(g.sync_ring); cudaFree(g.amp_ring); cudaFree(g.tmpl);
   }
-  for (auto st : b->aux_streams) cudaStreamDestroy(st);
-  for (auto ev : b->aux_done) cudaEventDestroy(ev);
-  if (b->fork_ev) cudaEventDestroy(b->fork_ev);
   for (int i = 0; i < 2; i++) {
     if (b->streams[i]) cudaStreamDestroy(b->streams[i]);
     cudaFree(b->stage_samples[i]); cudaFree(b->stage_out[i]); cudaFree(b->stage_len[i]);
@@ -386,25 +424,15 @@ extern "C" int wam_fsk_batch_create(int device, long n_streams, const wam_fsk_co
       free_batch(b);
       return fail(e == cudaErrorMemoryAllocation ? WAM_E_NOMEM : WAM_E_CUDA, std::string("state allocation: ") + cudaGetErrorString(e));
     }
-    int rc = init_group_state(g, nullptr);
+    int rc = build_sync_templates(g);
+    if (rc == WAM_OK) rc = atan_table_device(device, &g.d.atan_tab);
+    if (rc == WAM_OK) rc = init_group_state(g, nullptr);
     if (rc != WAM_OK) { free_batch(b); return rc; }
   }
   CUDA_TRY(cudaDeviceSynchronize());
   for (int i = 0; i < 2; i++) {
     cudaError_t e = cudaStreamCreateWithFlags(&b->streams[i], cudaStreamNonBlocking);
     if (e != cudaSuccess) { free_batch(b); return fail(WAM_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
-  }
-  {
-    size_t live = 0;
-    for (auto& g : b->groups) live += g.ids.empty() ? 0 : 1;
-    cudaError_t e = cudaEventCreateWithFlags(&b->fork_ev, cudaEventDisableTiming);
-    for (size_t i = 1; i < live && e == cudaSuccess; i++) {
-      cudaStream_t st; cudaEvent_t ev;
-      e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
-      if (e == cudaSuccess) { b->aux_streams.push_back(st); e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); }
-      if (e == cudaSuccess) b->aux_done.push_back(ev);
-    }
-    if (e != cudaSuccess) { free_batch(b); return fail(WAM_E_CUDA, std::string("stream/event creation: ") + cudaGetErrorString(e)); }
   }
   *out = b;
   return WAM_OK;
@@ -463,36 +491,45 @@ extern "C" long wam_fsk_batch_out_capacity(wam_fsk_batch* b, long n_samples) {
 }
 
 template <bool A, bool W, bool T>
-static void launch_demod(const DemodArgs& args, cudaStream_t st) {
-  const int n = args.l_end - args.l_begin;
-  fsk_demod_exact_kernel<A, W, T><<<(n + 31) / 32, 32, 0, st>>>(args);
+static void launch_demod(const DemodLaunch& L, cudaStream_t st) {
+  fsk_demod_exact_kernel<A, W, T><<<L.block_begin[L.n_groups], 32, 0, st>>>(L);
 }
 
 // launch the demodulator for all streams of `b` whose global id lies in [s0, s1); row 0 of the
-// buffers is stream `row_base`.
+// buffers is stream `row_base`.  All configuration groups go into one launch (up to
+// kMaxGroupsPerLaunch per launch) so their one-warp CTAs share the SMs.
 static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base, float* d_samples, long stride, long n,
                               uint8_t* d_out, long out_stride, int32_t* d_out_len, float* d_tap, uint32_t flags,
                               cudaStream_t st) {
   const bool aligned = ((reinterpret_cast<uintptr_t>(d_samples) & 15) == 0) && (stride % 4 == 0);
   const bool wb = (flags & WAM_BATCH_WRITEBACK_AGC) != 0;
   const bool tap = (flags & WAM_BATCH_TAP_PREFILTER) != 0 && d_tap != nullptr;
-  // The groups (one per configuration) are independent: group 0 runs on the caller's stream, the
-  // others on auxiliary streams forked from / joined back into it, so their CTAs share the SMs.
-  size_t live = 0;
-  bool forked = false;
+  DemodLaunch L;
+  memset(&L, 0, sizeof(L));
+  auto flush = [&]() -> int {
+    if (L.n_groups == 0) return WAM_OK;
+    const int sel = (aligned ? 4 : 0) | (wb ? 2 : 0) | (tap ? 1 : 0);
+    switch (sel) {
+      case 0: launch_demod<false, false, false>(L, st); break;
+      case 1: launch_demod<false, false, true>(L, st); break;
+      case 2: launch_demod<false, true, false>(L, st); break;
+      case 3: launch_demod<false, true, true>(L, st); break;
+      case 4: launch_demod<true, false, false>(L, st); break;
+      case 5: launch_demod<true, false, true>(L, st); break;
+      case 6: launch_demod<true, true, false>(L, st); break;
+      default: launch_demod<true, true, true>(L, st); break;
+    }
+    b->launches++;
+    CUDA_TRY(cudaGetLastError());
+    memset(&L, 0, sizeof(L));
+    return WAM_OK;
+  };
   for (auto& g : b->groups) {
     if (g.ids.empty()) continue;
-    const size_t slot = live++;
     const auto lo = std::lower_bound(g.ids.begin(), g.ids.end(), (int32_t)s0) - g.ids.begin();
     const auto hi = std::lower_bound(g.ids.begin(), g.ids.end(), (int32_t)s1) - g.ids.begin();
     if (hi <= lo) continue;
-    cudaStream_t gst = st;
-    if (slot > 0) {
-      if (!forked) { CUDA_TRY(cudaEventRecord(b->fork_ev, st)); forked = true; }
-      gst = b->aux_streams[slot - 1];
-      CUDA_TRY(cudaStreamWaitEvent(gst, b->fork_ev, 0));
-    }
-    DemodArgs a;
+    DemodArgs& a = L.g[L.n_groups];
     a.d = g.d;
     a.ids = g.contiguous ? nullptr : g.d_ids;
     a.id0 = g.ids.front();
@@ -502,25 +539,14 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
     a.f64 = g.f64; a.u32 = g.u32; a.sync_ring = g.sync_ring; a.amp_ring = g.amp_ring;
     a.samples = d_samples; a.stride = stride; a.n = n;
     a.out = d_out; a.out_stride = out_stride; a.out_len = d_out_len; a.tap = d_tap;
-    const int sel = (aligned ? 4 : 0) | (wb ? 2 : 0) | (tap ? 1 : 0);
-    switch (sel) {
-      case 0: launch_demod<false, false, false>(a, gst); break;
-      case 1: launch_demod<false, false, true>(a, gst); break;
-      case 2: launch_demod<false, true, false>(a, gst); break;
-      case 3: launch_demod<false, true, true>(a, gst); break;
-      case 4: launch_demod<true, false, false>(a, gst); break;
-      case 5: launch_demod<true, false, true>(a, gst); break;
-      case 6: launch_demod<true, true, false>(a, gst); break;
-      default: launch_demod<true, true, true>(a, gst); break;
-    }
-    b->launches++;
-    CUDA_TRY(cudaGetLastError());
-    if (slot > 0) {
-      CUDA_TRY(cudaEventRecord(b->aux_done[slot - 1], gst));
-      CUDA_TRY(cudaStreamWaitEvent(st, b->aux_done[slot - 1], 0));
+    L.block_begin[L.n_groups + 1] = L.block_begin[L.n_groups] + (int)((hi - lo + 31) / 32);
+    L.n_groups++;
+    if (L.n_groups == kMaxGroupsPerLaunch) {
+      int rc = flush();
+      if (rc != WAM_OK) return rc;
     }
   }
-  return WAM_OK;
+  return flush();
 }
 
 extern "C" int wam_fsk_batch_demodulate_device(wam_fsk_batch* b, float* d_samples, long stream_stride, long n_samples,
@@ -1040,6 +1066,29 @@ extern "C" int wam_fir_process_batch(int device, const double* taps, int ntaps, 
   if (rc != WAM_OK) return rc;
   if (n == 0 || n_streams == 0) return WAM_OK;
   return fir_process_batch_host(taps, ntaps, in, out, stride, n, n_streams, state);
+}
+
+// test hook for the device math primitives (tests/test_gpu_fastmath.py)
+extern "C" int wam_debug_fastmath(int device, const double* y, const double* x, long n, double* out_atan2,
+                                  double* out_sqrt, double* out_rcp) {
+  if (n < 0 || (n > 0 && (!y || !x || !out_atan2 || !out_sqrt || !out_rcp))) return fail(WAM_E_INVALID, "bad argument");
+  int rc = select_device(device);
+  if (rc != WAM_OK) return rc;
+  if (n == 0) return WAM_OK;
+  const double* tab = nullptr;
+  if ((rc = atan_table_device(device, &tab)) != WAM_OK) return rc;
+  DevBuf dy, dx, d1, d2, d3;
+  const size_t nb = sizeof(double) * (size_t)n;
+  if ((rc = dy.alloc(nb)) || (rc = dx.alloc(nb)) || (rc = d1.alloc(nb)) || (rc = d2.alloc(nb)) || (rc = d3.alloc(nb))) return rc;
+  CUDA_TRY(cudaMemcpy(dy.p, y, nb, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dx.p, x, nb, cudaMemcpyHostToDevice));
+  fastmath_debug_kernel<<<(unsigned)((n + 255) / 256), 256>>>((const double*)dy.p, (const double*)dx.p, n, tab,
+                                                             (double*)d1.p, (double*)d2.p, (double*)d3.p);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(out_atan2, d1.p, nb, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(out_sqrt, d2.p, nb, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(out_rcp, d3.p, nb, cudaMemcpyDeviceToHost));
+  return WAM_OK;
 }
 
 extern "C" int wam_host_alloc(void** p, size_t bytes) {

@@ -45,6 +45,13 @@ struct FskDerived {
   int ring_words;       // integral path: power-of-two number of 32-bit words (>= total_bits+64 bits)
                         // fractional path: ceil(ring_cap_int/32)
   int amp_cap;          // dspb * 8 (fsk.ts:150)
+  // word-aligned sync templates (integral ring): for every bit offset o = 0..31 of the window start,
+  // tmpl_words words of expected bits and of compare masks (device memory, [32][tmpl_words])
+  const uint32_t* tmpl_expect;
+  const uint32_t* tmpl_mask;
+  int tmpl_words;
+  int max_mismatch;     // care_bits - min_matched (negative: can never sync)
+  const double* atan_tab;  // device: atan(k / 64), k = 0..64
   // modulator (fsk.ts:389-424)
   double mark, space, fs;
   int n_preamble, n_sfd;
@@ -86,6 +93,15 @@ struct DemodArgs {
   long out_stride;
   int32_t* out_len;     // [rows]
   float* tap;           // optional [rows][stride]
+};
+
+// All configuration groups of a batch run in ONE launch (one-warp CTAs; blockIdx selects the group)
+// so that their CTAs fill the SMs together.
+constexpr int kMaxGroupsPerLaunch = 4;
+struct DemodLaunch {
+  int n_groups;
+  int block_begin[kMaxGroupsPerLaunch + 1];  // first CTA of every group, then the total
+  DemodArgs g[kMaxGroupsPerLaunch];
 };
 
 #define WAM_ERR_OUT_OVERFLOW 1u
