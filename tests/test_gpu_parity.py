@@ -216,3 +216,29 @@ def test_batch_modulate_then_demodulate(gpu_wam, oracle):
         np.testing.assert_allclose(sig[s], want, rtol=0, atol=TOL)
     got = b.demodulate_bytes(sig)
     assert got == [data[s].tobytes() for s in range(40)]
+
+
+def test_event_driven_state_machine_equals_generic(gpu_wam, oracle):
+    """The event-driven tile state machine and the per-sample one (debug flag) must agree exactly,
+    including counters, on noisy multi-frame streams with many resets."""
+    L = gpu_wam._lib
+    n_streams, n = 64, 48000 * 2
+    xs = [siggen.multi_frame_stream({}, n, 24, float(s % 8) * 2 - 4, seed=900 + s, max_gap=3000)[0] for s in range(n_streams)]
+    x = np.ascontiguousarray(np.stack(xs))
+    a = gpu_wam.FSKBatch(n_streams, {})
+    b = gpu_wam.FSKBatch(n_streams, {})
+    got_a, got_b = [b""] * n_streams, [b""] * n_streams
+    for lo, hi in ((0, 30001), (30001, 30002), (30002, n)):  # odd slab lengths exercise the decimator parity
+        pa = a.demodulate_bytes(np.ascontiguousarray(x[:, lo:hi]))
+        pb = b.demodulate_bytes(np.ascontiguousarray(x[:, lo:hi]), flags=L.WAM_BATCH_DEBUG_GENERIC_SM)
+        got_a = [u + v for u, v in zip(got_a, pa)]
+        got_b = [u + v for u, v in zip(got_b, pb)]
+    assert got_a == got_b
+    sa, sb = a.status(), b.status()
+    for i in range(n_streams):
+        assert sa[i] == sb[i], i
+    want, ost = oracle.batch_demodulate([{}], None, x.copy(), n_threads=8)
+    assert got_a == want
+    for i in range(n_streams):
+        for k in ["frameStarted", "globalSampleCounter", "receivedBitsLength", "syncDetections", "eodEvents"]:
+            assert float(sa[i][k]) == float(ost[i][k]), (i, k)

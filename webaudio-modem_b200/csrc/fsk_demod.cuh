@@ -199,42 +199,27 @@ __device__ __forceinline__ bool process_byte(LaneState& s, int bit, const FskDer
 }
 
 // silence threshold = mean(amplitude ring) * 0.1, summed oldest -> newest in f64 — fsk.ts:321-326
-__device__ __noinline__ double amp_ring_threshold(const float* __restrict__ aring, long ns, uint32_t amp_pos,
-                                                  uint32_t amp_len, uint32_t amp_cap) {
+// amp_next = physical slot following the newest entry; the ring has amp_phys physical slots of
+// which the newest amp_len (<= amp_cap) are the reference's ring contents.
+__device__ __noinline__ double amp_ring_threshold(const float* __restrict__ aring, long ns, uint32_t amp_next,
+                                                  uint32_t amp_len, uint32_t amp_phys) {
   double sum = 0.0;
-  uint32_t slot = (amp_pos + amp_cap - amp_len) % amp_cap;
+  uint32_t slot = (amp_next + amp_phys - amp_len) % amp_phys;
   for (uint32_t i = 0; i < amp_len; ++i) {
     sum += (double)aring[(long)slot * ns];
-    slot = (slot + 1u == amp_cap) ? 0u : slot + 1u;
+    slot = (slot + 1u == amp_phys) ? 0u : slot + 1u;
   }
   return (sum / (double)amp_len) * 0.1;
 }
 
-// FSKCore.processDownsampledBit — fsk.ts:278-344.  Returns true when resetState() ran.
-__device__ __forceinline__ bool process_downsampled_bit(LaneState& s, int bit, double amplitude, const DemodArgs& a,
-                                                        int li, uint8_t* out_row) {
+// One decimated sample of FSKCore.processDownsampledBit (fsk.ts:278-344) AFTER the ring puts:
+// silence/EOD, sync search or vote/bit decision.  ring_pos / amp_next describe the rings including
+// this sample.  Returns true when resetState() ran.
+__device__ __forceinline__ bool sm_step(LaneState& s, int bit, double amplitude, uint32_t ring_pos, bool ring_ready,
+                                        uint32_t amp_next, uint32_t amp_len, const DemodArgs& a, int li,
+                                        uint8_t* out_row, bool& thr_changed) {
   const FskDerived& d = a.d;
   const long ns = a.n_local;
-  uint32_t* ring = a.sync_ring + li;
-  float* aring = a.amp_ring + li;
-
-  // syncSamplesBuffer.put(bit) — fsk.ts:281
-  if (!d.ring_fractional) {
-    s.cur_word |= (uint32_t)bit << (s.ring_pos & 31u);
-    s.ring_pos++;
-    if ((s.ring_pos & 31u) == 0u) {
-      ring[(long)(((s.ring_pos - 1u) >> 5) & (uint32_t)(d.ring_words - 1)) * ns] = s.cur_word;
-      s.cur_word = 0u;
-    }
-    s.ring_len = min(s.ring_len + 1u, (uint32_t)d.ring_cap_int);
-  } else {
-    ring_put_fractional(s, ring, ns, bit, d);
-  }
-  // syncAmplitudeBuffer.put(amplitude) — fsk.ts:282 (Float32Array store)
-  aring[(long)s.amp_pos * ns] = (float)amplitude;
-  s.amp_pos = (s.amp_pos + 1u == (uint32_t)d.amp_cap) ? 0u : s.amp_pos + 1u;
-  s.amp_len = min(s.amp_len + 1u, (uint32_t)d.amp_cap);
-
   // silence / EOD — fsk.ts:285-295
   s.gsc++;
   s.gmod = (s.gmod + 1u == (uint32_t)d.check_period) ? 0u : s.gmod + 1u;
@@ -248,17 +233,16 @@ __device__ __forceinline__ bool process_downsampled_bit(LaneState& s, int bit, d
   } else {
     s.sil_cnt = 0;
   }
-
   if (!s.started) {
     // fsk.ts:297-328
     const bool due = d.check_period > 0 && s.gmod == 0u;
-    const bool enough = d.ring_fractional ? (s.ring_flen >= (double)d.total_bits) : (s.ring_len >= (uint32_t)d.total_bits);
-    if (due && enough && d.total_bits > 0) {
+    if (due && ring_ready && d.total_bits > 0) {
+      uint32_t* ring = a.sync_ring + li;
       int matched;
       if (!d.ring_fractional) {
-        if ((s.ring_pos & 31u) != 0u)
-          ring[(long)((s.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns] = s.cur_word;  // flush partial word
-        matched = (d.total_bits - d.dspb) - sync_mismatches(ring, ns, s.ring_pos, d);
+        if ((s.ring_pos & 31u) != 0u)  // flush the register copy of the newest (partial) word
+          ring[(long)((s.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns] = s.cur_word;
+        matched = (d.total_bits - d.dspb) - sync_mismatches(ring, ns, ring_pos, d);
       } else {
         matched = sync_matched_fractional(s.ring_ri, s.ring_flen, ring, ns, d);
       }
@@ -267,7 +251,8 @@ __device__ __forceinline__ bool process_downsampled_bit(LaneState& s, int bit, d
         s.current = 0; s.bitpos = 0;
         s.bit_acc = 0; s.bit_cnt = 0; s.bsc = 0; s.next_idx = 0;
         s.sync_det++;
-        s.sil_thr = amp_ring_threshold(aring, ns, s.amp_pos, s.amp_len, (uint32_t)d.amp_cap);
+        s.sil_thr = amp_ring_threshold(a.amp_ring + li, ns, amp_next, amp_len, (uint32_t)d.amp_phys);
+        thr_changed = true;
       }
     }
     return false;
@@ -280,9 +265,139 @@ __device__ __forceinline__ bool process_downsampled_bit(LaneState& s, int bit, d
     const int decided = (2u * s.bit_acc > s.bit_cnt) ? 1 : 0;  // acc > count/2
     s.bit_acc = 0; s.bit_cnt = 0;
     s.next_idx += (uint32_t)d.dspb;
-    return process_byte(s, decided, d, out_row, a.out_stride);
+    const bool was_started = s.started != 0;
+    const bool rst = process_byte(s, decided, d, out_row, a.out_stride);
+    // gmod is only maintained while searching: resynchronise it when the frame ends
+    if (!rst && was_started && !s.started && d.check_period > 0) s.gmod = s.gsc % (uint32_t)d.check_period;
+    return rst;
   }
   return false;
+}
+
+// Generic per-sample state machine (any ring kind, any eod_count): puts + sm_step.
+__device__ __forceinline__ bool process_downsampled_bit(LaneState& s, int bit, double amplitude, const DemodArgs& a,
+                                                        int li, uint8_t* out_row) {
+  const FskDerived& d = a.d;
+  const long ns = a.n_local;
+  uint32_t* ring = a.sync_ring + li;
+  float* aring = a.amp_ring + li;
+  bool ready;
+  // syncSamplesBuffer.put(bit) — fsk.ts:281
+  if (!d.ring_fractional) {
+    s.cur_word |= (uint32_t)bit << (s.ring_pos & 31u);
+    s.ring_pos++;
+    if ((s.ring_pos & 31u) == 0u) {
+      ring[(long)(((s.ring_pos - 1u) >> 5) & (uint32_t)(d.ring_words - 1)) * ns] = s.cur_word;
+      s.cur_word = 0u;
+    }
+    s.ring_len = min(s.ring_len + 1u, (uint32_t)d.ring_cap_int);
+    ready = s.ring_len >= (uint32_t)d.total_bits;
+  } else {
+    ring_put_fractional(s, ring, ns, bit, d);
+    ready = s.ring_flen >= (double)d.total_bits;
+  }
+  // syncAmplitudeBuffer.put(amplitude) — fsk.ts:282 (Float32Array store)
+  aring[(long)s.amp_pos * ns] = (float)amplitude;
+  s.amp_pos = (s.amp_pos + 1u == (uint32_t)d.amp_phys) ? 0u : s.amp_pos + 1u;
+  s.amp_len = min(s.amp_len + 1u, (uint32_t)d.amp_cap);
+  bool thr_changed = false;
+  const bool was_started = s.started != 0;
+  const bool rst = sm_step(s, bit, amplitude, s.ring_pos, ready, s.amp_pos, s.amp_len, a, li, out_row, thr_changed);
+  // while a frame is being received sm_step does not advance gmod beyond the wrap it does itself;
+  // the generic path keeps it exact anyway (it increments every sample above)
+  (void)was_started;
+  return rst;
+}
+
+// Event-driven state machine for one tile (integral ring, eod_count > 16).  `bits` holds the hard
+// decisions of decimated samples 0..nk-1 of the tile, amp[k*32] their amplitudes (f64, smem).
+// Ring puts, counters and the vote accumulator are advanced in bulk with bit operations; only the
+// samples where something can happen (EOD crossing, a due sync check, a bit decision) go through
+// sm_step.  Returns the decimated index at which resetState() ran, or -1.
+__device__ __forceinline__ int sm_tile_events(LaneState& s, uint32_t bits, const double* __restrict__ amp, int b_from,
+                                              int nk, uint32_t pos_t0, uint32_t len_t0, uint32_t slot_t0,
+                                              uint32_t alen_t0, const DemodArgs& a, int li, uint8_t* out_row) {
+  const FskDerived& d = a.d;
+  const long ns = a.n_local;
+  uint32_t* ring = a.sync_ring + li;
+  float* aring = a.amp_ring + li;
+  const uint32_t wmask = (uint32_t)(d.ring_words - 1);
+
+  // ---- bulk ring puts for samples [b_from, nk) — fsk.ts:281-282
+  {
+    const uint32_t p = pos_t0 + (uint32_t)b_from;
+    if (b_from > 0) {
+      // replay pass: the word holding position p may already have been flushed
+      ring[(long)((s.ring_pos >> 5) & wmask) * ns] = s.cur_word;
+      s.cur_word = ring[(long)((p >> 5) & wmask) * ns];
+    }
+    const uint32_t cnt = (uint32_t)(nk - b_from);
+    const uint32_t o = p & 31u;
+    const uint32_t chunk = (bits >> b_from) & ((1u << cnt) - 1u);
+    s.cur_word = (s.cur_word & ((1u << o) - 1u)) | (chunk << o);
+    if (o + cnt >= 32u) {
+      ring[(long)((p >> 5) & wmask) * ns] = s.cur_word;
+      s.cur_word = (o + cnt > 32u) ? (chunk >> (32u - o)) : 0u;
+    }
+    s.ring_pos = pos_t0 + (uint32_t)nk;
+    uint32_t slot = slot_t0 + (uint32_t)b_from;
+    if (slot >= (uint32_t)d.amp_phys) slot -= (uint32_t)d.amp_phys;
+    for (int k = b_from; k < nk; ++k) {
+      aring[(long)slot * ns] = (float)amp[k * 32];
+      slot = (slot + 1u == (uint32_t)d.amp_phys) ? 0u : slot + 1u;
+    }
+  }
+  // silence flags for the current threshold — fsk.ts:286
+  uint32_t silent = 0u;
+  for (int k = b_from; k < nk; ++k) silent |= (amp[k * 32] < s.sil_thr ? 1u : 0u) << k;
+
+  int k = b_from;
+  while (k < nk) {
+    // next sample at which an event can happen
+    int k_evt = nk;
+    {
+      const uint32_t run = (uint32_t)__ffs((int)(~(silent >> k))) - 1u;  // leading silent run from k
+      const uint32_t need = (uint32_t)d.eod_count - s.sil_cnt - 1u;      // silent samples before the EOD one
+      if (need < run) k_evt = min(k_evt, k + (int)need);
+    }
+    if (!s.started) {
+      if (d.check_period > 0) k_evt = min(k_evt, k + (int)((uint32_t)d.check_period - 1u - s.gmod));
+    } else {
+      const uint32_t nb = s.bsc + 1u;
+      k_evt = min(k_evt, k + (int)(s.next_idx > nb ? s.next_idx - nb : 0u));
+    }
+    // ---- bulk advance over [k, k_evt)
+    const int len = k_evt - k;
+    if (len > 0) {
+      const uint32_t m = ((1u << len) - 1u) << k;
+      s.gsc += (uint32_t)len;
+      if (!s.started) s.gmod += (uint32_t)len;  // stays below check_period by construction
+      const uint32_t nz = ~silent & m;
+      s.sil_cnt = nz ? (uint32_t)(k_evt - 1) - (31u - (uint32_t)__clz((int)nz)) : s.sil_cnt + (uint32_t)len;
+      if (s.started) {
+        s.bit_acc += (uint32_t)__popc(bits & m);
+        s.bit_cnt += (uint32_t)len;
+        s.bsc += (uint32_t)len;
+      }
+    }
+    if (k_evt >= nk) break;
+    // ---- the event sample itself
+    const uint32_t pos_k = pos_t0 + (uint32_t)k_evt + 1u;
+    const bool ready = len_t0 + (uint32_t)k_evt + 1u >= (uint32_t)d.total_bits;
+    uint32_t slot_next = slot_t0 + (uint32_t)k_evt + 1u;
+    if (slot_next >= (uint32_t)d.amp_phys) slot_next -= (uint32_t)d.amp_phys;
+    const uint32_t alen = min(alen_t0 + (uint32_t)k_evt + 1u, (uint32_t)d.amp_cap);
+    bool thr_changed = false;
+    if (sm_step(s, (int)((bits >> k_evt) & 1u), amp[k_evt * 32], pos_k, ready, slot_next, alen, a, li, out_row,
+                thr_changed))
+      return k_evt;
+    if (thr_changed) {
+      silent = 0u;
+      for (int kk = k_evt + 1; kk < nk; ++kk) silent |= (amp[kk * 32] < s.sil_thr ? 1u : 0u) << kk;
+    }
+    k = k_evt + 1;
+  }
+  return -1;
 }
 
 // ---- phase A1: AGC + pre-filter for one sample -------------------------------------------------
@@ -298,18 +413,18 @@ __device__ __forceinline__ double agc_target(float level) {
   return fma(r, e, r);
 }
 
-__device__ __forceinline__ float phase_a1_sample(LaneState& s, float x, const FskDerived& d, float& agc_out) {
-  float sg = x;
-  if (d.agc_enabled) {  // fsk.ts:52-76
-    sg = (float)((double)x * s.gain);
-    const float level = fabsf(sg);
-    const double target = agc_target(level);
-    const double rate = level > 0.5f ? d.agc_attack : d.agc_release;
-    double g = fma(target - s.gain, rate, s.gain);
-    g = g > 10.0 ? 10.0 : g;
-    g = g < 0.1 ? 0.1 : g;
-    s.gain = level > 0.0f ? g : s.gain;
-  }
+__device__ __forceinline__ float phase_a1_sample(LaneState& s, float x, const FskDerived& d, bool agc, double att,
+                                                 double rel, float& agc_out) {
+  // AGC, fsk.ts:52-76 (evaluated unconditionally, selected by `agc`, so the code stays branch-free)
+  const float sg_agc = (float)((double)x * s.gain);
+  const float sg = agc ? sg_agc : x;
+  const float level = fabsf(sg);
+  const double target = agc_target(level);
+  const double rate = level > 0.5f ? att : rel;
+  double g = fma(target - s.gain, rate, s.gain);
+  g = g > 10.0 ? 10.0 : g;
+  g = g < 0.1 ? 0.1 : g;
+  s.gain = (agc && level > 0.0f) ? g : s.gain;
   agc_out = sg;
   // pre-filter: butterworthBandpass has b1 == 0 and b2 == -b0 exactly (filters.ts:230)
   const double xin = (double)sg;
@@ -467,20 +582,28 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
 
     // ---------------- A1: AGC + pre-filter ----------------
     if (active) {
+      const bool agc = d.agc_enabled != 0;
+      const double att = d.agc_attack, rel = d.agc_release;
+      if (len == kTile && !WRITEBACK && !TAP) {
 #pragma unroll 1
-      for (int ch = 0; ch < 8; ++ch) {
-        const float4 v = *reinterpret_cast<const float4*>(tile + tile_index(lane, ch * 4));
-        const float xs[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int i = ch * 4 + k;
-          if (i < len) {
-            float sg;
-            const float pf = phase_a1_sample(s, xs[k], d, sg);
-            pfbuf[i * 32 + lane] = pf;
-            if (WRITEBACK) a.samples[row * a.stride + t0 + i] = sg;  // fsk.ts:55 mutates the input
-            if (TAP) tap_row[t0 + i] = pf;
-          }
+        for (int ch = 0; ch < 8; ++ch) {
+          const float4 v = *reinterpret_cast<const float4*>(tile + tile_index(lane, ch * 4));
+          float sg;
+          const float p0 = phase_a1_sample(s, v.x, d, agc, att, rel, sg);
+          const float p1 = phase_a1_sample(s, v.y, d, agc, att, rel, sg);
+          const float p2 = phase_a1_sample(s, v.z, d, agc, att, rel, sg);
+          const float p3 = phase_a1_sample(s, v.w, d, agc, att, rel, sg);
+          float* pfp = pfbuf + (ch * 4) * 32 + lane;
+          pfp[0] = p0; pfp[32] = p1; pfp[64] = p2; pfp[96] = p3;
+        }
+      } else {
+#pragma unroll 1
+        for (int i = 0; i < len; ++i) {
+          float sg;
+          const float pf = phase_a1_sample(s, tile[tile_index(lane, i)], d, agc, att, rel, sg);
+          pfbuf[i * 32 + lane] = pf;
+          if (WRITEBACK) a.samples[row * a.stride + t0 + i] = sg;  // fsk.ts:55 mutates the input
+          if (TAP) tap_row[t0 + i] = pf;
         }
       }
     }
@@ -496,25 +619,43 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
     int v_lo = dsc0;                // first virtual sample present
     uint32_t bits = 0u;
     bool redo = active;
+    // ring bookkeeping at the start of the tile (event-driven state machine)
+    const uint32_t pos_t0 = s.ring_pos, len_t0 = s.ring_len, slot_t0 = s.amp_pos, alen_t0 = s.amp_len;
+    const bool fast_sm = !d.ring_fractional && d.eod_count > 16 && !a.force_generic;
     while (__any_sync(0xffffffffu, redo)) {
       if (redo) {
         // re-anchor the LO rotation on the accumulated phase (start of tile / after a reset)
         if (v_lo == dsc0 && t != 0) sincos(s.lo_phase, &s.lo_s, &s.lo_c);
+        bits &= (1u << k_from) - 1u;
+        if (dsc0 == 0 && (v_hi & 1) == 0) {
+          // fast path: every pair is complete
 #pragma unroll 1
-        for (int k = k_from; 2 * k < v_hi; ++k) {
-          const int v0 = 2 * k, v1 = 2 * k + 1;
-          double yi, yq;
-          if (v0 >= v_lo) {
-            phase_a2_half(s, pfbuf[(v0 - dsc0) * 32 + lane], d, yi, yq);
-            s.iacc = yi; s.qacc = yq;  // 0 + y
-          }
-          if (v1 < v_hi) {
-            phase_a2_half(s, pfbuf[(v1 - dsc0) * 32 + lane], d, yi, yq);
-            double pp;
-            const int bit = phase_a2_decim(s, s.iacc + yi, s.qacc + yq, d, atan_tab, pp);
-            s.iacc = 0.0; s.qacc = 0.0;
-            bits = (bits & ~(1u << k)) | ((uint32_t)bit << k);
+          for (int k = k_from; k < nk; ++k) {
+            double yi0, yq0, yi1, yq1, pp;
+            const float* pfp = pfbuf + (2 * k) * 32 + lane;
+            phase_a2_half(s, pfp[0], d, yi0, yq0);
+            phase_a2_half(s, pfp[32], d, yi1, yq1);
+            const int bit = phase_a2_decim(s, yi0 + yi1, yq0 + yq1, d, atan_tab, pp);
+            bits |= (uint32_t)bit << k;
             pbuf[k * 32 + lane] = pp;
+          }
+        } else {
+#pragma unroll 1
+          for (int k = k_from; 2 * k < v_hi; ++k) {
+            const int v0 = 2 * k, v1 = 2 * k + 1;
+            double yi, yq;
+            if (v0 >= v_lo) {
+              phase_a2_half(s, pfbuf[(v0 - dsc0) * 32 + lane], d, yi, yq);
+              s.iacc = yi; s.qacc = yq;  // 0 + y
+            }
+            if (v1 < v_hi) {
+              phase_a2_half(s, pfbuf[(v1 - dsc0) * 32 + lane], d, yi, yq);
+              double pp;
+              const int bit = phase_a2_decim(s, s.iacc + yi, s.qacc + yq, d, atan_tab, pp);
+              s.iacc = 0.0; s.qacc = 0.0;
+              bits |= (uint32_t)bit << k;
+              pbuf[k * 32 + lane] = pp;
+            }
           }
         }
         // LO phase bookkeeping: (phase + omega) % 2pi per sample in the reference (fsk.ts:232)
@@ -525,15 +666,37 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
         }
         s.dsc = (uint32_t)(v_hi & 1);
         // ---------------- B ----------------
+        // amplitude = sqrt(avgI^2 + avgQ^2) = sqrt(p) / 2 (fsk.ts:252), in place over p
+#pragma unroll 4
+        for (int k = b_from; k < nk; ++k) pbuf[k * 32 + lane] = 0.5 * fast_sqrt(pbuf[k * 32 + lane]);
         redo = false;
+        int k_reset = -1;
+        if (fast_sm) {
+          k_reset = sm_tile_events(s, bits, pbuf + lane, b_from, nk, pos_t0, len_t0, slot_t0, alen_t0, a, li, out_row);
+          if (k_reset < 0) {
+            s.ring_len = min(len_t0 + (uint32_t)nk, (uint32_t)d.ring_cap_int);
+            uint32_t sl = slot_t0 + (uint32_t)nk;
+            s.amp_pos = sl >= (uint32_t)d.amp_phys ? sl - (uint32_t)d.amp_phys : sl;
+            s.amp_len = min(alen_t0 + (uint32_t)nk, (uint32_t)d.amp_cap);
+          }
+        } else {
 #pragma unroll 1
-        for (int k = b_from; k < nk; ++k) {
-          const double amplitude = 0.5 * fast_sqrt(pbuf[k * 32 + lane]);
-          if (process_downsampled_bit(s, (int)((bits >> k) & 1u), amplitude, a, li, out_row)) {
-            // resetState(): A2 restarts from the zeroed state at the next pair
-            k_from = k + 1; b_from = k + 1; v_lo = 2 * (k + 1);
-            redo = (v_lo < v_hi);
-            break;
+          for (int k = b_from; k < nk; ++k) {
+            if (process_downsampled_bit(s, (int)((bits >> k) & 1u), pbuf[k * 32 + lane], a, li, out_row)) {
+              k_reset = k;
+              break;
+            }
+          }
+        }
+        if (k_reset >= 0) {
+          // resetState(): A2 restarts from the zeroed state at the next pair
+          k_from = k_reset + 1; b_from = k_reset + 1; v_lo = 2 * (k_reset + 1);
+          redo = (v_lo < v_hi);
+          if (fast_sm && !redo) {
+            s.ring_len = min(len_t0 + (uint32_t)nk, (uint32_t)d.ring_cap_int);
+            uint32_t sl = slot_t0 + (uint32_t)nk;
+            s.amp_pos = sl >= (uint32_t)d.amp_phys ? sl - (uint32_t)d.amp_phys : sl;
+            s.amp_len = min(alen_t0 + (uint32_t)nk, (uint32_t)d.amp_cap);
           }
         }
       }

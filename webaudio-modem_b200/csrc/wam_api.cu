@@ -251,6 +251,7 @@ static int derive(const wam_fsk_config& c, FskDerived& d) {
     d.ring_words = (d.ring_cap_int + 31) / 32 + 1;
   }
   d.amp_cap = d.dspb * 8;
+  d.amp_phys = d.amp_cap + 32;
   d.mark = c.markFrequency; d.space = c.spaceFrequency; d.fs = fs;
   return WAM_OK;
 }
@@ -351,7 +352,7 @@ static int init_group_state(Group& g, cudaStream_t st) {
   CUDA_TRY(cudaMemsetAsync(g.f64, 0, sizeof(double) * F64_COUNT * n, st));
   CUDA_TRY(cudaMemsetAsync(g.u32, 0, sizeof(uint32_t) * U32_COUNT * n, st));
   CUDA_TRY(cudaMemsetAsync(g.sync_ring, 0, sizeof(uint32_t) * (size_t)g.d.ring_words * n, st));
-  CUDA_TRY(cudaMemsetAsync(g.amp_ring, 0, sizeof(float) * (size_t)g.d.amp_cap * n, st));
+  CUDA_TRY(cudaMemsetAsync(g.amp_ring, 0, sizeof(float) * (size_t)g.d.amp_phys * n, st));
   // AGC gain 1.0 (fsk.ts:46), silence threshold 0.01 (fsk.ts:128)
   const unsigned blocks = (unsigned)((n + 255) / 256);
   fill_f64_kernel<<<blocks, 256, 0, st>>>(g.f64 + (size_t)F_GAIN * n, 1.0, (long)n);
@@ -419,7 +420,7 @@ extern "C" int wam_fsk_batch_create(int device, long n_streams, const wam_fsk_co
     if (e == cudaSuccess) e = cudaMalloc(&g.f64, sizeof(double) * F64_COUNT * n);
     if (e == cudaSuccess) e = cudaMalloc(&g.u32, sizeof(uint32_t) * U32_COUNT * n);
     if (e == cudaSuccess) e = cudaMalloc(&g.sync_ring, sizeof(uint32_t) * (size_t)g.d.ring_words * n);
-    if (e == cudaSuccess) e = cudaMalloc(&g.amp_ring, sizeof(float) * (size_t)g.d.amp_cap * n);
+    if (e == cudaSuccess) e = cudaMalloc(&g.amp_ring, sizeof(float) * (size_t)g.d.amp_phys * n);
     if (e != cudaSuccess) {
       free_batch(b);
       return fail(e == cudaErrorMemoryAllocation ? WAM_E_NOMEM : WAM_E_CUDA, std::string("state allocation: ") + cudaGetErrorString(e));
@@ -539,6 +540,7 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
     a.f64 = g.f64; a.u32 = g.u32; a.sync_ring = g.sync_ring; a.amp_ring = g.amp_ring;
     a.samples = d_samples; a.stride = stride; a.n = n;
     a.out = d_out; a.out_stride = out_stride; a.out_len = d_out_len; a.tap = d_tap;
+    a.force_generic = (flags & WAM_BATCH_DEBUG_GENERIC_SM) ? 1 : 0;
     L.block_begin[L.n_groups + 1] = L.block_begin[L.n_groups] + (int)((hi - lo + 31) / 32);
     L.n_groups++;
     if (L.n_groups == kMaxGroupsPerLaunch) {
@@ -583,7 +585,7 @@ extern "C" int wam_fsk_batch_demodulate(wam_fsk_batch* b, float* samples, long s
   CUDA_TRY(cudaSetDevice(b->device));
   b->demodulation_calls += 1;
   b->total_samples += (double)n_samples;
-  flags &= WAM_BATCH_WRITEBACK_AGC;
+  flags &= (WAM_BATCH_WRITEBACK_AGC | WAM_BATCH_DEBUG_GENERIC_SM);
 
   // Streams are processed in chunks so that the H2D copy of chunk k+1 overlaps the kernel of
   // chunk k (two CUDA streams, two staging buffers).  Device rows are packed (stride = n padded to 4).

@@ -44,7 +44,8 @@ struct FskDerived {
   int ring_cap_int;     // trunc(ring_cap) = typed-array length
   int ring_words;       // integral path: power-of-two number of 32-bit words (>= total_bits+64 bits)
                         // fractional path: ceil(ring_cap_int/32)
-  int amp_cap;          // dspb * 8 (fsk.ts:150)
+  int amp_cap;          // dspb * 8 (fsk.ts:150): logical capacity of the amplitude ring
+  int amp_phys;         // physical slots (amp_cap + 32): a tile's 16 amplitudes are stored ahead of use
   // word-aligned sync templates (integral ring): for every bit offset o = 0..31 of the window start,
   // tmpl_words words of expected bits and of compare masks (device memory, [32][tmpl_words])
   const uint32_t* tmpl_expect;
@@ -84,7 +85,7 @@ struct DemodArgs {
   double* f64;
   uint32_t* u32;
   uint32_t* sync_ring;  // [ring_words][n_local]
-  float* amp_ring;      // [amp_cap][n_local]
+  float* amp_ring;      // [amp_phys][n_local]
   // data
   float* samples;       // [rows][stride]
   long stride;
@@ -93,6 +94,7 @@ struct DemodArgs {
   long out_stride;
   int32_t* out_len;     // [rows]
   float* tap;           // optional [rows][stride]
+  int force_generic;    // debug: per-sample state machine even where the event-driven one applies
 };
 
 // All configuration groups of a batch run in ONE launch (one-warp CTAs; blockIdx selects the group)

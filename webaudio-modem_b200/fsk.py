@@ -254,7 +254,7 @@ class FSKBatch:
         return int(self._lib.wam_fsk_batch_launch_count(self._h))
 
     # -- host buffers --------------------------------------------------------------------------
-    def demodulate(self, samples: np.ndarray, writeback_agc: bool = False):
+    def demodulate(self, samples: np.ndarray, writeback_agc: bool = False, flags: int = 0):
         """samples float32 [n_streams, n]; returns (out uint8 [n_streams, cap], out_len int32 [n_streams])."""
         assert samples.dtype == np.float32 and samples.ndim == 2 and samples.shape[0] == self.n_streams
         assert samples.strides[1] == 4
@@ -264,11 +264,11 @@ class FSKBatch:
         out_len = np.zeros(self.n_streams, dtype=np.int32)
         L.check(self._lib.wam_fsk_batch_demodulate(
             self._h, samples.ctypes.data, samples.strides[0] // 4, n, out.ctypes.data, cap, out_len.ctypes.data,
-            L.WAM_BATCH_WRITEBACK_AGC if writeback_agc else 0))
+            (L.WAM_BATCH_WRITEBACK_AGC if writeback_agc else 0) | flags))
         return out, out_len
 
-    def demodulate_bytes(self, samples: np.ndarray, writeback_agc: bool = False) -> list[bytes]:
-        out, out_len = self.demodulate(samples, writeback_agc)
+    def demodulate_bytes(self, samples: np.ndarray, writeback_agc: bool = False, flags: int = 0) -> list[bytes]:
+        out, out_len = self.demodulate(samples, writeback_agc, flags)
         return [bytes(out[i, : out_len[i]]) for i in range(self.n_streams)]
 
     # -- device buffers (raw pointers, e.g. torch tensors' data_ptr()) --------------------------
