@@ -7,7 +7,7 @@
 //   fast_rcp    MUFU.RCP64H seed (2^-23) + two Newton steps            -> <= 2 ulp
 //   fast_sqrt   MUFU.RSQ64H seed + two coupled Goldschmidt steps       -> <= 2 ulp
 //   fast_atan2  octant fold, 64-interval table rotation (c_k = k/64, atan(c_k) from the host's
-//               libm), one reciprocal, degree-7 odd polynomial on |t| <= 1/120 -> <= 4 ulp
+//               libm), one reciprocal, degree-7 odd polynomial on |t| <= 1/120 -> <= 6 ulp
 #pragma once
 
 #include <cuda_runtime.h>
@@ -43,50 +43,45 @@ __device__ __forceinline__ double fast_sqrt(double p) {
 
 // atan2(y, x) with JS/libm quadrant conventions (including signed zeros); NaN/Inf are not handled
 // specially (the discriminator never produces them from finite samples).
-__device__ __forceinline__ double fast_atan2(double y, double x, const double* __restrict__ atan_tab) {
-  const double ax = fabs(x), ay = fabs(y);
+// tab[k] = {k / 64, atan(k / 64)}, k = 0..64 (device global memory, read through L1).
+__device__ __forceinline__ double fast_atan2(double y, double x, const double2* __restrict__ tab) {
+  const int hx = __double2hiint(x), hy = __double2hiint(y);
+  const double ax = __hiloint2double(hx & 0x7fffffff, __double2loint(x));
+  const double ay = __hiloint2double(hy & 0x7fffffff, __double2loint(y));
   const bool swap = ay > ax;
   double mx = swap ? ay : ax;
   double mn = swap ? ax : ay;
-  // coarse ratio in f32 picks the table interval
-  float fm = (float)mx, fn = (float)mn;
-  if (!(fm > 1e-30f && fm < 1e30f) && mx > 0.0) {
-    // rare: magnitudes outside the float32 range (incl. denormals) — renormalise, the angle is
-    // scale invariant
-    const int e = ilogb(mx);
-    mx = scalbn(mx, -e);
-    mn = scalbn(mn, -e);
-    fm = (float)mx; fn = (float)mn;
+  if (__double2hiint(mx) < 0x06000000) {
+    // rare: zero / denormal / tiny magnitudes — renormalise (the angle is scale invariant)
+    mx *= 0x1p+900; mn *= 0x1p+900;
   }
-  float r32;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r32) : "f"(fm));
-  const float t32 = (mx > 0.0) ? fn * r32 : 0.0f;
-  int k = __float2int_rn(t32 * 64.0f);
+  // coarse ratio from the reciprocal seed picks the table interval
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(mx));
+  int k = __double2int_rn(mn * r0 * 64.0);
   k = max(0, min(k, 64));
-  const double c = (double)k * 0.015625;
-  const double ak = atan_tab[k];
+  const double2 e = __ldg(tab + k);
   // rotate by -atan(c): t = (mn - c*mx) / (mx + c*mn), |t| <= ~1/120
-  const double xr = fma(c, mn, mx);
-  const double yr = fma(-c, mx, mn);
+  const double xr = fma(e.x, mn, mx);
+  const double yr = fma(-e.x, mx, mn);
   const double t = yr * fast_rcp(xr);
   const double z = t * t;
   double p = fma(z, -0.14285714285714285, 0.2);
   p = fma(z, p, -0.3333333333333333);
   p = p * z;
-  double a = ak + fma(t, p, t);
+  double a = e.y + fma(t, p, t);
   a = (mx > 0.0) ? a : 0.0;
-  if (swap) a = 1.5707963267948966 - a;
-  if (__double2hiint(x) < 0) a = 3.141592653589793 - a;  // sign bit, so that atan2(+-0, -0) = +-pi
+  // quadrant: swap -> pi/2 - a ; x < 0 -> pi - a  (sign bit of x, so that atan2(+-0, -0) = +-pi)
+  const bool xneg = hx < 0;
+  const double base = swap ? 1.5707963267948966 : (xneg ? 3.141592653589793 : 0.0);
+  a = (swap != xneg) ? base - a : base + a;
   return copysign(a, y);
 }
 
 // test hook: out[i] = fast_atan2(y[i], x[i]); out2[i] = fast_sqrt(|x[i]|); out3[i] = fast_rcp(x[i])
 __global__ void fastmath_debug_kernel(const double* __restrict__ y, const double* __restrict__ x, long n,
-                                      const double* __restrict__ atan_tab_g, double* out_atan2, double* out_sqrt,
+                                      const double2* __restrict__ tab, double* out_atan2, double* out_sqrt,
                                       double* out_rcp) {
-  __shared__ double tab[kAtanTableSize];
-  for (int i = threadIdx.x; i < kAtanTableSize; i += blockDim.x) tab[i] = atan_tab_g[i];
-  __syncthreads();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   out_atan2[i] = fast_atan2(y[i], x[i], tab);

@@ -2,8 +2,8 @@
 //
 // Restates FSKCore.demodulateData (src/modems/fsk.ts:190-222) for thousands of independent
 // streams: one thread walks one stream in time and carries the whole reference state
-// (AGC gain, four biquads, LO phase, decimator, both rings, bit-sync / byte / silence state) in
-// registers; a warp owns 32 streams and is its own CTA.  Samples are [stream][time] float32 in
+// (AGC gain, four biquads, LO, decimator, both rings, bit-sync / byte / silence state);
+// a warp owns 32 streams and is its own CTA.  Samples are [stream][time] float32 in
 // HBM; each warp stages 32-stream x 32-sample tiles (one 128-byte line per stream) into shared
 // memory with a double-buffered cp.async pipeline, XOR-swizzled so that the row-per-lane LDS.128
 // reads are bank-conflict free.  Arithmetic is the reference's float64 pipeline with float32
@@ -16,12 +16,18 @@
 //       difference, post low-pass and slicer (fsk.ts:241-264) -> 16 hard bits (a register mask)
 //       and 16 squared magnitudes in smem;
 //   B   the decimated-rate state machine (fsk.ts:278-375): ring puts, silence/EOD, sync search,
-//       majority-vote bit sampler, UART framing.
+//       majority-vote bit sampler, UART framing — event-driven per tile: ring puts, counters and
+//       the vote accumulator advance in bulk with bit operations, and only the samples where
+//       something can happen (EOD crossing, a due sync check, a bit decision) are stepped.
 // resetState() (fsk.ts:175-188; on EOD or a bad start bit) zeroes the A2 state from inside B.  It is
 // rare (about once per frame), so B reports the decimated index of the reset and A2 is REPLAYED
 // for the rest of the tile from the zeroed state; A1 (AGC, pre-filter) is never reset and never
 // replayed.  The result is the reference's exact causal order without a data-dependent branch in
 // the per-sample arithmetic.
+//
+// Register budget: BASELINE config 2 needs 14 one-warp CTAs resident per SM (2048 warps / 148
+// SMs), i.e. <= 128 registers per thread.  Only the A2 state lives in registers for the whole
+// kernel; the A1 state and the state-machine state are parked in shared memory between phases.
 #pragma once
 
 #include "fastmath.cuh"
@@ -29,65 +35,61 @@
 
 namespace wam {
 
-struct LaneState {
-  double gain, px1, px2, py1, py2;
-  double lo_phase, lo_c, lo_s;
+struct A1State {  // AGC + pre-filter (never reset)
+  double gain, py1, py2;
+  float px1, px2;  // pre-filter input history: float32 values (AGC output)
+};
+struct A2State {  // everything resetState() zeroes on the DSP side
+  double lo_c, lo_s;
   double ix1, ix2, iy1, iy2, qx1, qx2, qy1, qy2;
-  double ox1, ox2, oy1, oy2, last_phase, iacc, qacc, sil_thr;
-  double ring_wi, ring_ri, ring_flen;  // fractional-capacity ring emulation only
-  uint32_t dsc, gsc, gmod, bsc, next_idx, bit_acc, bit_cnt, started, current, sil_cnt;
+  double ox1, ox2, oy1, oy2, last_phase, iacc, qacc;
+  uint32_t dsc;
+};
+struct BState {  // decimated-rate state machine
+  double sil_thr;
+  uint32_t gsc, gmod, bsc, next_idx, bit_acc, bit_cnt, started, current, sil_cnt;
   int bitpos;
-  uint32_t ring_pos, ring_len, amp_pos, amp_len, sync_det, eod_ev, err;
-  uint32_t cur_word;
+  uint32_t ring_pos, ring_len, amp_pos, amp_len, cur_word;
   int out_n;
 };
 
-__device__ __forceinline__ void lane_load(LaneState& s, const DemodArgs& a, int li) {
-  const double* f = a.f64 + li;
-  const uint32_t* u = a.u32 + li;
-  const long n = a.n_local;
-  s.gain = f[F_GAIN * n]; s.px1 = f[F_PX1 * n]; s.px2 = f[F_PX2 * n]; s.py1 = f[F_PY1 * n]; s.py2 = f[F_PY2 * n];
-  s.lo_phase = f[F_LO_PHASE * n];
-  s.ix1 = f[F_IX1 * n]; s.ix2 = f[F_IX2 * n]; s.iy1 = f[F_IY1 * n]; s.iy2 = f[F_IY2 * n];
-  s.qx1 = f[F_QX1 * n]; s.qx2 = f[F_QX2 * n]; s.qy1 = f[F_QY1 * n]; s.qy2 = f[F_QY2 * n];
-  s.ox1 = f[F_OX1 * n]; s.ox2 = f[F_OX2 * n]; s.oy1 = f[F_OY1 * n]; s.oy2 = f[F_OY2 * n];
-  s.last_phase = f[F_LAST_PHASE * n]; s.iacc = f[F_IACC * n]; s.qacc = f[F_QACC * n]; s.sil_thr = f[F_SIL_THR * n];
-  s.ring_wi = f[F_RING_WI * n]; s.ring_ri = f[F_RING_RI * n]; s.ring_flen = f[F_RING_LEN * n];
-  s.dsc = u[U_DSC * n]; s.gsc = u[U_GSC * n]; s.gmod = u[U_GMOD * n]; s.bsc = u[U_BSC * n];
-  s.next_idx = u[U_NEXT_IDX * n]; s.bit_acc = u[U_BIT_ACC * n]; s.bit_cnt = u[U_BIT_CNT * n];
-  s.started = u[U_STARTED * n]; s.bitpos = (int)u[U_BITPOS * n]; s.current = u[U_CURRENT * n];
-  s.sil_cnt = u[U_SIL_CNT * n]; s.ring_pos = u[U_RING_POS * n]; s.ring_len = u[U_RING_LEN * n];
-  s.amp_pos = u[U_AMP_POS * n]; s.amp_len = u[U_AMP_LEN * n]; s.sync_det = u[U_SYNC_DET * n];
-  s.eod_ev = u[U_EOD_EV * n]; s.err = u[U_ERR * n];
-  s.out_n = 0;
-}
+// shared-memory parking slots (word-major, one column per lane)
+constexpr int kParkD = 4;   // gain, py1, py2, sil_thr
+constexpr int kParkU = 16;  // px1, px2 (float bits), 14 state-machine words
 
-__device__ __forceinline__ void lane_store(const LaneState& s, const DemodArgs& a, int li) {
-  double* f = a.f64 + li;
-  uint32_t* u = a.u32 + li;
-  const long n = a.n_local;
-  f[F_GAIN * n] = s.gain; f[F_PX1 * n] = s.px1; f[F_PX2 * n] = s.px2; f[F_PY1 * n] = s.py1; f[F_PY2 * n] = s.py2;
-  f[F_LO_PHASE * n] = s.lo_phase;
-  f[F_IX1 * n] = s.ix1; f[F_IX2 * n] = s.ix2; f[F_IY1 * n] = s.iy1; f[F_IY2 * n] = s.iy2;
-  f[F_QX1 * n] = s.qx1; f[F_QX2 * n] = s.qx2; f[F_QY1 * n] = s.qy1; f[F_QY2 * n] = s.qy2;
-  f[F_OX1 * n] = s.ox1; f[F_OX2 * n] = s.ox2; f[F_OY1 * n] = s.oy1; f[F_OY2 * n] = s.oy2;
-  f[F_LAST_PHASE * n] = s.last_phase; f[F_IACC * n] = s.iacc; f[F_QACC * n] = s.qacc; f[F_SIL_THR * n] = s.sil_thr;
-  f[F_RING_WI * n] = s.ring_wi; f[F_RING_RI * n] = s.ring_ri; f[F_RING_LEN * n] = s.ring_flen;
-  u[U_DSC * n] = s.dsc; u[U_GSC * n] = s.gsc; u[U_GMOD * n] = s.gmod; u[U_BSC * n] = s.bsc;
-  u[U_NEXT_IDX * n] = s.next_idx; u[U_BIT_ACC * n] = s.bit_acc; u[U_BIT_CNT * n] = s.bit_cnt;
-  u[U_STARTED * n] = s.started; u[U_BITPOS * n] = (uint32_t)s.bitpos; u[U_CURRENT * n] = s.current;
-  u[U_SIL_CNT * n] = s.sil_cnt; u[U_RING_POS * n] = s.ring_pos; u[U_RING_LEN * n] = s.ring_len;
-  u[U_AMP_POS * n] = s.amp_pos; u[U_AMP_LEN * n] = s.amp_len; u[U_SYNC_DET * n] = s.sync_det;
-  u[U_EOD_EV * n] = s.eod_ev; u[U_ERR * n] = s.err;
+__device__ __forceinline__ void a1_load(A1State& s, const double (*pd)[32], const uint32_t (*pu)[32], int lane) {
+  s.gain = pd[0][lane]; s.py1 = pd[1][lane]; s.py2 = pd[2][lane];
+  s.px1 = __uint_as_float(pu[0][lane]); s.px2 = __uint_as_float(pu[1][lane]);
+}
+__device__ __forceinline__ void a1_store(const A1State& s, double (*pd)[32], uint32_t (*pu)[32], int lane) {
+  pd[0][lane] = s.gain; pd[1][lane] = s.py1; pd[2][lane] = s.py2;
+  pu[0][lane] = __float_as_uint(s.px1); pu[1][lane] = __float_as_uint(s.px2);
+}
+__device__ __forceinline__ void b_load(BState& b, const double (*pd)[32], const uint32_t (*pu)[32], int lane) {
+  b.sil_thr = pd[3][lane];
+  b.gsc = pu[2][lane]; b.gmod = pu[3][lane]; b.bsc = pu[4][lane]; b.next_idx = pu[5][lane];
+  b.bit_acc = pu[6][lane]; b.bit_cnt = pu[7][lane];
+  const uint32_t f = pu[8][lane];
+  b.started = f & 1u; b.bitpos = (int)((f >> 8) & 0xffu) - 1; b.current = (f >> 16) & 0xffu;
+  b.sil_cnt = pu[9][lane]; b.ring_pos = pu[10][lane]; b.ring_len = pu[11][lane];
+  b.amp_pos = pu[12][lane]; b.amp_len = pu[13][lane]; b.cur_word = pu[14][lane]; b.out_n = (int)pu[15][lane];
+}
+__device__ __forceinline__ void b_store(const BState& b, double (*pd)[32], uint32_t (*pu)[32], int lane) {
+  pd[3][lane] = b.sil_thr;
+  pu[2][lane] = b.gsc; pu[3][lane] = b.gmod; pu[4][lane] = b.bsc; pu[5][lane] = b.next_idx;
+  pu[6][lane] = b.bit_acc; pu[7][lane] = b.bit_cnt;
+  pu[8][lane] = (b.started & 1u) | ((uint32_t)(b.bitpos + 1) << 8) | ((b.current & 0xffu) << 16);
+  pu[9][lane] = b.sil_cnt; pu[10][lane] = b.ring_pos; pu[11][lane] = b.ring_len;
+  pu[12][lane] = b.amp_pos; pu[13][lane] = b.amp_len; pu[14][lane] = b.cur_word; pu[15][lane] = (uint32_t)b.out_n;
 }
 
 // FSKCore.resetState — fsk.ts:175-188.  Not reset: AGC, pre-filter, rings, silence threshold.
-__device__ __forceinline__ void reset_state(LaneState& s) {
-  s.lo_phase = 0.0; s.lo_c = 1.0; s.lo_s = 0.0; s.last_phase = 0.0;
-  s.gsc = 0; s.gmod = 0; s.bsc = 0; s.bit_acc = 0; s.bit_cnt = 0; s.next_idx = 0;
-  s.current = 0; s.bitpos = 0;
-  s.started = 0;
-  s.sil_cnt = 0;
+__device__ __forceinline__ void reset_state(A2State& s, BState& b) {
+  s.lo_c = 1.0; s.lo_s = 0.0; s.last_phase = 0.0;  // localOscPhase = 0
+  b.gsc = 0; b.gmod = 0; b.bsc = 0; b.bit_acc = 0; b.bit_cnt = 0; b.next_idx = 0;
+  b.current = 0; b.bitpos = 0;
+  b.started = 0;
+  b.sil_cnt = 0;
   s.ix1 = s.ix2 = s.iy1 = s.iy2 = 0.0;
   s.qx1 = s.qx2 = s.qy1 = s.qy2 = 0.0;
   s.ox1 = s.ox2 = s.oy1 = s.oy2 = 0.0;
@@ -127,6 +129,7 @@ __device__ __noinline__ int sync_mismatches(const uint32_t* __restrict__ ring, l
 }
 
 // ---- literal emulation of RingBuffer with a fractional capacity (utils.ts:14-47) ----
+// writeIndex / readIndex / length live in the global f64 state (slow path, quirk configurations).
 __device__ __forceinline__ double ring_fmod_cap(double x, double cap) {  // x in [0, 3*cap)
   const double cap2 = cap + cap;
   if (x >= cap2) return x - cap2;  // exact (Sterbenz)
@@ -137,19 +140,23 @@ __device__ __forceinline__ bool ring_index_valid(double p, int buflen, int& ip) 
   ip = (int)p;
   return ((double)ip == p) && ip >= 0 && ip < buflen;
 }
-__device__ __forceinline__ void ring_put_fractional(LaneState& s, uint32_t* ring, long ns, int bit,
-                                                    const FskDerived& d) {
+__device__ __noinline__ bool ring_put_fractional(double* __restrict__ f64, long ns, uint32_t* ring, int bit,
+                                                 const FskDerived& d) {
+  double wi = f64[F_RING_WI * ns], ri = f64[F_RING_RI * ns], flen = f64[F_RING_LEN * ns];
   int ip;
-  if (ring_index_valid(s.ring_wi, d.ring_cap_int, ip)) {
+  if (ring_index_valid(wi, d.ring_cap_int, ip)) {
     uint32_t* w = ring + (long)(ip >> 5) * ns;
     *w = (*w & ~(1u << (ip & 31))) | ((uint32_t)bit << (ip & 31));
   }
-  s.ring_wi = ring_fmod_cap(s.ring_wi + 1.0, d.ring_cap);
-  if (s.ring_flen < d.ring_cap) s.ring_flen += 1.0;
-  else s.ring_ri = ring_fmod_cap(s.ring_ri + 1.0, d.ring_cap);
+  wi = ring_fmod_cap(wi + 1.0, d.ring_cap);
+  if (flen < d.ring_cap) flen += 1.0;
+  else ri = ring_fmod_cap(ri + 1.0, d.ring_cap);
+  f64[F_RING_WI * ns] = wi; f64[F_RING_RI * ns] = ri; f64[F_RING_LEN * ns] = flen;
+  return flen >= (double)d.total_bits;
 }
-__device__ __noinline__ int sync_matched_fractional(double ring_ri, double ring_flen, const uint32_t* __restrict__ ring,
-                                                    long ns, const FskDerived& d) {
+__device__ __noinline__ int sync_matched_fractional(const double* __restrict__ f64, long ns,
+                                                    const uint32_t* __restrict__ ring, const FskDerived& d) {
+  const double ring_ri = f64[F_RING_RI * ns], ring_flen = f64[F_RING_LEN * ns];
   int matched = 0;
   int remaining = d.nbits * d.dspb;
   for (int j = 0; j < d.nbits; ++j) {
@@ -174,31 +181,32 @@ __device__ __noinline__ int sync_matched_fractional(double ring_ri, double ring_
 }
 
 // FSKCore.processByte — fsk.ts:346-375.  Returns true when resetState() ran.
-__device__ __forceinline__ bool process_byte(LaneState& s, int bit, const FskDerived& d, uint8_t* out_row,
-                                             long out_cap) {
-  const int bp = s.bitpos;
+__device__ __forceinline__ bool process_byte(A2State& s, BState& b, int bit, const DemodArgs& a, int li,
+                                             uint8_t* out_row) {
+  const FskDerived& d = a.d;
+  const int bp = b.bitpos;
   if (bp == 0) {
-    if (bit != 0) { reset_state(s); return true; }
+    if (bit != 0) { reset_state(s, b); return true; }
   } else if (bp >= 1 && bp <= 8) {
-    s.current |= (uint32_t)bit << (8 - bp);
+    b.current |= (uint32_t)bit << (8 - bp);
   } else if (d.parity != 0 && bp == 9) {
     // parity bit is skipped, never checked
   } else if (bp == d.stop_pos) {
-    if (bit != 1) { s.started = 0; return false; }
-    if (s.out_n < out_cap) out_row[s.out_n] = (uint8_t)s.current;
-    else s.err |= WAM_ERR_OUT_OVERFLOW;
-    s.out_n++;
-    s.current = 0;
-    s.bitpos = -1;
+    if (bit != 1) { b.started = 0; return false; }
+    if (b.out_n < a.out_stride) out_row[b.out_n] = (uint8_t)b.current;
+    else a.u32[(long)U_ERR * a.n_local + li] |= WAM_ERR_OUT_OVERFLOW;
+    b.out_n++;
+    b.current = 0;
+    b.bitpos = -1;
   } else {
-    s.started = 0;
+    b.started = 0;
     return false;
   }
-  s.bitpos++;
+  b.bitpos++;
   return false;
 }
 
-// silence threshold = mean(amplitude ring) * 0.1, summed oldest -> newest in f64 — fsk.ts:321-326
+// silence threshold = mean(amplitude ring) * 0.1, summed oldest -> newest in f64 — fsk.ts:321-326.
 // amp_next = physical slot following the newest entry; the ring has amp_phys physical slots of
 // which the newest amp_len (<= amp_cap) are the reference's ring contents.
 __device__ __noinline__ double amp_ring_threshold(const float* __restrict__ aring, long ns, uint32_t amp_next,
@@ -215,107 +223,97 @@ __device__ __noinline__ double amp_ring_threshold(const float* __restrict__ arin
 // One decimated sample of FSKCore.processDownsampledBit (fsk.ts:278-344) AFTER the ring puts:
 // silence/EOD, sync search or vote/bit decision.  ring_pos / amp_next describe the rings including
 // this sample.  Returns true when resetState() ran.
-__device__ __forceinline__ bool sm_step(LaneState& s, int bit, double amplitude, uint32_t ring_pos, bool ring_ready,
-                                        uint32_t amp_next, uint32_t amp_len, const DemodArgs& a, int li,
-                                        uint8_t* out_row, bool& thr_changed) {
+__device__ __forceinline__ bool sm_step(A2State& s, BState& b, int bit, double amplitude, uint32_t ring_pos,
+                                        bool ring_ready, uint32_t amp_next, uint32_t amp_len, const DemodArgs& a,
+                                        int li, uint8_t* out_row, bool& thr_changed) {
   const FskDerived& d = a.d;
   const long ns = a.n_local;
   // silence / EOD — fsk.ts:285-295
-  s.gsc++;
-  s.gmod = (s.gmod + 1u == (uint32_t)d.check_period) ? 0u : s.gmod + 1u;
-  if (amplitude < s.sil_thr) {
-    s.sil_cnt++;
-    if (s.sil_cnt >= (uint32_t)d.eod_count) {
-      s.eod_ev++;
-      reset_state(s);
+  b.gsc++;
+  b.gmod = (b.gmod + 1u == (uint32_t)d.check_period) ? 0u : b.gmod + 1u;
+  if (amplitude < b.sil_thr) {
+    b.sil_cnt++;
+    if (b.sil_cnt >= (uint32_t)d.eod_count) {
+      a.u32[(long)U_EOD_EV * ns + li]++;  // emit('eod')
+      reset_state(s, b);
       return true;
     }
   } else {
-    s.sil_cnt = 0;
+    b.sil_cnt = 0;
   }
-  if (!s.started) {
+  if (!b.started) {
     // fsk.ts:297-328
-    const bool due = d.check_period > 0 && s.gmod == 0u;
+    const bool due = d.check_period > 0 && b.gmod == 0u;
     if (due && ring_ready && d.total_bits > 0) {
       uint32_t* ring = a.sync_ring + li;
       int matched;
       if (!d.ring_fractional) {
-        if ((s.ring_pos & 31u) != 0u)  // flush the register copy of the newest (partial) word
-          ring[(long)((s.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns] = s.cur_word;
+        if ((b.ring_pos & 31u) != 0u)  // flush the register copy of the newest (partial) word
+          ring[(long)((b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns] = b.cur_word;
         matched = (d.total_bits - d.dspb) - sync_mismatches(ring, ns, ring_pos, d);
       } else {
-        matched = sync_matched_fractional(s.ring_ri, s.ring_flen, ring, ns, d);
+        matched = sync_matched_fractional(a.f64 + li, ns, ring, d);
       }
       if (matched >= d.min_matched) {
-        s.started = 1;
-        s.current = 0; s.bitpos = 0;
-        s.bit_acc = 0; s.bit_cnt = 0; s.bsc = 0; s.next_idx = 0;
-        s.sync_det++;
-        s.sil_thr = amp_ring_threshold(a.amp_ring + li, ns, amp_next, amp_len, (uint32_t)d.amp_phys);
+        b.started = 1;
+        b.current = 0; b.bitpos = 0;
+        b.bit_acc = 0; b.bit_cnt = 0; b.bsc = 0; b.next_idx = 0;
+        a.u32[(long)U_SYNC_DET * ns + li]++;
+        b.sil_thr = amp_ring_threshold(a.amp_ring + li, ns, amp_next, amp_len, (uint32_t)d.amp_phys);
         thr_changed = true;
       }
     }
     return false;
   }
   // fsk.ts:330-341
-  s.bit_acc += (uint32_t)bit;
-  s.bit_cnt++;
-  s.bsc++;
-  if (s.bsc >= s.next_idx) {
-    const int decided = (2u * s.bit_acc > s.bit_cnt) ? 1 : 0;  // acc > count/2
-    s.bit_acc = 0; s.bit_cnt = 0;
-    s.next_idx += (uint32_t)d.dspb;
-    const bool was_started = s.started != 0;
-    const bool rst = process_byte(s, decided, d, out_row, a.out_stride);
+  b.bit_acc += (uint32_t)bit;
+  b.bit_cnt++;
+  b.bsc++;
+  if (b.bsc >= b.next_idx) {
+    const int decided = (2u * b.bit_acc > b.bit_cnt) ? 1 : 0;  // acc > count/2
+    b.bit_acc = 0; b.bit_cnt = 0;
+    b.next_idx += (uint32_t)d.dspb;
+    const bool rst = process_byte(s, b, decided, a, li, out_row);
     // gmod is only maintained while searching: resynchronise it when the frame ends
-    if (!rst && was_started && !s.started && d.check_period > 0) s.gmod = s.gsc % (uint32_t)d.check_period;
+    if (!rst && !b.started && d.check_period > 0) b.gmod = b.gsc % (uint32_t)d.check_period;
     return rst;
   }
   return false;
 }
 
 // Generic per-sample state machine (any ring kind, any eod_count): puts + sm_step.
-__device__ __forceinline__ bool process_downsampled_bit(LaneState& s, int bit, double amplitude, const DemodArgs& a,
-                                                        int li, uint8_t* out_row) {
+__device__ __forceinline__ bool sm_sample_generic(A2State& s, BState& b, int bit, double amplitude,
+                                                  const DemodArgs& a, int li, uint8_t* out_row) {
   const FskDerived& d = a.d;
   const long ns = a.n_local;
   uint32_t* ring = a.sync_ring + li;
-  float* aring = a.amp_ring + li;
   bool ready;
   // syncSamplesBuffer.put(bit) — fsk.ts:281
   if (!d.ring_fractional) {
-    s.cur_word |= (uint32_t)bit << (s.ring_pos & 31u);
-    s.ring_pos++;
-    if ((s.ring_pos & 31u) == 0u) {
-      ring[(long)(((s.ring_pos - 1u) >> 5) & (uint32_t)(d.ring_words - 1)) * ns] = s.cur_word;
-      s.cur_word = 0u;
+    b.cur_word |= (uint32_t)bit << (b.ring_pos & 31u);
+    b.ring_pos++;
+    if ((b.ring_pos & 31u) == 0u) {
+      ring[(long)(((b.ring_pos - 1u) >> 5) & (uint32_t)(d.ring_words - 1)) * ns] = b.cur_word;
+      b.cur_word = 0u;
     }
-    s.ring_len = min(s.ring_len + 1u, (uint32_t)d.ring_cap_int);
-    ready = s.ring_len >= (uint32_t)d.total_bits;
+    b.ring_len = min(b.ring_len + 1u, (uint32_t)d.ring_cap_int);
+    ready = b.ring_len >= (uint32_t)d.total_bits;
   } else {
-    ring_put_fractional(s, ring, ns, bit, d);
-    ready = s.ring_flen >= (double)d.total_bits;
+    ready = ring_put_fractional(a.f64 + li, ns, ring, bit, d);
   }
   // syncAmplitudeBuffer.put(amplitude) — fsk.ts:282 (Float32Array store)
-  aring[(long)s.amp_pos * ns] = (float)amplitude;
-  s.amp_pos = (s.amp_pos + 1u == (uint32_t)d.amp_phys) ? 0u : s.amp_pos + 1u;
-  s.amp_len = min(s.amp_len + 1u, (uint32_t)d.amp_cap);
+  a.amp_ring[(long)b.amp_pos * ns + li] = (float)amplitude;
+  b.amp_pos = (b.amp_pos + 1u == (uint32_t)d.amp_phys) ? 0u : b.amp_pos + 1u;
+  b.amp_len = min(b.amp_len + 1u, (uint32_t)d.amp_cap);
   bool thr_changed = false;
-  const bool was_started = s.started != 0;
-  const bool rst = sm_step(s, bit, amplitude, s.ring_pos, ready, s.amp_pos, s.amp_len, a, li, out_row, thr_changed);
-  // while a frame is being received sm_step does not advance gmod beyond the wrap it does itself;
-  // the generic path keeps it exact anyway (it increments every sample above)
-  (void)was_started;
-  return rst;
+  return sm_step(s, b, bit, amplitude, b.ring_pos, ready, b.amp_pos, b.amp_len, a, li, out_row, thr_changed);
 }
 
 // Event-driven state machine for one tile (integral ring, eod_count > 16).  `bits` holds the hard
 // decisions of decimated samples 0..nk-1 of the tile, amp[k*32] their amplitudes (f64, smem).
-// Ring puts, counters and the vote accumulator are advanced in bulk with bit operations; only the
-// samples where something can happen (EOD crossing, a due sync check, a bit decision) go through
-// sm_step.  Returns the decimated index at which resetState() ran, or -1.
-__device__ __forceinline__ int sm_tile_events(LaneState& s, uint32_t bits, const double* __restrict__ amp, int b_from,
-                                              int nk, uint32_t pos_t0, uint32_t len_t0, uint32_t slot_t0,
+// Returns the decimated index at which resetState() ran, or -1.
+__device__ __forceinline__ int sm_tile_events(A2State& s, BState& b, uint32_t bits, const double* __restrict__ amp,
+                                              int b_from, int nk, uint32_t pos_t0, uint32_t len_t0, uint32_t slot_t0,
                                               uint32_t alen_t0, const DemodArgs& a, int li, uint8_t* out_row) {
   const FskDerived& d = a.d;
   const long ns = a.n_local;
@@ -328,18 +326,18 @@ __device__ __forceinline__ int sm_tile_events(LaneState& s, uint32_t bits, const
     const uint32_t p = pos_t0 + (uint32_t)b_from;
     if (b_from > 0) {
       // replay pass: the word holding position p may already have been flushed
-      ring[(long)((s.ring_pos >> 5) & wmask) * ns] = s.cur_word;
-      s.cur_word = ring[(long)((p >> 5) & wmask) * ns];
+      ring[(long)((b.ring_pos >> 5) & wmask) * ns] = b.cur_word;
+      b.cur_word = ring[(long)((p >> 5) & wmask) * ns];
     }
     const uint32_t cnt = (uint32_t)(nk - b_from);
     const uint32_t o = p & 31u;
     const uint32_t chunk = (bits >> b_from) & ((1u << cnt) - 1u);
-    s.cur_word = (s.cur_word & ((1u << o) - 1u)) | (chunk << o);
+    b.cur_word = (b.cur_word & ((1u << o) - 1u)) | (chunk << o);
     if (o + cnt >= 32u) {
-      ring[(long)((p >> 5) & wmask) * ns] = s.cur_word;
-      s.cur_word = (o + cnt > 32u) ? (chunk >> (32u - o)) : 0u;
+      ring[(long)((p >> 5) & wmask) * ns] = b.cur_word;
+      b.cur_word = (o + cnt > 32u) ? (chunk >> (32u - o)) : 0u;
     }
-    s.ring_pos = pos_t0 + (uint32_t)nk;
+    b.ring_pos = pos_t0 + (uint32_t)nk;
     uint32_t slot = slot_t0 + (uint32_t)b_from;
     if (slot >= (uint32_t)d.amp_phys) slot -= (uint32_t)d.amp_phys;
     for (int k = b_from; k < nk; ++k) {
@@ -349,7 +347,7 @@ __device__ __forceinline__ int sm_tile_events(LaneState& s, uint32_t bits, const
   }
   // silence flags for the current threshold — fsk.ts:286
   uint32_t silent = 0u;
-  for (int k = b_from; k < nk; ++k) silent |= (amp[k * 32] < s.sil_thr ? 1u : 0u) << k;
+  for (int k = b_from; k < nk; ++k) silent |= (amp[k * 32] < b.sil_thr ? 1u : 0u) << k;
 
   int k = b_from;
   while (k < nk) {
@@ -357,27 +355,27 @@ __device__ __forceinline__ int sm_tile_events(LaneState& s, uint32_t bits, const
     int k_evt = nk;
     {
       const uint32_t run = (uint32_t)__ffs((int)(~(silent >> k))) - 1u;  // leading silent run from k
-      const uint32_t need = (uint32_t)d.eod_count - s.sil_cnt - 1u;      // silent samples before the EOD one
+      const uint32_t need = (uint32_t)d.eod_count - b.sil_cnt - 1u;      // silent samples before the EOD one
       if (need < run) k_evt = min(k_evt, k + (int)need);
     }
-    if (!s.started) {
-      if (d.check_period > 0) k_evt = min(k_evt, k + (int)((uint32_t)d.check_period - 1u - s.gmod));
+    if (!b.started) {
+      if (d.check_period > 0) k_evt = min(k_evt, k + (int)((uint32_t)d.check_period - 1u - b.gmod));
     } else {
-      const uint32_t nb = s.bsc + 1u;
-      k_evt = min(k_evt, k + (int)(s.next_idx > nb ? s.next_idx - nb : 0u));
+      const uint32_t nb = b.bsc + 1u;
+      k_evt = min(k_evt, k + (int)(b.next_idx > nb ? b.next_idx - nb : 0u));
     }
     // ---- bulk advance over [k, k_evt)
     const int len = k_evt - k;
     if (len > 0) {
       const uint32_t m = ((1u << len) - 1u) << k;
-      s.gsc += (uint32_t)len;
-      if (!s.started) s.gmod += (uint32_t)len;  // stays below check_period by construction
+      b.gsc += (uint32_t)len;
+      if (!b.started) b.gmod += (uint32_t)len;  // stays below check_period by construction
       const uint32_t nz = ~silent & m;
-      s.sil_cnt = nz ? (uint32_t)(k_evt - 1) - (31u - (uint32_t)__clz((int)nz)) : s.sil_cnt + (uint32_t)len;
-      if (s.started) {
-        s.bit_acc += (uint32_t)__popc(bits & m);
-        s.bit_cnt += (uint32_t)len;
-        s.bsc += (uint32_t)len;
+      b.sil_cnt = nz ? (uint32_t)(k_evt - 1) - (31u - (uint32_t)__clz((int)nz)) : b.sil_cnt + (uint32_t)len;
+      if (b.started) {
+        b.bit_acc += (uint32_t)__popc(bits & m);
+        b.bit_cnt += (uint32_t)len;
+        b.bsc += (uint32_t)len;
       }
     }
     if (k_evt >= nk) break;
@@ -388,12 +386,12 @@ __device__ __forceinline__ int sm_tile_events(LaneState& s, uint32_t bits, const
     if (slot_next >= (uint32_t)d.amp_phys) slot_next -= (uint32_t)d.amp_phys;
     const uint32_t alen = min(alen_t0 + (uint32_t)k_evt + 1u, (uint32_t)d.amp_cap);
     bool thr_changed = false;
-    if (sm_step(s, (int)((bits >> k_evt) & 1u), amp[k_evt * 32], pos_k, ready, slot_next, alen, a, li, out_row,
+    if (sm_step(s, b, (int)((bits >> k_evt) & 1u), amp[k_evt * 32], pos_k, ready, slot_next, alen, a, li, out_row,
                 thr_changed))
       return k_evt;
     if (thr_changed) {
       silent = 0u;
-      for (int kk = k_evt + 1; kk < nk; ++kk) silent |= (amp[kk * 32] < s.sil_thr ? 1u : 0u) << kk;
+      for (int kk = k_evt + 1; kk < nk; ++kk) silent |= (amp[kk * 32] < b.sil_thr ? 1u : 0u) << kk;
     }
     k = k_evt + 1;
   }
@@ -413,7 +411,7 @@ __device__ __forceinline__ double agc_target(float level) {
   return fma(r, e, r);
 }
 
-__device__ __forceinline__ float phase_a1_sample(LaneState& s, float x, const FskDerived& d, bool agc, double att,
+__device__ __forceinline__ float phase_a1_sample(A1State& s, float x, const FskDerived& d, bool agc, double att,
                                                  double rel, float& agc_out) {
   // AGC, fsk.ts:52-76 (evaluated unconditionally, selected by `agc`, so the code stays branch-free)
   const float sg_agc = (float)((double)x * s.gain);
@@ -427,19 +425,20 @@ __device__ __forceinline__ float phase_a1_sample(LaneState& s, float x, const Fs
   s.gain = (agc && level > 0.0f) ? g : s.gain;
   agc_out = sg;
   // pre-filter: butterworthBandpass has b1 == 0 and b2 == -b0 exactly (filters.ts:230)
-  const double xin = (double)sg;
-  double y = d.pre_b0 * (xin - s.px2);
+  double y = d.pre_b0 * ((double)sg - (double)s.px2);
   y = fma(-d.pre_a1, s.py1, y);
   y = fma(-d.pre_a2, s.py2, y);
-  s.px2 = s.px1; s.px1 = xin; s.py2 = s.py1; s.py1 = y;
+  s.px2 = s.px1; s.px1 = sg; s.py2 = s.py1; s.py1 = y;
   return (float)y;  // Float32Array store of processBuffer (filters.ts:82-85)
 }
 
 // ---- phase A2: one input sample through LO mix and the I/Q low-pass filters --------------------
-// butterworthLowpass has b1 == 2*b0 and b2 == b0 exactly (filters.ts:188).
-__device__ __forceinline__ void phase_a2_half(LaneState& s, float pf, const FskDerived& d, double& yi, double& yq) {
+// butterworthLowpass has b1 == 2*b0 and b2 == b0 exactly (filters.ts:188).  The LO is a rotation
+// recurrence started from (1, 0) at every reset (cos/sin of the pre-increment phase, fsk.ts:229-232),
+// renormalised once per tile.
+__device__ __forceinline__ void phase_a2_half(A2State& s, float pf, const FskDerived& d, double& yi, double& yq) {
   const double smp = (double)pf;
-  const double xi = smp * s.lo_c;  // fsk.ts:229-230 (cos/sin of the pre-increment phase)
+  const double xi = smp * s.lo_c;
   const double xq = smp * s.lo_s;
   const double nc = s.lo_c * d.cos_omega - s.lo_s * d.sin_omega;
   const double nsn = s.lo_s * d.cos_omega + s.lo_c * d.sin_omega;
@@ -460,11 +459,10 @@ __device__ __forceinline__ void phase_a2_half(LaneState& s, float pf, const FskD
 
 // decimated-rate discriminator (fsk.ts:246-264) on the summed pair (2*avgI, 2*avgQ): returns the
 // hard bit, and the squared magnitude whose root is twice the reference amplitude.
-__device__ __forceinline__ int phase_a2_decim(LaneState& s, double si, double sq, const FskDerived& d,
-                                              const double* __restrict__ atan_tab, double& p) {
+__device__ __forceinline__ int phase_a2_decim(A2State& s, double si, double sq, const FskDerived& d, double& p) {
   const double kTwoPi = 6.283185307179586;  // 2 * Math.PI
   const double kPi = 3.141592653589793;
-  const double phase = fast_atan2(sq, si, atan_tab);  // atan2(avgQ, avgI): scale invariant
+  const double phase = fast_atan2(sq, si, d.atan_tab);  // atan2(avgQ, avgI): scale invariant
   p = __dadd_rn(__dmul_rn(si, si), __dmul_rn(sq, sq));
   double pd = phase - s.last_phase;
   if (pd > kPi) pd -= kTwoPi;
@@ -500,7 +498,7 @@ __device__ __forceinline__ int tile_index(int row, int col) {
 
 // Stage one 32-stream x 32-sample tile starting at sample t0 into `tile`.
 template <bool ALIGNED>
-__device__ __forceinline__ void stage_tile(float* tile, const DemodArgs& a, const long* rows, long t0, int lane) {
+__device__ __forceinline__ void stage_tile(float* tile, const DemodArgs& a, const int* rows, long t0, int lane) {
   if (ALIGNED) {
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
@@ -532,38 +530,60 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
     if (i < L.n_groups && (int)blockIdx.x >= L.block_begin[i]) gi = i;
   const DemodArgs& a = L.g[gi];
   // stage buffers: input tile (swizzled f32 [32][32]); after A1 the same 4 KiB hold the squared
-  // magnitudes of the tile as f64 [16][32]
+  // magnitudes / amplitudes of the tile as f64 [16][32]
   __shared__ __align__(128) float tiles[kStages][kTile * kTile];
   __shared__ __align__(128) float pfbuf[kTile * 32];  // pre-filtered samples [i][lane]
-  __shared__ long rows[32];
-  __shared__ double atan_tab[kAtanTableSize];
+  __shared__ double park_d[kParkD][32];
+  __shared__ uint32_t park_u[kParkU][32];
+  __shared__ int rows[32];
 
   const int lane = threadIdx.x;
   const int li = a.l_begin + ((int)blockIdx.x - L.block_begin[gi]) * 32 + lane;
   const bool active = li < a.l_end;
-  long row = -1;
-  if (active) row = (long)(a.ids ? a.ids[li] : a.id0 + li) - a.row_base;
+  int row = -1;
+  if (active) row = (a.ids ? a.ids[li] : a.id0 + li) - a.row_base;
   rows[lane] = row;
-  for (int i = lane; i < kAtanTableSize; i += 32) atan_tab[i] = a.d.atan_tab[i];
-  __syncwarp();
 
   const FskDerived& d = a.d;
-  LaneState s;
+  const long ns = a.n_local;
+  A2State s;
+  s.lo_c = 1.0; s.lo_s = 0.0;
+  s.ix1 = s.ix2 = s.iy1 = s.iy2 = s.qx1 = s.qx2 = s.qy1 = s.qy2 = 0.0;
+  s.ox1 = s.ox2 = s.oy1 = s.oy2 = s.last_phase = s.iacc = s.qacc = 0.0;
+  s.dsc = 0;
   if (active) {
-    lane_load(s, a, li);
-    sincos(s.lo_phase, &s.lo_s, &s.lo_c);  // exact (1, 0) for the post-reset phase 0
-    s.cur_word = 0u;
-    if (!d.ring_fractional && (s.ring_pos & 31u) != 0u) {
-      const uint32_t w = a.sync_ring[(long)((s.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * a.n_local + li];
-      s.cur_word = w & ((1u << (s.ring_pos & 31u)) - 1u);
+    const double* f = a.f64 + li;
+    const uint32_t* u = a.u32 + li;
+    s.lo_c = f[F_LO_C * ns]; s.lo_s = f[F_LO_S * ns];
+    s.ix1 = f[F_IX1 * ns]; s.ix2 = f[F_IX2 * ns]; s.iy1 = f[F_IY1 * ns]; s.iy2 = f[F_IY2 * ns];
+    s.qx1 = f[F_QX1 * ns]; s.qx2 = f[F_QX2 * ns]; s.qy1 = f[F_QY1 * ns]; s.qy2 = f[F_QY2 * ns];
+    s.ox1 = f[F_OX1 * ns]; s.ox2 = f[F_OX2 * ns]; s.oy1 = f[F_OY1 * ns]; s.oy2 = f[F_OY2 * ns];
+    s.last_phase = f[F_LAST_PHASE * ns]; s.iacc = f[F_IACC * ns]; s.qacc = f[F_QACC * ns];
+    s.dsc = u[U_DSC * ns];
+    A1State a1;
+    a1.gain = f[F_GAIN * ns]; a1.py1 = f[F_PY1 * ns]; a1.py2 = f[F_PY2 * ns];
+    a1.px1 = (float)f[F_PX1 * ns]; a1.px2 = (float)f[F_PX2 * ns];
+    a1_store(a1, park_d, park_u, lane);
+    BState b;
+    b.sil_thr = f[F_SIL_THR * ns];
+    b.gsc = u[U_GSC * ns]; b.gmod = u[U_GMOD * ns]; b.bsc = u[U_BSC * ns]; b.next_idx = u[U_NEXT_IDX * ns];
+    b.bit_acc = u[U_BIT_ACC * ns]; b.bit_cnt = u[U_BIT_CNT * ns]; b.started = u[U_STARTED * ns];
+    b.bitpos = (int)u[U_BITPOS * ns]; b.current = u[U_CURRENT * ns]; b.sil_cnt = u[U_SIL_CNT * ns];
+    b.ring_pos = u[U_RING_POS * ns]; b.ring_len = u[U_RING_LEN * ns];
+    b.amp_pos = u[U_AMP_POS * ns]; b.amp_len = u[U_AMP_LEN * ns];
+    b.out_n = 0;
+    b.cur_word = 0u;
+    if (!d.ring_fractional && (b.ring_pos & 31u) != 0u) {
+      const uint32_t w = a.sync_ring[(long)((b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns + li];
+      b.cur_word = w & ((1u << (b.ring_pos & 31u)) - 1u);
     }
+    b_store(b, park_d, park_u, lane);
   }
-  uint8_t* out_row = active ? a.out + row * a.out_stride : nullptr;
-  float* wb_row = ((WRITEBACK || TAP) && active) ? (WRITEBACK ? a.samples : a.tap) + row * a.stride : nullptr;
-  float* tap_row = (TAP && active) ? a.tap + row * a.stride : nullptr;
-  (void)wb_row;
+  __syncwarp();
+  uint8_t* out_row = active ? a.out + (long)row * a.out_stride : nullptr;
+  float* tap_row = (TAP && active) ? a.tap + (long)row * a.stride : nullptr;
+  const bool fast_sm = !d.ring_fractional && d.eod_count > 16 && !a.force_generic;
 
-  const double kTwoPi = 6.283185307179586;
   const long n_tiles = (a.n + kTile - 1) / kTile;
   for (int p = 0; p < kStages - 1; ++p) {
     if (p < n_tiles) stage_tile<ALIGNED>(tiles[p], a, rows, (long)p * kTile, lane);
@@ -582,6 +602,8 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
 
     // ---------------- A1: AGC + pre-filter ----------------
     if (active) {
+      A1State a1;
+      a1_load(a1, park_d, park_u, lane);
       const bool agc = d.agc_enabled != 0;
       const double att = d.agc_attack, rel = d.agc_release;
       if (len == kTile && !WRITEBACK && !TAP) {
@@ -589,10 +611,10 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
         for (int ch = 0; ch < 8; ++ch) {
           const float4 v = *reinterpret_cast<const float4*>(tile + tile_index(lane, ch * 4));
           float sg;
-          const float p0 = phase_a1_sample(s, v.x, d, agc, att, rel, sg);
-          const float p1 = phase_a1_sample(s, v.y, d, agc, att, rel, sg);
-          const float p2 = phase_a1_sample(s, v.z, d, agc, att, rel, sg);
-          const float p3 = phase_a1_sample(s, v.w, d, agc, att, rel, sg);
+          const float p0 = phase_a1_sample(a1, v.x, d, agc, att, rel, sg);
+          const float p1 = phase_a1_sample(a1, v.y, d, agc, att, rel, sg);
+          const float p2 = phase_a1_sample(a1, v.z, d, agc, att, rel, sg);
+          const float p3 = phase_a1_sample(a1, v.w, d, agc, att, rel, sg);
           float* pfp = pfbuf + (ch * 4) * 32 + lane;
           pfp[0] = p0; pfp[32] = p1; pfp[64] = p2; pfp[96] = p3;
         }
@@ -600,12 +622,13 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
 #pragma unroll 1
         for (int i = 0; i < len; ++i) {
           float sg;
-          const float pf = phase_a1_sample(s, tile[tile_index(lane, i)], d, agc, att, rel, sg);
+          const float pf = phase_a1_sample(a1, tile[tile_index(lane, i)], d, agc, att, rel, sg);
           pfbuf[i * 32 + lane] = pf;
-          if (WRITEBACK) a.samples[row * a.stride + t0 + i] = sg;  // fsk.ts:55 mutates the input
+          if (WRITEBACK) a.samples[(long)row * a.stride + t0 + i] = sg;  // fsk.ts:55 mutates the input
           if (TAP) tap_row[t0 + i] = pf;
         }
       }
+      a1_store(a1, park_d, park_u, lane);
     }
     __syncwarp();  // every lane is done with the input tile; its storage becomes pbuf
 
@@ -620,12 +643,16 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
     uint32_t bits = 0u;
     bool redo = active;
     // ring bookkeeping at the start of the tile (event-driven state machine)
-    const uint32_t pos_t0 = s.ring_pos, len_t0 = s.ring_len, slot_t0 = s.amp_pos, alen_t0 = s.amp_len;
-    const bool fast_sm = !d.ring_fractional && d.eod_count > 16 && !a.force_generic;
+    const uint32_t pos_t0 = park_u[10][lane], len_t0 = park_u[11][lane];
+    const uint32_t slot_t0 = park_u[12][lane], alen_t0 = park_u[13][lane];
+    if (active) {
+      // renormalise the LO rotation (one Newton step towards |(c, s)| = 1)
+      const double m = fma(s.lo_c, s.lo_c, s.lo_s * s.lo_s);
+      const double f = fma(-0.5, m, 1.5);
+      s.lo_c *= f; s.lo_s *= f;
+    }
     while (__any_sync(0xffffffffu, redo)) {
       if (redo) {
-        // re-anchor the LO rotation on the accumulated phase (start of tile / after a reset)
-        if (v_lo == dsc0 && t != 0) sincos(s.lo_phase, &s.lo_s, &s.lo_c);
         bits &= (1u << k_from) - 1u;
         if (dsc0 == 0 && (v_hi & 1) == 0) {
           // fast path: every pair is complete
@@ -635,9 +662,9 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
             const float* pfp = pfbuf + (2 * k) * 32 + lane;
             phase_a2_half(s, pfp[0], d, yi0, yq0);
             phase_a2_half(s, pfp[32], d, yi1, yq1);
-            const int bit = phase_a2_decim(s, yi0 + yi1, yq0 + yq1, d, atan_tab, pp);
+            const int bit = phase_a2_decim(s, yi0 + yi1, yq0 + yq1, d, pp);
             bits |= (uint32_t)bit << k;
-            pbuf[k * 32 + lane] = pp;
+            pbuf[k * 32 + lane] = 0.5 * fast_sqrt(pp);  // amplitude (fsk.ts:252)
           }
         } else {
 #pragma unroll 1
@@ -651,38 +678,31 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
             if (v1 < v_hi) {
               phase_a2_half(s, pfbuf[(v1 - dsc0) * 32 + lane], d, yi, yq);
               double pp;
-              const int bit = phase_a2_decim(s, s.iacc + yi, s.qacc + yq, d, atan_tab, pp);
+              const int bit = phase_a2_decim(s, s.iacc + yi, s.qacc + yq, d, pp);
               s.iacc = 0.0; s.qacc = 0.0;
               bits |= (uint32_t)bit << k;
-              pbuf[k * 32 + lane] = pp;
+              pbuf[k * 32 + lane] = 0.5 * fast_sqrt(pp);
             }
           }
         }
-        // LO phase bookkeeping: (phase + omega) % 2pi per sample in the reference (fsk.ts:232)
-        {
-          double ph = s.lo_phase + (double)(v_hi - v_lo) * d.omega;
-          ph -= kTwoPi * floor(ph / kTwoPi);
-          s.lo_phase = ph;
-        }
         s.dsc = (uint32_t)(v_hi & 1);
         // ---------------- B ----------------
-        // amplitude = sqrt(avgI^2 + avgQ^2) = sqrt(p) / 2 (fsk.ts:252), in place over p
-#pragma unroll 4
-        for (int k = b_from; k < nk; ++k) pbuf[k * 32 + lane] = 0.5 * fast_sqrt(pbuf[k * 32 + lane]);
+        BState b;
+        b_load(b, park_d, park_u, lane);
         redo = false;
         int k_reset = -1;
         if (fast_sm) {
-          k_reset = sm_tile_events(s, bits, pbuf + lane, b_from, nk, pos_t0, len_t0, slot_t0, alen_t0, a, li, out_row);
-          if (k_reset < 0) {
-            s.ring_len = min(len_t0 + (uint32_t)nk, (uint32_t)d.ring_cap_int);
-            uint32_t sl = slot_t0 + (uint32_t)nk;
-            s.amp_pos = sl >= (uint32_t)d.amp_phys ? sl - (uint32_t)d.amp_phys : sl;
-            s.amp_len = min(alen_t0 + (uint32_t)nk, (uint32_t)d.amp_cap);
+          k_reset = sm_tile_events(s, b, bits, pbuf + lane, b_from, nk, pos_t0, len_t0, slot_t0, alen_t0, a, li, out_row);
+          if (k_reset < 0 || 2 * (k_reset + 1) >= v_hi) {
+            b.ring_len = min(len_t0 + (uint32_t)nk, (uint32_t)d.ring_cap_int);
+            const uint32_t sl = slot_t0 + (uint32_t)nk;
+            b.amp_pos = sl >= (uint32_t)d.amp_phys ? sl - (uint32_t)d.amp_phys : sl;
+            b.amp_len = min(alen_t0 + (uint32_t)nk, (uint32_t)d.amp_cap);
           }
         } else {
 #pragma unroll 1
           for (int k = b_from; k < nk; ++k) {
-            if (process_downsampled_bit(s, (int)((bits >> k) & 1u), pbuf[k * 32 + lane], a, li, out_row)) {
+            if (sm_sample_generic(s, b, (int)((bits >> k) & 1u), pbuf[k * 32 + lane], a, li, out_row)) {
               k_reset = k;
               break;
             }
@@ -692,13 +712,8 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
           // resetState(): A2 restarts from the zeroed state at the next pair
           k_from = k_reset + 1; b_from = k_reset + 1; v_lo = 2 * (k_reset + 1);
           redo = (v_lo < v_hi);
-          if (fast_sm && !redo) {
-            s.ring_len = min(len_t0 + (uint32_t)nk, (uint32_t)d.ring_cap_int);
-            uint32_t sl = slot_t0 + (uint32_t)nk;
-            s.amp_pos = sl >= (uint32_t)d.amp_phys ? sl - (uint32_t)d.amp_phys : sl;
-            s.amp_len = min(alen_t0 + (uint32_t)nk, (uint32_t)d.amp_cap);
-          }
         }
+        b_store(b, park_d, park_u, lane);
       }
     }
     __syncwarp();
@@ -706,10 +721,29 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
   cp_async_wait<0>();
 
   if (active) {
-    if (!d.ring_fractional && (s.ring_pos & 31u) != 0u)
-      a.sync_ring[(long)((s.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * a.n_local + li] = s.cur_word;
-    lane_store(s, a, li);
-    a.out_len[row] = s.out_n < a.out_stride ? s.out_n : (int)a.out_stride;
+    double* f = a.f64 + li;
+    uint32_t* u = a.u32 + li;
+    f[F_LO_C * ns] = s.lo_c; f[F_LO_S * ns] = s.lo_s;
+    f[F_IX1 * ns] = s.ix1; f[F_IX2 * ns] = s.ix2; f[F_IY1 * ns] = s.iy1; f[F_IY2 * ns] = s.iy2;
+    f[F_QX1 * ns] = s.qx1; f[F_QX2 * ns] = s.qx2; f[F_QY1 * ns] = s.qy1; f[F_QY2 * ns] = s.qy2;
+    f[F_OX1 * ns] = s.ox1; f[F_OX2 * ns] = s.ox2; f[F_OY1 * ns] = s.oy1; f[F_OY2 * ns] = s.oy2;
+    f[F_LAST_PHASE * ns] = s.last_phase; f[F_IACC * ns] = s.iacc; f[F_QACC * ns] = s.qacc;
+    u[U_DSC * ns] = s.dsc;
+    A1State a1;
+    a1_load(a1, park_d, park_u, lane);
+    f[F_GAIN * ns] = a1.gain; f[F_PY1 * ns] = a1.py1; f[F_PY2 * ns] = a1.py2;
+    f[F_PX1 * ns] = (double)a1.px1; f[F_PX2 * ns] = (double)a1.px2;
+    BState b;
+    b_load(b, park_d, park_u, lane);
+    f[F_SIL_THR * ns] = b.sil_thr;
+    u[U_GSC * ns] = b.gsc; u[U_GMOD * ns] = b.gmod; u[U_BSC * ns] = b.bsc; u[U_NEXT_IDX * ns] = b.next_idx;
+    u[U_BIT_ACC * ns] = b.bit_acc; u[U_BIT_CNT * ns] = b.bit_cnt; u[U_STARTED * ns] = b.started;
+    u[U_BITPOS * ns] = (uint32_t)b.bitpos; u[U_CURRENT * ns] = b.current; u[U_SIL_CNT * ns] = b.sil_cnt;
+    u[U_RING_POS * ns] = b.ring_pos; u[U_RING_LEN * ns] = b.ring_len;
+    u[U_AMP_POS * ns] = b.amp_pos; u[U_AMP_LEN * ns] = b.amp_len;
+    if (!d.ring_fractional && (b.ring_pos & 31u) != 0u)
+      a.sync_ring[(long)((b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns + li] = b.cur_word;
+    a.out_len[row] = b.out_n < a.out_stride ? b.out_n : (int)a.out_stride;
   }
 }
 

@@ -298,13 +298,13 @@ struct wam_fsk_batch {
 };
 
 // atan(k / 64) table shared by every kernel launch on a device
-static int atan_table_device(int device, const double** out) {
-  static double* tabs[64] = {nullptr};
+static int atan_table_device(int device, const double2** out) {
+  static double2* tabs[64] = {nullptr};
   if (device < 0 || device >= 64) return fail(WAM_E_INVALID, "device index out of range");
   if (!tabs[device]) {
-    double h[kAtanTableSize];
-    for (int k = 0; k < kAtanTableSize; k++) h[k] = atan((double)k / 64.0);
-    double* dptr = nullptr;
+    double2 h[kAtanTableSize];
+    for (int k = 0; k < kAtanTableSize; k++) { h[k].x = (double)k / 64.0; h[k].y = atan((double)k / 64.0); }
+    double2* dptr = nullptr;
     CUDA_TRY(cudaMalloc(&dptr, sizeof(h)));
     CUDA_TRY(cudaMemcpy(dptr, h, sizeof(h), cudaMemcpyHostToDevice));
     tabs[device] = dptr;
@@ -357,6 +357,7 @@ static int init_group_state(Group& g, cudaStream_t st) {
   const unsigned blocks = (unsigned)((n + 255) / 256);
   fill_f64_kernel<<<blocks, 256, 0, st>>>(g.f64 + (size_t)F_GAIN * n, 1.0, (long)n);
   fill_f64_kernel<<<blocks, 256, 0, st>>>(g.f64 + (size_t)F_SIL_THR * n, 0.01, (long)n);
+  fill_f64_kernel<<<blocks, 256, 0, st>>>(g.f64 + (size_t)F_LO_C * n, 1.0, (long)n);  // cos(0)
   CUDA_TRY(cudaGetLastError());
   return WAM_OK;
 }
@@ -464,7 +465,7 @@ extern "C" int wam_fsk_batch_reset(wam_fsk_batch* b) {
   if (!b) return fail(WAM_E_INVALID, "batch is NULL");
   CUDA_TRY(cudaSetDevice(b->device));
   CUDA_TRY(cudaDeviceSynchronize());
-  static const int f_zero[] = {F_LO_PHASE, F_IX1, F_IX2, F_IY1, F_IY2, F_QX1, F_QX2, F_QY1, F_QY2, F_OX1, F_OX2,
+  static const int f_zero[] = {F_LO_S, F_IX1, F_IX2, F_IY1, F_IY2, F_QX1, F_QX2, F_QY1, F_QY2, F_OX1, F_OX2,
                                F_OY1, F_OY2, F_LAST_PHASE, F_IACC, F_QACC, F_RING_WI, F_RING_RI, F_RING_LEN};
   static const int u_zero[] = {U_DSC, U_GSC, U_GMOD, U_BSC, U_NEXT_IDX, U_BIT_ACC, U_BIT_CNT, U_STARTED, U_BITPOS,
                                U_CURRENT, U_SIL_CNT, U_RING_POS, U_RING_LEN, U_SYNC_DET};
@@ -473,6 +474,8 @@ extern "C" int wam_fsk_batch_reset(wam_fsk_batch* b) {
     if (n == 0) continue;
     for (int f : f_zero) CUDA_TRY(cudaMemset(g.f64 + (size_t)f * n, 0, sizeof(double) * n));
     for (int u : u_zero) CUDA_TRY(cudaMemset(g.u32 + (size_t)u * n, 0, sizeof(uint32_t) * n));
+    fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256>>>(g.f64 + (size_t)F_LO_C * n, 1.0, (long)n);
+    CUDA_TRY(cudaGetLastError());
   }
   b->demodulation_calls = 0;
   b->total_samples = 0;
@@ -1077,7 +1080,7 @@ extern "C" int wam_debug_fastmath(int device, const double* y, const double* x, 
   int rc = select_device(device);
   if (rc != WAM_OK) return rc;
   if (n == 0) return WAM_OK;
-  const double* tab = nullptr;
+  const double2* tab = nullptr;
   if ((rc = atan_table_device(device, &tab)) != WAM_OK) return rc;
   DevBuf dy, dx, d1, d2, d3;
   const size_t nb = sizeof(double) * (size_t)n;

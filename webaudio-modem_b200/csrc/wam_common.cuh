@@ -52,7 +52,7 @@ struct FskDerived {
   const uint32_t* tmpl_mask;
   int tmpl_words;
   int max_mismatch;     // care_bits - min_matched (negative: can never sync)
-  const double* atan_tab;  // device: atan(k / 64), k = 0..64
+  const double2* atan_tab;  // device: {k / 64, atan(k / 64)}, k = 0..64
   // modulator (fsk.ts:389-424)
   double mark, space, fs;
   int n_preamble, n_sfd;
@@ -61,7 +61,7 @@ struct FskDerived {
 
 // Per-stream streaming state, struct-of-arrays: f64[k * n + stream], u32[k * n + stream].
 enum F64Field {
-  F_GAIN = 0, F_PX1, F_PX2, F_PY1, F_PY2, F_LO_PHASE,
+  F_GAIN = 0, F_PX1, F_PX2, F_PY1, F_PY2, F_LO_C, F_LO_S,
   F_IX1, F_IX2, F_IY1, F_IY2, F_QX1, F_QX2, F_QY1, F_QY2,
   F_OX1, F_OX2, F_OY1, F_OY2, F_LAST_PHASE, F_IACC, F_QACC, F_SIL_THR,
   F_RING_WI, F_RING_RI, F_RING_LEN,
