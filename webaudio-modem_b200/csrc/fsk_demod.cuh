@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
     b.bitpos = (int)u[U_BITPOS * ns]; b.current = u[U_CURRENT * ns]; b.sil_cnt = u[U_SIL_CNT * ns];
     b.ring_pos = u[U_RING_POS * ns]; b.ring_len = u[U_RING_LEN * ns];
     b.amp_pos = u[U_AMP_POS * ns]; b.amp_len = u[U_AMP_LEN * ns];
-    b.out_n = 0;
+    b.out_n = a.append ? a.out_len[row] : 0;
     b.cur_word = 0u;
     if (!d.ring_fractional && (b.ring_pos & 31u) != 0u) {
       const uint32_t w = a.sync_ring[(long)((b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns + li];

@@ -282,6 +282,7 @@ struct wam_fsk_batch {
   long launches = 0;
   // staging for the HOST-buffer entry points
   cudaStream_t streams[2] = {nullptr, nullptr};
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   float* stage_samples[2] = {nullptr, nullptr};
   uint8_t* stage_out[2] = {nullptr, nullptr};
   int32_t* stage_len[2] = {nullptr, nullptr};
@@ -370,6 +371,8 @@ static void free_batch(wam_fsk_batch* b) {
   }
   for (int i = 0; i < 2; i++) {
     if (b->streams[i]) cudaStreamDestroy(b->streams[i]);
+    if (b->ev_copied[i]) cudaEventDestroy(b->ev_copied[i]);
+    if (b->ev_consumed[i]) cudaEventDestroy(b->ev_consumed[i]);
     cudaFree(b->stage_samples[i]); cudaFree(b->stage_out[i]); cudaFree(b->stage_len[i]);
   }
   cudaFree(b->mod_prefix); cudaFree(b->mod_data); cudaFree(b->mod_out); cudaFree(b->mod_len);
@@ -504,7 +507,7 @@ static void launch_demod(const DemodLaunch& L, cudaStream_t st) {
 // kMaxGroupsPerLaunch per launch) so their one-warp CTAs share the SMs.
 static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base, float* d_samples, long stride, long n,
                               uint8_t* d_out, long out_stride, int32_t* d_out_len, float* d_tap, uint32_t flags,
-                              cudaStream_t st) {
+                              cudaStream_t st, bool append = false) {
   const bool aligned = ((reinterpret_cast<uintptr_t>(d_samples) & 15) == 0) && (stride % 4 == 0);
   const bool wb = (flags & WAM_BATCH_WRITEBACK_AGC) != 0;
   const bool tap = (flags & WAM_BATCH_TAP_PREFILTER) != 0 && d_tap != nullptr;
@@ -544,6 +547,7 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
     a.samples = d_samples; a.stride = stride; a.n = n;
     a.out = d_out; a.out_stride = out_stride; a.out_len = d_out_len; a.tap = d_tap;
     a.force_generic = (flags & WAM_BATCH_DEBUG_GENERIC_SM) ? 1 : 0;
+    a.append = append ? 1 : 0;
     L.block_begin[L.n_groups + 1] = L.block_begin[L.n_groups] + (int)((hi - lo + 31) / 32);
     L.n_groups++;
     if (L.n_groups == kMaxGroupsPerLaunch) {
@@ -590,52 +594,74 @@ extern "C" int wam_fsk_batch_demodulate(wam_fsk_batch* b, float* samples, long s
   b->total_samples += (double)n_samples;
   flags &= (WAM_BATCH_WRITEBACK_AGC | WAM_BATCH_DEBUG_GENERIC_SM);
 
-  // Streams are processed in chunks so that the H2D copy of chunk k+1 overlaps the kernel of
-  // chunk k (two CUDA streams, two staging buffers).  Device rows are packed (stride = n padded to 4).
-  const long dstride = (n_samples + 3) / 4 * 4;
-  const size_t row_bytes = sizeof(float) * (size_t)std::max<long>(dstride, 4);
-  long chunk = (long)((size_t)256 << 20) / (long)row_bytes;  // ~256 MiB of samples per chunk
-  chunk = std::max<long>(32, chunk / 32 * 32);
-  chunk = std::min<long>(chunk, (b->n_streams + 31) / 32 * 32);
-  const size_t need_s = row_bytes * (size_t)chunk;
-  const size_t need_o = (size_t)std::max<long>(out_stride, 1) * (size_t)chunk;
-  const size_t need_l = sizeof(int32_t) * (size_t)chunk;
-  for (int i = 0; i < 2; i++) {
+  // The call is cut into TIME slabs (all streams, samples [t0, t1)): the H2D copy of slab k+1 overlaps
+  // the kernel of slab k (copy stream + compute stream, two staging buffers), and every slab launch
+  // keeps all of the batch's warps busy.  The per-stream state carries from slab to slab exactly as
+  // it does between demodulateData() calls; decoded bytes are appended in device memory and read
+  // back once.
+  long slab = n_samples;
+  {
+    const long target = (long)(((size_t)768 << 20) / (sizeof(float) * (size_t)b->n_streams));
+    if (target < n_samples) slab = std::max<long>(2048, target / 32 * 32);
+    slab = std::min(slab, n_samples);
+  }
+  const long dstride = (std::max<long>(slab, 1) + 3) / 4 * 4;
+  const size_t need_s = sizeof(float) * (size_t)dstride * (size_t)b->n_streams;
+  const size_t need_o = (size_t)std::max<long>(out_stride, 1) * (size_t)b->n_streams;
+  const size_t need_l = sizeof(int32_t) * (size_t)b->n_streams;
+  {
     size_t cs = b->stage_samples_bytes, co = b->stage_out_bytes, cl = b->stage_len_bytes;
-    int rc = ensure((void**)&b->stage_samples[i], &cs, need_s);
-    if (rc == WAM_OK) rc = ensure((void**)&b->stage_out[i], &co, need_o);
-    if (rc == WAM_OK) rc = ensure((void**)&b->stage_len[i], &cl, need_l);
-    if (rc != WAM_OK) {
-      b->stage_samples_bytes = b->stage_out_bytes = b->stage_len_bytes = 0;
-      return rc;
+    for (int i = 0; i < 2; i++) {
+      cs = b->stage_samples_bytes;
+      int rc = ensure((void**)&b->stage_samples[i], &cs, need_s);
+      if (rc != WAM_OK) { b->stage_samples_bytes = 0; return rc; }
     }
-    if (i == 1) { b->stage_samples_bytes = cs; b->stage_out_bytes = co; b->stage_len_bytes = cl; }
+    b->stage_samples_bytes = cs;
+    int rc = ensure((void**)&b->stage_out[0], &co, need_o);
+    if (rc == WAM_OK) rc = ensure((void**)&b->stage_len[0], &cl, need_l);
+    if (rc != WAM_OK) { b->stage_out_bytes = b->stage_len_bytes = 0; return rc; }
+    b->stage_out_bytes = co; b->stage_len_bytes = cl;
   }
-
+  cudaStream_t copy_st = b->streams[0], comp_st = b->streams[1];
+  if (!b->ev_copied[0]) {
+    for (int i = 0; i < 2; i++) {
+      CUDA_TRY(cudaEventCreateWithFlags(&b->ev_copied[i], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&b->ev_consumed[i], cudaEventDisableTiming));
+    }
+  }
+  CUDA_TRY(cudaMemsetAsync(b->stage_len[0], 0, need_l, comp_st));
+  const bool wb = (flags & WAM_BATCH_WRITEBACK_AGC) != 0;
   int k = 0;
-  for (long s0 = 0; s0 < b->n_streams; s0 += chunk, k ^= 1) {
-    const long s1 = std::min(b->n_streams, s0 + chunk);
-    const long rows = s1 - s0;
-    cudaStream_t st = b->streams[k];
-    if (n_samples > 0)
-      CUDA_TRY(cudaMemcpy2DAsync(b->stage_samples[k], sizeof(float) * (size_t)dstride, samples + s0 * stream_stride,
-                                 sizeof(float) * (size_t)stream_stride, sizeof(float) * (size_t)n_samples, (size_t)rows,
-                                 cudaMemcpyHostToDevice, st));
-    int rc = launch_demod_range(b, s0, s1, s0, b->stage_samples[k], dstride, n_samples, b->stage_out[k], out_stride,
-                                b->stage_len[k], nullptr, flags, st);
+  long nslab = 0;
+  for (long t0 = 0; t0 < n_samples || (n_samples == 0 && nslab == 0); t0 += slab, k ^= 1, nslab++) {
+    const long len = std::min(slab, n_samples - t0);
+    if (nslab >= 2) CUDA_TRY(cudaStreamWaitEvent(copy_st, b->ev_consumed[k], 0));  // staging buffer k is free again
+    if (len > 0) {
+      if (stream_stride == dstride && len == dstride)
+        CUDA_TRY(cudaMemcpyAsync(b->stage_samples[k], samples, sizeof(float) * (size_t)dstride * (size_t)b->n_streams,
+                                 cudaMemcpyHostToDevice, copy_st));
+      else
+        CUDA_TRY(cudaMemcpy2DAsync(b->stage_samples[k], sizeof(float) * (size_t)dstride, samples + t0,
+                                   sizeof(float) * (size_t)stream_stride, sizeof(float) * (size_t)len,
+                                   (size_t)b->n_streams, cudaMemcpyHostToDevice, copy_st));
+    }
+    CUDA_TRY(cudaEventRecord(b->ev_copied[k], copy_st));
+    CUDA_TRY(cudaStreamWaitEvent(comp_st, b->ev_copied[k], 0));
+    int rc = launch_demod_range(b, 0, b->n_streams, 0, b->stage_samples[k], dstride, len, b->stage_out[0], out_stride,
+                                b->stage_len[0], nullptr, flags, comp_st, /*append=*/true);
     if (rc != WAM_OK) return rc;
-    if (out_stride > 0)
-      CUDA_TRY(cudaMemcpyAsync(out + s0 * out_stride, b->stage_out[k], (size_t)out_stride * (size_t)rows,
-                               cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(out_len + s0, b->stage_len[k], sizeof(int32_t) * (size_t)rows, cudaMemcpyDeviceToHost, st));
-    if ((flags & WAM_BATCH_WRITEBACK_AGC) && n_samples > 0)
-      CUDA_TRY(cudaMemcpy2DAsync(samples + s0 * stream_stride, sizeof(float) * (size_t)stream_stride, b->stage_samples[k],
-                                 sizeof(float) * (size_t)dstride, sizeof(float) * (size_t)n_samples, (size_t)rows,
-                                 cudaMemcpyDeviceToHost, st));
+    if (wb && len > 0)
+      CUDA_TRY(cudaMemcpy2DAsync(samples + t0, sizeof(float) * (size_t)stream_stride, b->stage_samples[k],
+                                 sizeof(float) * (size_t)dstride, sizeof(float) * (size_t)len, (size_t)b->n_streams,
+                                 cudaMemcpyDeviceToHost, comp_st));
+    CUDA_TRY(cudaEventRecord(b->ev_consumed[k], comp_st));
+    if (n_samples == 0) break;
   }
-  CUDA_TRY(cudaStreamSynchronize(b->streams[0]));
-  CUDA_TRY(cudaStreamSynchronize(b->streams[1]));
-  // per-stream overflow flags would have clamped out_len; report it
+  if (out_stride > 0)
+    CUDA_TRY(cudaMemcpyAsync(out, b->stage_out[0], (size_t)out_stride * (size_t)b->n_streams, cudaMemcpyDeviceToHost, comp_st));
+  CUDA_TRY(cudaMemcpyAsync(out_len, b->stage_len[0], need_l, cudaMemcpyDeviceToHost, comp_st));
+  CUDA_TRY(cudaStreamSynchronize(copy_st));
+  CUDA_TRY(cudaStreamSynchronize(comp_st));
   return WAM_OK;
 }
 

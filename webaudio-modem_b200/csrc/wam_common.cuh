@@ -95,6 +95,7 @@ struct DemodArgs {
   int32_t* out_len;     // [rows]
   float* tap;           // optional [rows][stride]
   int force_generic;    // debug: per-sample state machine even where the event-driven one applies
+  int append;           // out_len[row] holds the bytes already written for this stream: append after them
 };
 
 // All configuration groups of a batch run in ONE launch (one-warp CTAs; blockIdx selects the group)
