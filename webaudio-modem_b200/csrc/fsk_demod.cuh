@@ -426,8 +426,8 @@ __device__ __forceinline__ float phase_a1_sample(A1State& s, float x, const FskD
   agc_out = sg;
   // pre-filter: butterworthBandpass has b1 == 0 and b2 == -b0 exactly (filters.ts:230)
   double y = d.pre_b0 * ((double)sg - (double)s.px2);
-  y = fma(-d.pre_a1, s.py1, y);
   y = fma(-d.pre_a2, s.py2, y);
+  y = fma(-d.pre_a1, s.py1, y);
   s.px2 = s.px1; s.px1 = sg; s.py2 = s.py1; s.py1 = y;
   return (float)y;  // Float32Array store of processBuffer (filters.ts:82-85)
 }
@@ -446,14 +446,14 @@ __device__ __forceinline__ void phase_a2_half(A2State& s, float pf, const FskDer
   double ui = xi + s.ix2;
   ui = fma(2.0, s.ix1, ui);
   yi = d.lp_b0 * ui;
-  yi = fma(-d.lp_a1, s.iy1, yi);
   yi = fma(-d.lp_a2, s.iy2, yi);
+  yi = fma(-d.lp_a1, s.iy1, yi);  // the newest output enters last: one DFMA on the recurrence chain
   s.ix2 = s.ix1; s.ix1 = xi; s.iy2 = s.iy1; s.iy1 = yi;
   double uq = xq + s.qx2;
   uq = fma(2.0, s.qx1, uq);
   yq = d.lp_b0 * uq;
-  yq = fma(-d.lp_a1, s.qy1, yq);
   yq = fma(-d.lp_a2, s.qy2, yq);
+  yq = fma(-d.lp_a1, s.qy1, yq);
   s.qx2 = s.qx1; s.qx1 = xq; s.qy2 = s.qy1; s.qy1 = yq;
 }
 
@@ -471,8 +471,8 @@ __device__ __forceinline__ int phase_a2_decim(A2State& s, double si, double sq, 
   double uo = pd + s.ox2;
   uo = fma(2.0, s.ox1, uo);
   double yo = d.lp_b0 * uo;
-  yo = fma(-d.lp_a1, s.oy1, yo);
   yo = fma(-d.lp_a2, s.oy2, yo);
+  yo = fma(-d.lp_a1, s.oy1, yo);
   s.ox2 = s.ox1; s.ox1 = pd; s.oy2 = s.oy1; s.oy1 = yo;
   return yo > 0.0 ? 1 : 0;
 }
@@ -655,8 +655,9 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
       if (redo) {
         bits &= (1u << k_from) - 1u;
         if (dsc0 == 0 && (v_hi & 1) == 0) {
-          // fast path: every pair is complete
-#pragma unroll 1
+          // fast path: every pair is complete (two pairs per iteration: the biquad histories rotate in
+          // place and two atan2 chains overlap)
+#pragma unroll 2
           for (int k = k_from; k < nk; ++k) {
             double yi0, yq0, yi1, yq1, pp;
             const float* pfp = pfbuf + (2 * k) * 32 + lane;
