@@ -146,6 +146,8 @@ int wam_fsk_batch_demodulate_device(wam_fsk_batch* b, float* d_samples, long str
                                     void* cuda_stream, uint32_t flags);
 /* per-stream getStatus(); st: host array [n_streams] */
 int wam_fsk_batch_status(wam_fsk_batch* b, wam_fsk_status* st);
+/* profiling aid: per-phase SM cycle counters of the demodulator (A1, A2, B, other), summed over CTAs */
+int wam_fsk_batch_debug_phase_cycles(wam_fsk_batch* b, int enable, double* out4, double* per_cta, long n_ctas);
 /* kernels launched by this handle so far (bench.py's gpu_launches) */
 long wam_fsk_batch_launch_count(wam_fsk_batch* b);
 

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwam.so")
+LIB_PATH = os.environ.get("WAM_LIB") or os.path.join(HERE, "libwam.so")  # WAM_LIB: A/B experiments only
 
 WAM_OK = 0
 WAM_E_INVALID = -1
@@ -91,6 +91,7 @@ SYMBOLS = {
     "wam_fsk_batch_demodulate_device": (C.c_int, [_vp, _vp, C.c_long, C.c_long, _vp, C.c_long, _vp, _vp, _vp, C.c_uint32]),
     "wam_fsk_batch_status": (C.c_int, [_vp, _stp]),
     "wam_fsk_batch_launch_count": (C.c_long, [_vp]),
+    "wam_fsk_batch_debug_phase_cycles": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_long]),
     "wam_fsk_batch_modulate": (C.c_int, [_vp, _vp, C.c_long, _vp, C.c_long, _vp, C.c_long, _vp]),
     "wam_fsk_batch_modulate_device": (C.c_int, [_vp, _vp, C.c_long, _vp, C.c_long, _vp, C.c_long, _vp, _vp]),
     "wam_crc16": (C.c_uint16, [_u8p, C.c_long]),

@@ -23,6 +23,8 @@ def _sources():
 
 
 def needs_build() -> bool:
+    if os.environ.get("WAM_LIB"):
+        return False
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)

@@ -584,6 +584,13 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
   float* tap_row = (TAP && active) ? a.tap + (long)row * a.stride : nullptr;
   const bool fast_sm = !d.ring_fractional && d.eod_count > 16 && !a.force_generic;
 
+  unsigned long long cyc_a1 = 0, cyc_a2 = 0, cyc_b = 0;
+#ifdef WAM_PHASE_TIMING
+  const bool timing = a.phase_cycles != nullptr;
+#else
+  constexpr bool timing = false;  // build with -DWAM_PHASE_TIMING for per-phase SM cycle counters
+#endif
+  const long long clk_begin = timing ? clock64() : 0;
   const long n_tiles = (a.n + kTile - 1) / kTile;
   for (int p = 0; p < kStages - 1; ++p) {
     if (p < n_tiles) stage_tile<ALIGNED>(tiles[p], a, rows, (long)p * kTile, lane);
@@ -601,6 +608,7 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
     const int len = (int)min((long)kTile, a.n - t0);
 
     // ---------------- A1: AGC + pre-filter ----------------
+    long long clk0 = timing ? clock64() : 0;
     if (active) {
       A1State a1;
       a1_load(a1, park_d, park_u, lane);
@@ -631,6 +639,7 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
       a1_store(a1, park_d, park_u, lane);
     }
     __syncwarp();  // every lane is done with the input tile; its storage becomes pbuf
+    if (timing) { const long long c = clock64(); cyc_a1 += (unsigned long long)(c - clk0); clk0 = c; }
 
     // ---------------- A2 + B with replay on resetState() ----------------
     // virtual sample index v = i + dsc0; pair k = v >> 1; a pair's second half emits decimated k.
@@ -687,6 +696,7 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
           }
         }
         s.dsc = (uint32_t)(v_hi & 1);
+        if (timing) { const long long c = clock64(); cyc_a2 += (unsigned long long)(c - clk0); clk0 = c; }
         // ---------------- B ----------------
         BState b;
         b_load(b, park_d, park_u, lane);
@@ -715,11 +725,17 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
           redo = (v_lo < v_hi);
         }
         b_store(b, park_d, park_u, lane);
+        if (timing) { const long long c = clock64(); cyc_b += (unsigned long long)(c - clk0); clk0 = c; }
       }
     }
     __syncwarp();
   }
   cp_async_wait<0>();
+  if (timing && lane == 0) {
+    unsigned long long* pc = a.phase_cycles + 4ull * blockIdx.x;
+    pc[0] += cyc_a1; pc[1] += cyc_a2; pc[2] += cyc_b;
+    pc[3] += (unsigned long long)(clock64() - clk_begin) - cyc_a1 - cyc_a2 - cyc_b;
+  }
 
   if (active) {
     double* f = a.f64 + li;

@@ -287,6 +287,8 @@ struct wam_fsk_batch {
   uint8_t* stage_out[2] = {nullptr, nullptr};
   int32_t* stage_len[2] = {nullptr, nullptr};
   size_t stage_samples_bytes = 0, stage_out_bytes = 0, stage_len_bytes = 0;
+  unsigned long long* phase_cycles = nullptr;  // debug: [max CTAs][4]
+  long phase_ctas = 0;
   // modulator scratch
   uint32_t* mod_prefix = nullptr;
   size_t mod_prefix_bytes = 0;
@@ -375,6 +377,7 @@ static void free_batch(wam_fsk_batch* b) {
     if (b->ev_consumed[i]) cudaEventDestroy(b->ev_consumed[i]);
     cudaFree(b->stage_samples[i]); cudaFree(b->stage_out[i]); cudaFree(b->stage_len[i]);
   }
+  cudaFree(b->phase_cycles);
   cudaFree(b->mod_prefix); cudaFree(b->mod_data); cudaFree(b->mod_out); cudaFree(b->mod_len);
   delete b;
 }
@@ -548,6 +551,7 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
     a.out = d_out; a.out_stride = out_stride; a.out_len = d_out_len; a.tap = d_tap;
     a.force_generic = (flags & WAM_BATCH_DEBUG_GENERIC_SM) ? 1 : 0;
     a.append = append ? 1 : 0;
+    a.phase_cycles = b->phase_cycles;
     L.block_begin[L.n_groups + 1] = L.block_begin[L.n_groups] + (int)((hi - lo + 31) / 32);
     L.n_groups++;
     if (L.n_groups == kMaxGroupsPerLaunch) {
@@ -696,6 +700,34 @@ extern "C" int wam_fsk_batch_status(wam_fsk_batch* b, wam_fsk_status* st) {
 }
 
 extern "C" long wam_fsk_batch_launch_count(wam_fsk_batch* b) { return b ? b->launches : 0; }
+
+// Debug: enable (enable != 0) / read-and-clear per-phase SM cycle counters of the demodulator kernel.
+// out4 (nullable) receives the sums over CTAs of cycles spent in A1, A2, B and staging/other;
+// per_cta (nullable, [n_ctas][4]) the individual counters (CTA order = launch order).
+extern "C" int wam_fsk_batch_debug_phase_cycles(wam_fsk_batch* b, int enable, double* out4, double* per_cta,
+                                                long n_ctas) {
+  if (!b) return fail(WAM_E_INVALID, "batch is NULL");
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const long ctas = (b->n_streams + 31) / 32 + (long)b->groups.size();
+  if (out4) {
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    if (b->phase_cycles) {
+      std::vector<unsigned long long> h((size_t)b->phase_ctas * 4);
+      CUDA_TRY(cudaMemcpy(h.data(), b->phase_cycles, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < h.size(); i++) out4[i & 3] += (double)h[i];
+      if (per_cta)
+        for (size_t i = 0; i < h.size() && i < (size_t)n_ctas * 4; i++) per_cta[i] = (double)h[i];
+    }
+  }
+  if (enable && !b->phase_cycles) {
+    CUDA_TRY(cudaMalloc(&b->phase_cycles, sizeof(unsigned long long) * (size_t)ctas * 4));
+    b->phase_ctas = ctas;
+  }
+  if (!enable && b->phase_cycles) { cudaFree(b->phase_cycles); b->phase_cycles = nullptr; b->phase_ctas = 0; }
+  if (b->phase_cycles) CUDA_TRY(cudaMemset(b->phase_cycles, 0, sizeof(unsigned long long) * (size_t)b->phase_ctas * 4));
+  return WAM_OK;
+}
 
 // ------------------------------------------------------------------------------------------
 // batched modulator

@@ -96,6 +96,7 @@ struct DemodArgs {
   float* tap;           // optional [rows][stride]
   int force_generic;    // debug: per-sample state machine even where the event-driven one applies
   int append;           // out_len[row] holds the bytes already written for this stream: append after them
+  unsigned long long* phase_cycles;  // debug (nullable): [CTA][4] SM cycles spent in A1, A2, B, staging/other
 };
 
 // All configuration groups of a batch run in ONE launch (one-warp CTAs; blockIdx selects the group)
