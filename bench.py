@@ -50,6 +50,22 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the demod kernel (one launch of this workload) from
+    the committed `ncu --set full` summary, or None."""
+    p = os.path.join(ROOT, "profiles", "r01_demod_ncu_full_summary.json")
+    try:
+        rec = json.load(open(p))[0]
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            v, u = rec[k]
+            tot += float(v.replace(",", "")) * scale[u]
+        return tot
+    except Exception:
+        return None
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -365,10 +381,13 @@ def run_gpu(args):
         "decoded_bits_per_s": decoded_bytes * 8 * world / (ms_total_max * 1e-3 / args.steps),
         "frame_ok_frac_snr_ge_6dB": frac_ok_hi,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "fsk_demod_exact_kernel",
+                     "traffic": (ncu_traffic_bytes() if S == 65536 else None), "traffic_unit": "bytes per launch",
+                     "peak_source": peak_src, "kernel": "fsk_demod_exact_kernel",
                      "launches_per_step": launches / args.steps,
-                     "note": "algorithmic 4 B/input sample x samples per step / CUDA-event time of the step's "
-                             "demod launches (one per V.21 channel, concurrent)"},
+                     "achieved_per_launch_bytes": S * N_SAMPLES * BYTES_PER_SAMPLE, "kernel_ms": k_ms,
+                     "note": "algorithmic 4 B/input sample x samples per launch / CUDA-event time of the launch "
+                             "(both V.21 channels in one launch); the kernel is instruction-issue/latency bound, "
+                             "see profiles/r01_notes.md for issue-slot utilisation"},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
