@@ -223,6 +223,7 @@ __device__ __noinline__ double amp_ring_threshold(const float* __restrict__ arin
 // One decimated sample of FSKCore.processDownsampledBit (fsk.ts:278-344) AFTER the ring puts:
 // silence/EOD, sync search or vote/bit decision.  ring_pos / amp_next describe the rings including
 // this sample.  Returns true when resetState() ran.
+template <bool GENERIC>
 __device__ __forceinline__ bool sm_step(A2State& s, BState& b, int bit, double amplitude, uint32_t ring_pos,
                                         bool ring_ready, uint32_t amp_next, uint32_t amp_len, const DemodArgs& a,
                                         int li, uint8_t* out_row, bool& thr_changed) {
@@ -247,7 +248,7 @@ __device__ __forceinline__ bool sm_step(A2State& s, BState& b, int bit, double a
     if (due && ring_ready && d.total_bits > 0) {
       uint32_t* ring = a.sync_ring + li;
       int matched;
-      if (!d.ring_fractional) {
+      if (!GENERIC || !d.ring_fractional) {
         if ((b.ring_pos & 31u) != 0u)  // flush the register copy of the newest (partial) word
           ring[(long)((b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns] = b.cur_word;
         matched = (d.total_bits - d.dspb) - sync_mismatches(ring, ns, ring_pos, d);
@@ -306,7 +307,7 @@ __device__ __forceinline__ bool sm_sample_generic(A2State& s, BState& b, int bit
   b.amp_pos = (b.amp_pos + 1u == (uint32_t)d.amp_phys) ? 0u : b.amp_pos + 1u;
   b.amp_len = min(b.amp_len + 1u, (uint32_t)d.amp_cap);
   bool thr_changed = false;
-  return sm_step(s, b, bit, amplitude, b.ring_pos, ready, b.amp_pos, b.amp_len, a, li, out_row, thr_changed);
+  return sm_step<true>(s, b, bit, amplitude, b.ring_pos, ready, b.amp_pos, b.amp_len, a, li, out_row, thr_changed);
 }
 
 // Event-driven state machine for one tile (integral ring, eod_count > 16).  `bits` holds the hard
@@ -386,7 +387,7 @@ __device__ __forceinline__ int sm_tile_events(A2State& s, BState& b, uint32_t bi
     if (slot_next >= (uint32_t)d.amp_phys) slot_next -= (uint32_t)d.amp_phys;
     const uint32_t alen = min(alen_t0 + (uint32_t)k_evt + 1u, (uint32_t)d.amp_cap);
     bool thr_changed = false;
-    if (sm_step(s, b, (int)((bits >> k_evt) & 1u), amp[k_evt * 32], pos_k, ready, slot_next, alen, a, li, out_row,
+    if (sm_step<false>(s, b, (int)((bits >> k_evt) & 1u), amp[k_evt * 32], pos_k, ready, slot_next, alen, a, li, out_row,
                 thr_changed))
       return k_evt;
     if (thr_changed) {
@@ -522,7 +523,10 @@ __device__ __forceinline__ void stage_tile(float* tile, const DemodArgs& a, cons
 }
 
 // Grid: one warp (32 streams) per CTA, so that 2048 warps spread evenly over 148 SMs.
-template <bool ALIGNED, bool WRITEBACK, bool TAP>
+// GENERIC = false: the common case (no AGC write-back, no tap, integral sync ring, eod_count > 16) —
+// only the event-driven state machine is compiled in, which keeps the kernel's code footprint small.
+// GENERIC = true: write-back / tap by run-time flag and the per-sample state machine as fallback.
+template <bool ALIGNED, bool GENERIC>
 __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kernel(const __grid_constant__ DemodLaunch L) {
   int gi = 0;
 #pragma unroll
@@ -581,8 +585,10 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
   }
   __syncwarp();
   uint8_t* out_row = active ? a.out + (long)row * a.out_stride : nullptr;
+  const bool WRITEBACK = GENERIC && a.writeback != 0;
+  const bool TAP = GENERIC && a.tap != nullptr;
   float* tap_row = (TAP && active) ? a.tap + (long)row * a.stride : nullptr;
-  const bool fast_sm = !d.ring_fractional && d.eod_count > 16 && !a.force_generic;
+  const bool fast_sm = !GENERIC || (!d.ring_fractional && d.eod_count > 16 && !a.force_generic);
 
   unsigned long long cyc_a1 = 0, cyc_a2 = 0, cyc_b = 0;
 #ifdef WAM_PHASE_TIMING
@@ -710,7 +716,7 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
             b.amp_pos = sl >= (uint32_t)d.amp_phys ? sl - (uint32_t)d.amp_phys : sl;
             b.amp_len = min(alen_t0 + (uint32_t)nk, (uint32_t)d.amp_cap);
           }
-        } else {
+        } else if (GENERIC) {
 #pragma unroll 1
           for (int k = b_from; k < nk; ++k) {
             if (sm_sample_generic(s, b, (int)((bits >> k) & 1u), pbuf[k * 32 + lane], a, li, out_row)) {

@@ -500,9 +500,9 @@ extern "C" long wam_fsk_batch_out_capacity(wam_fsk_batch* b, long n_samples) {
   return (cap + 15) / 16 * 16;
 }
 
-template <bool A, bool W, bool T>
+template <bool A, bool G>
 static void launch_demod(const DemodLaunch& L, cudaStream_t st) {
-  fsk_demod_exact_kernel<A, W, T><<<L.block_begin[L.n_groups], 32, 0, st>>>(L);
+  fsk_demod_exact_kernel<A, G><<<L.block_begin[L.n_groups], 32, 0, st>>>(L);
 }
 
 // launch the demodulator for all streams of `b` whose global id lies in [s0, s1); row 0 of the
@@ -516,22 +516,15 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
   const bool tap = (flags & WAM_BATCH_TAP_PREFILTER) != 0 && d_tap != nullptr;
   DemodLaunch L;
   memset(&L, 0, sizeof(L));
+  bool generic = wb || tap || (flags & WAM_BATCH_DEBUG_GENERIC_SM);
   auto flush = [&]() -> int {
     if (L.n_groups == 0) return WAM_OK;
-    const int sel = (aligned ? 4 : 0) | (wb ? 2 : 0) | (tap ? 1 : 0);
-    switch (sel) {
-      case 0: launch_demod<false, false, false>(L, st); break;
-      case 1: launch_demod<false, false, true>(L, st); break;
-      case 2: launch_demod<false, true, false>(L, st); break;
-      case 3: launch_demod<false, true, true>(L, st); break;
-      case 4: launch_demod<true, false, false>(L, st); break;
-      case 5: launch_demod<true, false, true>(L, st); break;
-      case 6: launch_demod<true, true, false>(L, st); break;
-      default: launch_demod<true, true, true>(L, st); break;
-    }
+    if (aligned) { if (generic) launch_demod<true, true>(L, st); else launch_demod<true, false>(L, st); }
+    else         { if (generic) launch_demod<false, true>(L, st); else launch_demod<false, false>(L, st); }
     b->launches++;
     CUDA_TRY(cudaGetLastError());
     memset(&L, 0, sizeof(L));
+    generic = wb || tap || (flags & WAM_BATCH_DEBUG_GENERIC_SM);
     return WAM_OK;
   };
   for (auto& g : b->groups) {
@@ -548,7 +541,9 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
     a.row_base = (int)row_base;
     a.f64 = g.f64; a.u32 = g.u32; a.sync_ring = g.sync_ring; a.amp_ring = g.amp_ring;
     a.samples = d_samples; a.stride = stride; a.n = n;
-    a.out = d_out; a.out_stride = out_stride; a.out_len = d_out_len; a.tap = d_tap;
+    a.out = d_out; a.out_stride = out_stride; a.out_len = d_out_len; a.tap = tap ? d_tap : nullptr;
+    a.writeback = wb ? 1 : 0;
+    if (g.d.ring_fractional || g.d.eod_count <= 16) generic = true;  // needs the per-sample state machine
     a.force_generic = (flags & WAM_BATCH_DEBUG_GENERIC_SM) ? 1 : 0;
     a.append = append ? 1 : 0;
     a.phase_cycles = b->phase_cycles;

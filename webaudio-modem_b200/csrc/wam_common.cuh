@@ -95,6 +95,7 @@ struct DemodArgs {
   int32_t* out_len;     // [rows]
   float* tap;           // optional [rows][stride]
   int force_generic;    // debug: per-sample state machine even where the event-driven one applies
+  int writeback;        // write the AGC-scaled samples back into `samples` (fsk.ts:55)
   int append;           // out_len[row] holds the bytes already written for this stream: append after them
   unsigned long long* phase_cycles;  // debug (nullable): [CTA][4] SM cycles spent in A1, A2, B, staging/other
 };
