@@ -746,13 +746,16 @@ static int modulate_device_group(wam_fsk_batch* b, const Group& g, const uint8_t
   a.out = d_out; a.out_stride = out_stride; a.out_len = d_out_len;
   a.prefix = b->mod_prefix; a.prefix_stride = prefix_stride;
   a.vec_ok = ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && out_stride % 4 == 0) ? 1 : 0;
+  a.rot_mark_c = (float)cos(2 * M_PI * g.d.mark / g.d.fs); a.rot_mark_s = (float)sin(2 * M_PI * g.d.mark / g.d.fs);
+  a.rot_space_c = (float)cos(2 * M_PI * g.d.space / g.d.fs); a.rot_space_s = (float)sin(2 * M_PI * g.d.space / g.d.fs);
   const int warps_per_block = 4;
   fsk_mark_prefix_kernel<<<(unsigned)((n_rows + warps_per_block - 1) / warps_per_block), 128, 0, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   const long max_total = std::min(modulate_size(g.d, max_bytes), out_stride);
-  dim3 grid((unsigned)((max_total + 511) / 512), (unsigned)n_rows);
+  const long per_block = (long)kModThreads * kModPerThread;
+  dim3 grid((unsigned)((max_total + per_block - 1) / per_block), (unsigned)n_rows);
   if (grid.x == 0) grid.x = 1;
-  fsk_modulate_kernel<<<grid, 128, 0, st>>>(a);
+  fsk_modulate_kernel<<<grid, kModThreads, 0, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   b->launches += 2;
   return WAM_OK;
@@ -1019,7 +1022,8 @@ extern "C" int wam_xmodem_batch_check_device(const uint8_t* d_bytes, long stride
   if (n_streams < 0 || !d_len || !d_results || (!d_bytes && stride > 0)) return fail(WAM_E_INVALID, "bad argument");
   if (n_streams == 0) return WAM_OK;
   static_assert(sizeof(PktResultDev) == sizeof(wam_pkt_result), "layout");
-  xmodem_check_kernel<<<(unsigned)((n_streams + 3) / 4), 128, 0, (cudaStream_t)cuda_stream>>>(
+  const long want_ctas = (n_streams + 3) / 4;
+  xmodem_check_kernel<<<(unsigned)std::min<long>(want_ctas, 148L * 16), 128, 0, (cudaStream_t)cuda_stream>>>(
       d_bytes, stride, d_len, d_expected_seq, n_streams, reinterpret_cast<PktResultDev*>(d_results));
   CUDA_TRY(cudaGetLastError());
   return WAM_OK;
