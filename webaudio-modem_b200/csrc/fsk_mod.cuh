@@ -2,11 +2,15 @@
 //
 // The reference walks one phase accumulator through the whole frame (fsk.ts:398-405).  Here the
 // phase of any sample is available in closed form, so time parallelises freely:
-//   kernel 1 (mark_prefix): per stream, the number of mark ('1') line bits before every byte —
-//       the integer form of "phase carried across blocks";
-//   kernel 2 (modulate):    one thread per 8 output samples; phase in cycles =
-//       (spb * (marks_before*f_mark + spaces_before*f_space) + r * f_bit) / fs, reduced to its
-//       fractional part in float64 (exact for integral tone frequencies), then sinpi in float32.
+//   kernel 1 (bit_phase): one CTA per stream; a block scan gives the number of mark ('1') line bits
+//       before every byte — the integer form of "phase carried across blocks" — and every line bit
+//       gets one table word: the phase at its first sample, in cycles =
+//       frac(spb * (marks_before*f_mark + spaces_before*f_space) / fs), evaluated in float64 (the
+//       products are exact integers for integral tone frequencies), stored as a 31-bit binary
+//       fraction with the bit's value in bit 0.  The table is 1/spb of the output in size.
+//   kernel 2 (modulate): HBM-write bound.  One thread per float4 of output, a warp per 512
+//       contiguous bytes; the phase inside a bit advances in 32-bit fixed point (wraps modulo one
+//       cycle for free), so a sample costs IMAD + I2F + FMUL + MUFU.SIN.
 // Layout: data [stream][data_stride] u8, out [stream][out_stride] f32 (float4 stores, coalesced).
 #pragma once
 
@@ -24,10 +28,11 @@ struct ModArgs {
   float* out;               // [n_streams][out_stride]
   long out_stride;
   int32_t* out_len;         // nullable
-  uint32_t* prefix;         // [n_streams][prefix_stride]: mark bits before byte k (k = 0..totalBytes)
-  int prefix_stride;
+  uint32_t* bittab;         // [n_streams][tab_stride]: per line bit, phase at its first sample | bit value
+  int tab_stride;
   int vec_ok;               // out rows 16-byte aligned
-  float rot_mark_c, rot_mark_s, rot_space_c, rot_space_s;  // cos/sin(2 pi f / fs) of the two tones
+  uint32_t step_fix[2];     // round(f / fs * 2^32) for space (0) and mark (1): cycles per sample, fixed point
+  uint32_t spb_magic;       // floor(2^32 / spb): division by multiply-high plus one fix-up
 };
 
 __device__ __forceinline__ int frame_byte(const ModArgs& a, const uint8_t* row, int k) {
@@ -60,150 +65,212 @@ __device__ __forceinline__ int framed_ones(const FskDerived& d, int byte) {
   return ones;
 }
 
-// one warp per stream: exclusive prefix sum of mark bits per framed byte
-__global__ void __launch_bounds__(128) fsk_mark_prefix_kernel(const __grid_constant__ ModArgs a) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= a.n_streams) return;
-  const int nbytes = a.data_len ? a.data_len[warp] : a.nbytes;
-  const int total = a.d.n_preamble + a.d.n_sfd + nbytes;
-  const uint8_t* row = a.data + (long)warp * a.data_stride;
-  uint32_t* pre = a.prefix + (long)warp * a.prefix_stride;
+// number of mark bits among line bits 0..b-1 of a framed byte
+__device__ __forceinline__ int framed_ones_before(const FskDerived& d, int byte, int b) {
+  int rest = b - d.start_bits;
+  if (rest <= 0) return 0;
+  const int nb = rest < 8 ? rest : 8;
+  int ones = __popc(((unsigned)byte & 0xffu) >> (8 - nb));
+  rest -= 8;
+  if (rest > 0 && d.parity != 0) {
+    const int p = __popc((unsigned)byte & 0xffu) & 1;
+    ones += d.parity == 1 ? p : 1 - p;
+    rest -= 1;
+  }
+  if (rest > 0) ones += rest;  // stop bits
+  return ones;
+}
+
+constexpr int kPhaseThreads = 128;
+
+// one CTA per stream; bytes in chunks of kPhaseThreads: a block scan gives the mark bits before every byte
+// of the chunk, then the threads fill the chunk's table words one line bit each (coalesced stores)
+__global__ void __launch_bounds__(kPhaseThreads) fsk_bit_phase_kernel(const __grid_constant__ ModArgs a) {
+  __shared__ uint32_t s_pre[kPhaseThreads];
+  __shared__ uint8_t s_byte[kPhaseThreads];
+  __shared__ uint32_t s_wsum[kPhaseThreads / 32];
+  const int s = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const FskDerived& d = a.d;
+  const int nbytes = a.data_len ? a.data_len[s] : a.nbytes;
+  const int total = d.n_preamble + d.n_sfd + nbytes;
+  const uint8_t* row = a.data + (long)s * a.data_stride;
+  uint32_t* tab = a.bittab + (long)s * a.tab_stride;
+  const double spb_d = (double)d.spb, inv_fs = 1.0 / d.fs;
   uint32_t carry = 0;
-  for (int base = 0; base <= total; base += 32) {
-    const int k = base + lane;
-    uint32_t v = (k < total) ? (uint32_t)framed_ones(a.d, frame_byte(a, row, k)) : 0u;
+  for (int base = 0; base < total; base += kPhaseThreads) {
+    const int k = base + tid;
+    const int byte = (k < total) ? frame_byte(a, row, k) : 0;
+    const uint32_t v = (k < total) ? (uint32_t)framed_ones(d, byte) : 0u;
     uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += t;
     }
-    if (k <= total) pre[k] = carry + incl - v;
-    carry += __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 31) s_wsum[wid] = incl;
+    __syncthreads();
+    uint32_t woff = 0, wtot = 0;
+#pragma unroll
+    for (int w = 0; w < kPhaseThreads / 32; ++w) {
+      const uint32_t t = s_wsum[w];
+      if (w < wid) woff += t;
+      wtot += t;
+    }
+    s_pre[tid] = carry + woff + incl - v;
+    s_byte[tid] = (uint8_t)byte;
+    __syncthreads();
+    const int nb = min(kPhaseThreads, total - base);
+    const uint32_t bpb_magic = 65536u / (uint32_t)d.bpb + 1u;  // i / bpb for i < 65536 / bpb
+    for (int i = tid; i < nb * d.bpb; i += kPhaseThreads) {
+      const int kk = (int)(((uint32_t)i * bpb_magic) >> 16);
+      const int b = i - kk * d.bpb;
+      const int by = s_byte[kk];
+      const int marks = (int)s_pre[kk] + framed_ones_before(d, by, b);
+      const int bitidx = base * d.bpb + i;
+      // cycles since the start of the frame at the first sample of this bit: an exact integer (for integral
+      // tone frequencies) times 1/fs, i.e. ~1e-13 cycles of rounding at most
+      const double spaces = (double)(bitidx - marks);
+      const double cyc = (spb_d * fma((double)marks, d.mark, spaces * d.space)) * inv_fs;
+      const double fr = cyc - floor(cyc);
+      const uint32_t fix = __double2uint_rz(fr * 4294967296.0);
+      tab[bitidx] = (fix & ~1u) | (uint32_t)framed_bit(d, by, b);
+    }
+    carry += wtot;
+    __syncthreads();
   }
 }
 
-// Per-thread bit cursor: everything that changes once per line bit.
-struct ModCursor {
-  int bitidx, bib, byteidx, byte, marks, cur;
-  double base;  // fractional cycles at the first sample of the current bit
-  double step;  // cycles per sample of the current bit
-};
+constexpr int kModThreads = 256;
 
-__device__ __forceinline__ void mod_cursor_phase(const FskDerived& d, ModCursor& c) {
-  // cycles since the start of the frame at the start of this bit; the products are exact integers for
-  // integral tone frequencies, so the only rounding is the division by fs
-  const double spaces = (double)(c.bitidx - c.marks);
-  double cyc = ((double)d.spb * ((double)c.marks * d.mark + spaces * d.space)) / d.fs;
-  c.base = cyc - floor(cyc);
-  c.step = (c.cur ? d.mark : d.space) / d.fs;
+// sin(2 pi * p / 2^32) for a 32-bit fixed-point phase: the signed reinterpretation is the angle in
+// (-pi, pi], where MUFU.SIN is accurate to ~5e-7 absolute
+__device__ __forceinline__ float sin_fix(uint32_t p) {
+  return __sinf((float)(int32_t)p * 1.4629180792671596e-9f);  // 2 pi / 2^32
 }
 
-__device__ __forceinline__ void mod_cursor_seek(const ModArgs& a, const uint8_t* row, const uint32_t* pre, int bitidx,
-                                                ModCursor& c) {
-  const FskDerived& d = a.d;
-  c.bitidx = bitidx;
-  c.byteidx = bitidx / d.bpb;
-  c.bib = bitidx - c.byteidx * d.bpb;
-  c.byte = frame_byte(a, row, c.byteidx);
-  c.marks = (int)pre[c.byteidx];
-  for (int b = 0; b < c.bib; ++b) c.marks += framed_bit(d, c.byte, b);
-  c.cur = framed_bit(d, c.byte, c.bib);
-  mod_cursor_phase(d, c);
-}
-
-__device__ __forceinline__ void mod_cursor_next_bit(const ModArgs& a, const uint8_t* row, ModCursor& c) {
-  const FskDerived& d = a.d;
-  c.marks += c.cur;
-  c.bitidx++;
-  if (++c.bib == d.bpb) {
-    c.bib = 0;
-    c.byteidx++;
-    c.byte = frame_byte(a, row, c.byteidx);
+// generic float4: crosses a bit boundary or an end of the frame body (one sample at a time)
+__device__ __noinline__ float4 mod_straddle(const ModArgs& a, const uint32_t* __restrict__ tab, uint32_t k0,
+                                            uint32_t pad, uint32_t body_end) {
+  const uint32_t spb = (uint32_t)a.d.spb;
+  float w[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  const uint32_t kf = k0 > pad ? k0 : pad;  // first body sample of this float4
+  const uint32_t m0 = kf - pad;
+  uint32_t q = __umulhi(m0, a.spb_magic);
+  uint32_t r = m0 - q * spb;
+  if (r >= spb) { ++q; r -= spb; }
+  uint32_t e = (kf < body_end) ? __ldg(tab + q) : 0u;
+#pragma unroll
+  for (uint32_t i = 0; i < 4u; ++i) {
+    const uint32_t k = k0 + i;
+    if (k >= kf && k < body_end) {
+      w[i] = sin_fix((e & ~1u) + r * a.step_fix[e & 1u]);
+      if (++r == spb) {
+        r = 0;
+        ++q;
+        if (k + 1u < body_end) e = __ldg(tab + q);
+      }
+    }
   }
-  c.cur = framed_bit(d, c.byte, c.bib);
-  mod_cursor_phase(d, c);
+  return make_float4(w[0], w[1], w[2], w[3]);
 }
 
-constexpr int kModPerThread = 8;   // consecutive samples per thread (two float4 stores)
-constexpr int kModThreads = 128;
+__device__ __forceinline__ void mod_divmod(uint32_t m, uint32_t spb, uint32_t magic, uint32_t& q, uint32_t& r) {
+  q = __umulhi(m, magic);  // floor(2^32 / spb) undershoots the quotient by at most one
+  r = m - q * spb;
+  if (r >= spb) { ++q; r -= spb; }
+}
 
-// grid: (ceil(max_total / (kModThreads * kModPerThread)), n_streams)
-// One division per thread locates its first sample's bit; inside a bit the phase advances linearly, so a
-// sample costs one FFMA + sinpif.  The run is re-based in float64 at its start and at every bit boundary,
-// which keeps the float32 phase error below 1e-7 cycles whatever the baud rate.
+// grid: (blocks per row, n_streams); a block walks its row with stride gridDim.x * kModThreads float4s, so
+// every warp store covers 512 contiguous bytes.  Sample indices inside a row are 32-bit (the host rejects
+// frames of 2^31 samples or more).  The (bit, offset) pair of a thread's next float4 advances incrementally.
+// ALIGNED (spb % 4 == 0, rows 16-byte aligned, out_stride % 4 == 0): every float4 lies inside one line bit
+// or inside the zero padding, so the loop body is branch-light: table word, fixed-point phase, four MUFU.SIN,
+// one streaming 16-byte store.
+template <bool ALIGNED>
 __global__ void __launch_bounds__(kModThreads) fsk_modulate_kernel(const __grid_constant__ ModArgs a) {
   const int s = blockIdx.y;
   const FskDerived& d = a.d;
   const int nbytes = a.data_len ? a.data_len[s] : a.nbytes;
-  const long total_bytes = (long)d.n_preamble + d.n_sfd + nbytes;
-  const long pad = total_bytes > 0 ? 2L * d.spb : 0;
-  const long body = total_bytes * d.bpb * d.spb;
-  const long total = body + pad + (long)d.bpb * d.spb;
-  const uint8_t* row = a.data + (long)s * a.data_stride;
-  const uint32_t* pre = a.prefix + (long)s * a.prefix_stride;
-  float* out = a.out + (long)s * a.out_stride;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && a.out_len) a.out_len[s] = (int32_t)(total < a.out_stride ? total : a.out_stride);
-  const long k0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * kModPerThread;
-  const long lim = total < a.out_stride ? total : a.out_stride;
-  if (k0 >= lim) return;
-
-  float v[kModPerThread];
-#pragma unroll
-  for (int i = 0; i < kModPerThread; ++i) v[i] = 0.0f;  // lead padding / tail silence stay zero (fsk.ts:392-395)
-  const long first = k0 > pad ? k0 : pad;                // first body sample of this run
-  const long last = (k0 + kModPerThread < pad + body) ? k0 + kModPerThread : pad + body;
-  if (first < last) {
-    const unsigned m0 = (unsigned)(first - pad);
-    const int bitidx = (int)(m0 / (unsigned)d.spb);
-    int r = (int)(m0 - (unsigned)bitidx * (unsigned)d.spb);
-    ModCursor c;
-    mod_cursor_seek(a, row, pre, bitidx, c);
-    double ph = fma((double)r, c.step, c.base);
-    ph -= floor(ph);
-    if (first == k0 && last == k0 + kModPerThread && r + kModPerThread <= d.spb) {
-      // whole run inside one line bit: a pure tone.  One sincospi seeds a rotation by the tone's
-      // per-sample angle (cos/sin computed on the host in float64); 8 steps add < 1e-6 of error.
-      float sn, cs;
-      sincospif(2.0f * (float)ph, &sn, &cs);
-      const float rc = c.cur ? a.rot_mark_c : a.rot_space_c;
-      const float rs = c.cur ? a.rot_mark_s : a.rot_space_s;
-#pragma unroll
-      for (int i = 0; i < kModPerThread; ++i) {
-        v[i] = sn;
-        const float ns = fmaf(sn, rc, cs * rs);
-        cs = fmaf(cs, rc, -sn * rs);
-        sn = ns;
+  const uint32_t spb = (uint32_t)d.spb;
+  const uint32_t total_bytes = (uint32_t)(d.n_preamble + d.n_sfd + nbytes);
+  const uint32_t pad = total_bytes > 0 ? 2u * spb : 0u;  // fsk.ts:392
+  const uint32_t body_end = pad + total_bytes * (uint32_t)d.bpb * spb;
+  const uint32_t total = body_end + (uint32_t)d.bpb * spb;
+  const uint32_t lim = (long)total < a.out_stride ? total : (uint32_t)a.out_stride;
+  const uint32_t* __restrict__ tab = a.bittab + (long)s * a.tab_stride;
+  float* __restrict__ out = a.out + (long)s * a.out_stride;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.out_len) a.out_len[s] = (int32_t)lim;
+  const uint32_t st0 = a.step_fix[0], st1 = a.step_fix[1];
+  const uint32_t stride = gridDim.x * (uint32_t)(4 * kModThreads);
+  uint32_t k0 = (blockIdx.x * (uint32_t)kModThreads + threadIdx.x) * 4u;
+  // (q, r) = divmod(k0 - pad, spb), kept valid while k0 >= pad; (dq, dr) = divmod(stride, spb)
+  uint32_t q = 0, r = 0, dq, dr;
+  mod_divmod(stride, spb, a.spb_magic, dq, dr);
+  if (ALIGNED) {
+    // pad is 0 or 2 * spb: divide k0 itself and shift the bit index by pad / spb
+    mod_divmod(k0, spb, a.spb_magic, q, r);
+    const uint32_t* __restrict__ tabq = tab - (pad ? 2 : 0);
+    const uint32_t body_len = body_end - pad;
+    const uint32_t lim4 = lim & ~3u;
+    float* po = out + k0;
+    // the table word of the NEXT float4 is requested before this one is evaluated (the table is read once,
+    // from HBM: without the prefetch every iteration waits out a full DRAM latency)
+    uint32_t e = (k0 < lim4 && k0 - pad < body_len) ? __ldg(tabq + q) : 0u;
+    for (; k0 < lim4; k0 += stride, po += stride) {
+      uint32_t qn = q + dq, rn = r + dr;
+      if (rn >= spb) { rn -= spb; ++qn; }
+      const uint32_t kn = k0 + stride;
+      const uint32_t en = (kn < lim4 && kn - pad < body_len) ? __ldg(tabq + qn) : 0u;
+      float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (k0 - pad < body_len) {  // unsigned: also false for k0 < pad
+        const uint32_t st = (e & 1u) ? st1 : st0;
+        const uint32_t p0 = (e & ~1u) + r * st;
+        v.x = sin_fix(p0); v.y = sin_fix(p0 + st); v.z = sin_fix(p0 + 2u * st); v.w = sin_fix(p0 + 3u * st);
       }
-    } else {
-      float basef = (float)ph;
-      float stepf = (float)c.step;
-      int j = 0;  // samples since the last re-base
-#pragma unroll
-      for (int i = 0; i < kModPerThread; ++i) {
-        const long k = k0 + i;
-        if (k >= first && k < last) {
-          v[i] = sinpif(2.0f * fmaf((float)j, stepf, basef));
-          ++j;
-          if (++r == d.spb && k + 1 < last) {  // next line bit: re-base in float64
-            r = 0;
-            mod_cursor_next_bit(a, row, c);
-            basef = (float)c.base;
-            stepf = (float)c.step;
-            j = 0;
-          }
-        }
-      }
+      __stcs(reinterpret_cast<float4*>(po), v);
+      q = qn; r = rn; e = en;
     }
+    // a row cut short by out_stride can end inside a float4
+    if (k0 < lim) {
+      const float4 v = mod_straddle(a, tab, k0, pad, body_end);
+      const float w[4] = {v.x, v.y, v.z, v.w};
+      for (uint32_t i = 0; k0 + i < lim; ++i) out[k0 + i] = w[i];
+    }
+    return;
   }
-  if (a.vec_ok && k0 + kModPerThread <= lim) {
-    reinterpret_cast<float4*>(out + k0)[0] = make_float4(v[0], v[1], v[2], v[3]);
-    reinterpret_cast<float4*>(out + k0)[1] = make_float4(v[4], v[5], v[6], v[7]);
-  } else {
+  bool have_qr = false;
+  const bool vec = a.vec_ok != 0;
+  for (; k0 < lim; k0 += stride) {
+    float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // lead padding / tail silence stay zero (fsk.ts:392-395)
+    if (k0 >= pad) {
+      if (!have_qr) { mod_divmod(k0 - pad, spb, a.spb_magic, q, r); have_qr = true; }
+      if (k0 + 4u <= body_end) {
+        if (r + 4u <= spb) {
+          // the whole float4 lies inside one line bit
+          const uint32_t e = __ldg(tab + q);
+          const uint32_t st = (e & 1u) ? st1 : st0;
+          const uint32_t p0 = (e & ~1u) + r * st;
+          v.x = sin_fix(p0); v.y = sin_fix(p0 + st); v.z = sin_fix(p0 + 2u * st); v.w = sin_fix(p0 + 3u * st);
+        } else {
+          v = mod_straddle(a, tab, k0, pad, body_end);
+        }
+      } else if (k0 < body_end) {
+        v = mod_straddle(a, tab, k0, pad, body_end);
+      }
+      q += dq; r += dr;
+      if (r >= spb) { r -= spb; ++q; }
+    } else if (k0 + 4u > pad && pad < body_end) {
+      v = mod_straddle(a, tab, k0, pad, body_end);
+    }
+    if (vec && k0 + 4u <= lim) {
+      __stcs(reinterpret_cast<float4*>(out + k0), v);
+    } else {
+      const float w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int i = 0; i < kModPerThread; ++i)
-      if (k0 + i < lim) out[k0 + i] = v[i];
+      for (int i = 0; i < 4; ++i)
+        if (k0 + i < lim) out[k0 + i] = w[i];
+    }
   }
 }
 

@@ -736,26 +736,33 @@ static long modulate_size(const FskDerived& d, long nbytes) {  // fsk.ts:391-394
 static int modulate_device_group(wam_fsk_batch* b, const Group& g, const uint8_t* d_data, long data_stride,
                                  const int32_t* d_data_len, long nbytes, long max_bytes, float* d_out, long out_stride,
                                  int32_t* d_out_len, long n_rows, cudaStream_t st) {
-  const int prefix_stride = (int)(g.d.n_preamble + g.d.n_sfd + max_bytes + 1);
-  int rc = ensure((void**)&b->mod_prefix, &b->mod_prefix_bytes, sizeof(uint32_t) * (size_t)prefix_stride * (size_t)n_rows);
+  const int tab_stride = std::max(1, (int)(g.d.n_preamble + g.d.n_sfd + max_bytes) * g.d.bpb);
+  int rc = ensure((void**)&b->mod_prefix, &b->mod_prefix_bytes, sizeof(uint32_t) * (size_t)tab_stride * (size_t)n_rows);
   if (rc != WAM_OK) return rc;
+  if (g.d.spb < 1) return fail(WAM_E_INVALID, "samplesPerBit must be >= 1");
+  if (modulate_size(g.d, max_bytes) >= (1L << 31)) return fail(WAM_E_UNSUPPORTED, "frame longer than 2^31 samples");
   ModArgs a;
   a.d = g.d;
   a.data = d_data; a.data_stride = data_stride; a.data_len = d_data_len; a.nbytes = (int)nbytes;
   a.n_streams = (int)n_rows;
   a.out = d_out; a.out_stride = out_stride; a.out_len = d_out_len;
-  a.prefix = b->mod_prefix; a.prefix_stride = prefix_stride;
+  a.bittab = b->mod_prefix; a.tab_stride = tab_stride;
   a.vec_ok = ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && out_stride % 4 == 0) ? 1 : 0;
-  a.rot_mark_c = (float)cos(2 * M_PI * g.d.mark / g.d.fs); a.rot_mark_s = (float)sin(2 * M_PI * g.d.mark / g.d.fs);
-  a.rot_space_c = (float)cos(2 * M_PI * g.d.space / g.d.fs); a.rot_space_s = (float)sin(2 * M_PI * g.d.space / g.d.fs);
-  const int warps_per_block = 4;
-  fsk_mark_prefix_kernel<<<(unsigned)((n_rows + warps_per_block - 1) / warps_per_block), 128, 0, st>>>(a);
+  // cycles per sample in 32-bit fixed point (the phase wraps modulo one cycle for free)
+  a.step_fix[0] = (uint32_t)(unsigned long long)llround(fmod(g.d.space / g.d.fs, 1.0) * 4294967296.0);
+  a.step_fix[1] = (uint32_t)(unsigned long long)llround(fmod(g.d.mark / g.d.fs, 1.0) * 4294967296.0);
+  a.spb_magic = g.d.spb >= 2 ? (uint32_t)(4294967296ull / (unsigned long long)g.d.spb) : 0xffffffffu;
+  fsk_bit_phase_kernel<<<(unsigned)n_rows, kPhaseThreads, 0, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   const long max_total = std::min(modulate_size(g.d, max_bytes), out_stride);
-  const long per_block = (long)kModThreads * kModPerThread;
-  dim3 grid((unsigned)((max_total + per_block - 1) / per_block), (unsigned)n_rows);
-  if (grid.x == 0) grid.x = 1;
-  fsk_modulate_kernel<<<grid, kModThreads, 0, st>>>(a);
+  // blocks per row: whole rows per block when there are enough rows to fill the GPU, otherwise split rows
+  const long per_pass = (long)kModThreads * 4;
+  const long passes = (max_total + per_pass - 1) / per_pass;
+  long bx = (8L * 148 + n_rows - 1) / n_rows;
+  bx = std::max(1L, std::min(bx, passes));
+  dim3 grid((unsigned)bx, (unsigned)n_rows);
+  if (a.vec_ok && g.d.spb % 4 == 0) fsk_modulate_kernel<true><<<grid, kModThreads, 0, st>>>(a);
+  else fsk_modulate_kernel<false><<<grid, kModThreads, 0, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   b->launches += 2;
   return WAM_OK;
