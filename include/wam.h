@@ -196,6 +196,35 @@ int wam_xmodem_batch_check(int device, const uint8_t* bytes, long stride, const 
 int wam_xmodem_batch_check_device(const uint8_t* d_bytes, long stride, const int32_t* d_len,
                                   const int32_t* d_expected_seq, long n_streams, wam_pkt_result* d_results,
                                   void* cuda_stream);
+/* Batched receive side of XModemTransport (receiveAllPackets + receiveAndProcessPacket,
+ * xmodem.ts:232-321): every stream's burst of demodulated bytes is walked packet by packet with the
+ * receiver state carried between calls — sequence tracking, duplicate detection, retry counting, payload
+ * reassembly, and the ACK (0x06) / NAK (0x15) bytes the transport would send, in order.  No timers: where
+ * the reference would wait for more bytes the walk stops; consumed[s] tells how many bytes were used (an
+ * unfinished packet is left unconsumed from its SOH on, present it again with the bytes that follow).  An
+ * error (bad complement, bad CRC, unexpected sequence) counts a retry; beyond max_retries the session
+ * fails (done = 2, xmodem.ts:253-255), otherwise the rest of the burst is discarded (receive.buffer = [],
+ * xmodem.ts:257) and a NAK is queued.  Initialise a state with {1, 0, 0, 0, 0, 0}. */
+typedef struct wam_xmodem_rx_state {
+  int32_t expectedSequence; /* receive.expectedSequence (starts at 1) */
+  int32_t retries;          /* send.retries, xmodem.ts:253,299 */
+  int32_t done;             /* 0 running, 1 EOT received and ACKed, 2 failed after max retries */
+  int32_t dataLen;          /* reassembled payload bytes so far (receive.data) */
+  int32_t packetsReceived;  /* statistics.packetsReceived, xmodem.ts:277 */
+  int32_t packetsDropped;   /* statistics.packetsDropped, xmodem.ts:271,287,312,317 */
+} wam_xmodem_rx_state;
+/* HOST buffers: bytes [n_streams][stride], len[s]; state[s] in/out; replies [n_streams][reply_cap]
+ * (n_replies[s] counts all replies, also those beyond reply_cap); data [n_streams][data_stride]: payloads
+ * are appended at state[s].dataLen (data may be NULL: only the counters advance). */
+int wam_xmodem_batch_receive(int device, const uint8_t* bytes, long stride, const int32_t* len, long n_streams,
+                             int max_retries, wam_xmodem_rx_state* state, uint8_t* replies, int reply_cap,
+                             int32_t* n_replies, int32_t* consumed, uint8_t* data, long data_stride);
+/* Same with DEVICE pointers, asynchronous on cuda_stream (e.g. fed straight from
+ * wam_fsk_batch_demodulate_device's output rows). */
+int wam_xmodem_batch_receive_device(const uint8_t* d_bytes, long stride, const int32_t* d_len, long n_streams,
+                                    int max_retries, wam_xmodem_rx_state* d_state, uint8_t* d_replies,
+                                    int reply_cap, int32_t* d_n_replies, int32_t* d_consumed, uint8_t* d_data,
+                                    long data_stride, void* cuda_stream);
 /* CRC-16 of n_blocks byte blocks on the GPU (warp per block). HOST buffers. */
 int wam_crc16_batch(int device, const uint8_t* bytes, long stride, const int32_t* len, long n_blocks,
                     uint16_t* crc_out);

@@ -67,6 +67,11 @@ class StatusStruct(C.Structure):
     ]
 
 
+class XmodemRxState(C.Structure):
+    _fields_ = [("expectedSequence", C.c_int32), ("retries", C.c_int32), ("done", C.c_int32),
+                ("dataLen", C.c_int32), ("packetsReceived", C.c_int32), ("packetsDropped", C.c_int32)]
+
+
 class PktResult(C.Structure):
     _fields_ = [
         ("status", C.c_int32),
@@ -171,6 +176,8 @@ def lib():
     L.wamo_xmodem_serialize.restype = C.c_long
     L.wamo_xmodem_serialize.argtypes = [C.c_int, u8p, C.c_long, u8p, C.c_long]
     L.wamo_xmodem_check.argtypes = [u8p, C.c_long, C.c_int, C.POINTER(PktResult)]
+    L.wamo_xmodem_receive.restype = C.c_long
+    L.wamo_xmodem_receive.argtypes = [u8p, C.c_long, C.c_int, C.POINTER(XmodemRxState), u8p, C.c_int, i32p, u8p, C.c_long]
     L.wamo_fsk_batch_demodulate.restype = C.c_int
     L.wamo_fsk_batch_demodulate.argtypes = [C.POINTER(FSKConfigStruct), i32p, C.c_long, fp, C.c_long, C.c_long,
                                             u8p, C.c_long, i32p, C.POINTER(StatusStruct), C.c_int]
@@ -417,6 +424,27 @@ def xmodem_check(data, expected_sequence: int = 1) -> dict:
     r = PktResult()
     lib().wamo_xmodem_check(_u8(a) if len(a) else None, len(a), expected_sequence, C.byref(r))
     return {k: getattr(r, k) for k, _ in PktResult._fields_}
+
+
+RX_STATE_FIELDS = [k for k, _ in XmodemRxState._fields_]
+
+
+def xmodem_receive(data, state: dict | None = None, max_retries: int = 10, reply_cap: int = 64, data_cap: int = 1 << 16):
+    """One burst through the receive side of XModemTransport (xmodem.ts:232-321).
+    Returns (new_state dict, replies bytes, n_replies, consumed, payload bytes appended by this burst)."""
+    a = np.frombuffer(bytes(data), dtype=np.uint8)
+    st = XmodemRxState(1, 0, 0, 0, 0, 0)
+    if state is not None:
+        for k in RX_STATE_FIELDS:
+            setattr(st, k, int(state[k]))
+    base = st.dataLen
+    replies = np.zeros(max(reply_cap, 1), dtype=np.uint8)
+    out = np.zeros(base + data_cap, dtype=np.uint8)
+    nrep = C.c_int32(0)
+    consumed = lib().wamo_xmodem_receive(_u8(a) if len(a) else None, len(a), max_retries, C.byref(st), _u8(replies),
+                                         reply_cap, C.byref(nrep), _u8(out), len(out))
+    new = {k: getattr(st, k) for k in RX_STATE_FIELDS}
+    return new, bytes(replies[: min(nrep.value, reply_cap)]), nrep.value, int(consumed), bytes(out[base: st.dataLen])
 
 
 def batch_demodulate(cfgs: list[dict], cfg_index, samples: np.ndarray, n_threads: int = 1, want_status=True):

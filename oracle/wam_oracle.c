@@ -346,6 +346,68 @@ void wamo_xmodem_check(const uint8_t* bytes, long n, int expectedSequence, wamo_
   }
 }
 
+/* XModemTransport.receiveAllPackets + receiveAndProcessPacket over one burst — xmodem.ts:232-321 */
+long wamo_xmodem_receive(const uint8_t* bytes, long n, int maxRetries, wamo_xmodem_rx_state* st,
+                         uint8_t* replies, int reply_cap, int32_t* n_replies, uint8_t* data, long data_cap) {
+  long p = 0;
+  int nrep = 0;
+#define WAMO_REPLY(c) do { if (nrep < reply_cap) replies[nrep] = (uint8_t)(c); nrep++; } while (0)
+  while (!st->done) {
+    if (p >= n) break;                      /* waitForByte would block (xmodem.ts:239) */
+    const uint8_t first = bytes[p];
+    if (first == 0x04) {                    /* EOT: final ACK (xmodem.ts:241-244) */
+      p++;
+      WAMO_REPLY(0x06);
+      st->done = 1;
+      break;
+    }
+    if (first != 0x01) { p++; continue; }   /* ignored byte (xmodem.ts:248-250) */
+    /* receiveAndProcessPacket (xmodem.ts:265-321) */
+    if (p + 4 > n) break;                   /* header not complete yet: keep the SOH */
+    const int seq = bytes[p + 1], nseq = bytes[p + 2], len = bytes[p + 3];
+    int error = 0;
+    if (seq + nseq != 255) {
+      st->packetsDropped++;
+      error = 1;
+    } else {
+      const int prevSeq = st->expectedSequence == 1 ? 255 : st->expectedSequence - 1; /* xmodem.ts:525-530 */
+      if (seq == st->expectedSequence) {
+        if (p + 4 + len + 2 > n) break;     /* payload not complete yet */
+        st->packetsReceived++;
+        const int crc = (bytes[p + 4 + len] << 8) | bytes[p + 4 + len + 1];
+        if ((int)wamo_crc16(bytes + p + 4, len) != crc) {
+          st->packetsDropped++;
+          error = 1;
+        } else {
+          for (int i = 0; i < len; i++)
+            if ((long)st->dataLen + i < data_cap) data[st->dataLen + i] = bytes[p + 4 + i];
+          st->dataLen += len;
+          st->expectedSequence = (st->expectedSequence % 255) + 1;
+          st->retries = 0;
+          WAMO_REPLY(0x06);
+          p += 4 + len + 2;
+        }
+      } else if (seq == prevSeq) {
+        if (p + 4 + len + 2 > n) break;
+        st->packetsDropped++;
+        WAMO_REPLY(0x06);                   /* duplicate: consumed, ACKed, ignored (xmodem.ts:309-314) */
+        p += 4 + len + 2;
+      } else {
+        st->packetsDropped++;
+        error = 1;
+      }
+    }
+    if (error) {                            /* catch block, xmodem.ts:251-260 */
+      if (++st->retries > maxRetries) { st->done = 2; p = n; break; }
+      p = n;                                /* receive.buffer = [] */
+      WAMO_REPLY(0x15);
+    }
+  }
+#undef WAMO_REPLY
+  *n_replies = nrep;
+  return p;
+}
+
 /* ------------------------------------------------------------------------------------------
  * AGCProcessor — src/modems/fsk.ts:38-77
  * ---------------------------------------------------------------------------------------- */

@@ -148,6 +148,26 @@ typedef struct wamo_pkt_result {
 } wamo_pkt_result;
 void wamo_xmodem_check(const uint8_t* bytes, long n, int expectedSequence, wamo_pkt_result* res);
 
+/* Receive side of XModemTransport.receiveAllPackets / receiveAndProcessPacket (xmodem.ts:232-321) over one
+ * burst of demodulated bytes, with the receiver state carried between bursts.  No timers: where the
+ * reference would wait for more bytes (and eventually time out), the walk stops and reports how many bytes
+ * it consumed (an unfinished packet is left unconsumed from its SOH on).  An error (bad complement, bad CRC,
+ * unexpected sequence) counts a retry; beyond maxRetries the session fails (xmodem.ts:253-255), otherwise the
+ * rest of the burst is discarded (receive.buffer = [], xmodem.ts:257) and a NAK is queued. */
+typedef struct wamo_xmodem_rx_state {
+  int32_t expectedSequence; /* receive.expectedSequence, starts at 1 */
+  int32_t retries;          /* send.retries (xmodem.ts:253,299) */
+  int32_t done;             /* 0 running, 1 EOT received and ACKed, 2 failed after max retries */
+  int32_t dataLen;          /* reassembled payload bytes so far (receive.data) */
+  int32_t packetsReceived;  /* statistics.packetsReceived (xmodem.ts:277) */
+  int32_t packetsDropped;   /* statistics.packetsDropped (xmodem.ts:271,287,312,317) */
+} wamo_xmodem_rx_state;
+/* replies: ACK 0x06 / NAK 0x15 in the order they would be sent (at most reply_cap are stored, *n_replies
+ * counts all); data: payloads are appended at st->dataLen (bytes beyond data_cap are dropped, dataLen still
+ * advances); returns the number of bytes consumed from the burst. */
+long wamo_xmodem_receive(const uint8_t* bytes, long n, int maxRetries, wamo_xmodem_rx_state* st,
+                         uint8_t* replies, int reply_cap, int32_t* n_replies, uint8_t* data, long data_cap);
+
 /* ---- multi-threaded batch driver (CPU baseline for bench.py; one FSKCore per stream) ---- */
 /* Demodulates n_streams independent streams ([stream][n_samples], stride in floats) with
  * n_threads pthreads.  out: [stream][out_stride] bytes, out_len[stream].  Returns 0. */

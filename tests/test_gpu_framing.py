@@ -144,3 +144,79 @@ def test_large_batch_properties(gpu_wam):
     assert int(np.bitwise_xor.reduce(crc)) == int(np.bitwise_xor.reduce(
         np.array([gpu_wam.CRC16.calculate(d.tobytes()) for d in data[::64]], dtype=np.uint16))) or True
     assert crc[5] == gpu_wam.CRC16.calculate(data[5].tobytes())
+
+
+def _random_session(rng, oracle, n_packets):
+    """A receive session as a list of bursts: in-sequence packets with injected duplicates, corrupted copies
+    (followed by the retransmission, as the sender would after a NAK), junk bytes, split bursts and a final EOT."""
+    bursts, seq = [], 1
+    for _ in range(n_packets):
+        payload = rng.integers(0, 256, int(rng.integers(0, 200)), dtype=np.uint8).tobytes()
+        good = oracle.xmodem_serialize(seq, payload)
+        roll = rng.random()
+        if roll < 0.15:    # bit error somewhere in the packet, then the retransmission
+            bad = bytearray(good)
+            bad[int(rng.integers(1, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+            bursts.append(bytes(bad))
+        elif roll < 0.25:  # sender missed the ACK: previous packet again
+            if seq > 1 or len(bursts):
+                prev = 255 if seq == 1 else seq - 1
+                bursts.append(oracle.xmodem_serialize(prev, b"dup"))
+        elif roll < 0.30:  # a packet from the future
+            bursts.append(oracle.xmodem_serialize((seq + 3) % 255 + 1, b"future"))
+        elif roll < 0.40:  # line noise that contains no SOH / EOT
+            bursts.append(bytes(int(v) for v in rng.integers(5, 256, int(rng.integers(1, 9)))))
+        if rng.random() < 0.3:  # the packet arrives in two pieces (unfinished packet carried over)
+            cut = int(rng.integers(1, len(good)))
+            bursts += [good[:cut], good[cut:]]
+        elif rng.random() < 0.2 and len(bursts):  # glued to the previous burst
+            bursts[-1] = bursts[-1] + good
+        else:
+            bursts.append(good)
+        seq = seq % 255 + 1
+    bursts.append(b"\x04")
+    return bursts
+
+
+@pytest.mark.parametrize("max_retries", [10, 2])
+def test_xmodem_batch_receive_sessions_match_oracle(gpu_wam, oracle, max_retries):
+    rng = np.random.default_rng(77 + max_retries)
+    n = 96
+    sessions = [_random_session(rng, oracle, int(rng.integers(1, 300 if i % 8 == 0 else 20))) for i in range(n)]
+    rx = gpu_wam.XModemBatchReceiver(n, max_retries=max_retries, data_capacity=64 * 1024)
+    want_state, want_pending, want_data = [None] * n, [b""] * n, [b""] * n
+    for step in range(max(len(s) for s in sessions)):
+        bursts = [s[step] if step < len(s) else b"" for s in sessions]
+        got_replies = rx.feed(bursts)
+        for i in range(n):
+            buf = want_pending[i] + bursts[i]
+            st, rep, nrep, consumed, payload = oracle.xmodem_receive(buf, want_state[i], max_retries)
+            want_state[i], want_pending[i] = st, buf[consumed:]
+            want_data[i] += payload
+            assert got_replies[i] == rep, (step, i)
+            assert {k: int(rx.state[k][i]) for k in oracle.RX_STATE_FIELDS} == st, (step, i)
+            assert rx.pending[i] == want_pending[i], (step, i)
+    done = [int(d) for d in rx.state["done"]]
+    assert set(done) <= {1, 2} and 1 in done
+    for i in range(n):
+        assert rx.received(i) == want_data[i]
+        if done[i] == 1 and max_retries == 10:
+            assert int(rx.state["packetsReceived"][i]) >= 1
+
+
+def test_xmodem_batch_receive_reference_cases(gpu_wam, oracle):
+    """The deterministic 'Data Reception' expectations (xmodem.node.test.ts:766-906) through the GPU path."""
+    pk = oracle.xmodem_serialize
+    cases = [
+        (pk(1, bytes([0x48, 0x65, 0x6C, 0x6C, 0x6F])) + b"\x04", bytes([0x48, 0x65, 0x6C, 0x6C, 0x6F]), b"\x06\x06", 1, 0),
+        (pk(1, bytes([1, 2, 3])) + pk(2, bytes([4, 5, 6])) + pk(3, bytes([7, 8])) + b"\x04", bytes(range(1, 9)), b"\x06" * 4, 3, 0),
+        (pk(1, b"\x42\x43") + pk(1, b"\x42\x43") + b"\x04", b"\x42\x43", b"\x06" * 3, 1, 1),
+        (pk(1, b"\x41") + pk(2, b"\x42") + pk(2, b"\x42") + pk(3, b"\x43") + b"\x04", b"\x41\x42\x43", b"\x06" * 5, 3, 1),
+        (pk(2, bytes([4, 5, 6])), b"", b"\x15", 0, 1),
+        (bytes([0x01, 0x01, 0xFE, 0x03, 0x42, 0x43, 0x44, 0xFF, 0xFF]), b"", b"\x15", 1, 1),
+    ]
+    rx = gpu_wam.XModemBatchReceiver(len(cases))
+    replies = rx.feed([c[0] for c in cases])
+    for i, (_, data, rep, received, dropped) in enumerate(cases):
+        assert rx.received(i) == data and replies[i] == rep
+        assert int(rx.state["packetsReceived"][i]) == received and int(rx.state["packetsDropped"][i]) == dropped

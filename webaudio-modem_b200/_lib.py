@@ -63,6 +63,12 @@ class PktResult(C.Structure):
     ]
 
 
+class XmodemRxState(C.Structure):
+    """wam_xmodem_rx_state (include/wam.h)"""
+    _fields_ = [("expectedSequence", C.c_int32), ("retries", C.c_int32), ("done", C.c_int32),
+                ("dataLen", C.c_int32), ("packetsReceived", C.c_int32), ("packetsDropped", C.c_int32)]
+
+
 # every symbol include/wam.h declares: name -> (restype, argtypes)
 _vp, _dp, _fp = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float)
 _u8p, _i32p, _u16p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_uint16)
@@ -98,6 +104,8 @@ SYMBOLS = {
     "wam_xmodem_serialize": (C.c_long, [C.c_int, _u8p, C.c_long, _u8p, C.c_long]),
     "wam_xmodem_batch_check": (C.c_int, [C.c_int, _vp, C.c_long, _vp, _vp, C.c_long, _pktp]),
     "wam_xmodem_batch_check_device": (C.c_int, [_vp, C.c_long, _vp, _vp, C.c_long, _vp, _vp]),
+    "wam_xmodem_batch_receive": (C.c_int, [C.c_int, _vp, C.c_long, _vp, C.c_long, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_long]),
+    "wam_xmodem_batch_receive_device": (C.c_int, [_vp, C.c_long, _vp, C.c_long, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_long, _vp]),
     "wam_crc16_batch": (C.c_int, [C.c_int, _vp, C.c_long, _vp, C.c_long, _vp]),
     "wam_design_butterworth_lowpass": (None, [C.c_double, C.c_double, _dp, _dp]),
     "wam_design_butterworth_highpass": (None, [C.c_double, C.c_double, _dp, _dp]),

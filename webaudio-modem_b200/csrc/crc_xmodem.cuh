@@ -174,4 +174,105 @@ __global__ void __launch_bounds__(128) xmodem_check_kernel(const uint8_t* __rest
   }
 }
 
+struct XmodemRxStateDev {  // same layout as wam_xmodem_rx_state
+  int32_t expectedSequence, retries, done, dataLen, packetsReceived, packetsDropped;
+};
+
+// Receive side of XModemTransport.receiveAllPackets / receiveAndProcessPacket (xmodem.ts:232-321) for one
+// burst of demodulated bytes per stream, receiver state carried between bursts.  One warp per stream: the
+// walk over packets is sequential, but inside it the scan for SOH / EOT is a ballot over 32 bytes at a time,
+// the CRC is the warp-level one above and the payload copy is lane-parallel.
+__global__ void __launch_bounds__(128) xmodem_receive_kernel(const uint8_t* __restrict__ bytes, long stride,
+                                                             const int32_t* __restrict__ len, long n_streams,
+                                                             int max_retries, XmodemRxStateDev* __restrict__ state,
+                                                             uint8_t* __restrict__ replies, int reply_cap,
+                                                             int32_t* __restrict__ n_replies,
+                                                             int32_t* __restrict__ consumed,
+                                                             uint8_t* __restrict__ data, long data_stride) {
+  __shared__ CrcTables tabs;
+  crc_tables_init(tabs);
+  const int lane = threadIdx.x & 31;
+  const long warps_total = (long)gridDim.x * (blockDim.x >> 5);
+  for (long w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_streams; w += warps_total) {
+    const uint8_t* row = bytes + w * stride;
+    const int n = len[w];
+    XmodemRxStateDev st = state[w];
+    uint8_t* rep = replies + w * (long)reply_cap;
+    uint8_t* out = data ? data + w * data_stride : nullptr;
+    int p = 0, nrep = 0;
+    while (!st.done && p < n) {
+      // next byte that is SOH or EOT; everything before it is ignored (xmodem.ts:248-250)
+      int first = -1, first_val = 0;
+      for (int base = p; base < n; base += 32) {
+        const int i = base + lane;
+        const int v = (i < n) ? row[i] : 0;
+        const unsigned m = __ballot_sync(0xffffffffu, i < n && (v == 0x01 || v == 0x04));
+        if (m) {
+          const int src = __ffs(m) - 1;
+          first = base + src;
+          first_val = __shfl_sync(0xffffffffu, v, src);
+          break;
+        }
+      }
+      if (first < 0) { p = n; break; }
+      p = first;
+      if (first_val == 0x04) {  // EOT: final ACK (xmodem.ts:241-244)
+        p++;
+        if (lane == 0 && nrep < reply_cap) rep[nrep] = 0x06;
+        nrep++;
+        st.done = 1;
+        break;
+      }
+      if (p + 4 > n) break;  // header not complete yet: keep the SOH
+      const int seq = row[p + 1], nseq = row[p + 2], plen = row[p + 3];
+      bool error = false;
+      if (seq + nseq != 255) {
+        st.packetsDropped++;
+        error = true;
+      } else {
+        const int prev = st.expectedSequence == 1 ? 255 : st.expectedSequence - 1;  // xmodem.ts:525-530
+        if (seq == st.expectedSequence) {
+          if (p + 4 + plen + 2 > n) break;  // payload not complete yet
+          st.packetsReceived++;
+          const int crc = (row[p + 4 + plen] << 8) | row[p + 4 + plen + 1];
+          if ((int)warp_crc16(tabs, row + p + 4, plen, lane) != crc) {
+            st.packetsDropped++;
+            error = true;
+          } else {
+            if (out)
+              for (int i = lane; i < plen; i += 32)
+                if ((long)st.dataLen + i < data_stride) out[st.dataLen + i] = row[p + 4 + i];
+            st.dataLen += plen;
+            st.expectedSequence = (st.expectedSequence % 255) + 1;
+            st.retries = 0;
+            if (lane == 0 && nrep < reply_cap) rep[nrep] = 0x06;
+            nrep++;
+            p += 4 + plen + 2;
+          }
+        } else if (seq == prev) {  // duplicate: consumed, ACKed, ignored (xmodem.ts:309-314)
+          if (p + 4 + plen + 2 > n) break;
+          st.packetsDropped++;
+          if (lane == 0 && nrep < reply_cap) rep[nrep] = 0x06;
+          nrep++;
+          p += 4 + plen + 2;
+        } else {
+          st.packetsDropped++;
+          error = true;
+        }
+      }
+      if (error) {  // catch block, xmodem.ts:251-260
+        p = n;      // receive.buffer = []
+        if (++st.retries > max_retries) { st.done = 2; break; }
+        if (lane == 0 && nrep < reply_cap) rep[nrep] = 0x15;
+        nrep++;
+      }
+    }
+    if (lane == 0) {
+      state[w] = st;
+      n_replies[w] = nrep;
+      consumed[w] = p;
+    }
+  }
+}
+
 }  // namespace wam

@@ -1078,6 +1078,58 @@ extern "C" int wam_xmodem_batch_check(int device, const uint8_t* bytes, long str
   return WAM_OK;
 }
 
+extern "C" int wam_xmodem_batch_receive_device(const uint8_t* d_bytes, long stride, const int32_t* d_len, long n_streams,
+                                               int max_retries, wam_xmodem_rx_state* d_state, uint8_t* d_replies,
+                                               int reply_cap, int32_t* d_n_replies, int32_t* d_consumed,
+                                               uint8_t* d_data, long data_stride, void* cuda_stream) {
+  if (n_streams < 0 || !d_len || !d_state || !d_n_replies || !d_consumed || (!d_bytes && stride > 0) ||
+      reply_cap < 0 || (reply_cap > 0 && !d_replies) || data_stride < 0 || max_retries < 0)
+    return fail(WAM_E_INVALID, "bad argument");
+  if (n_streams == 0) return WAM_OK;
+  static_assert(sizeof(XmodemRxStateDev) == sizeof(wam_xmodem_rx_state), "layout");
+  const long want_ctas = (n_streams + 3) / 4;
+  xmodem_receive_kernel<<<(unsigned)std::min<long>(want_ctas, 148L * 16), 128, 0, (cudaStream_t)cuda_stream>>>(
+      d_bytes, stride, d_len, n_streams, max_retries, reinterpret_cast<XmodemRxStateDev*>(d_state), d_replies,
+      reply_cap, d_n_replies, d_consumed, d_data, data_stride);
+  CUDA_TRY(cudaGetLastError());
+  return WAM_OK;
+}
+
+extern "C" int wam_xmodem_batch_receive(int device, const uint8_t* bytes, long stride, const int32_t* len, long n_streams,
+                                        int max_retries, wam_xmodem_rx_state* state, uint8_t* replies, int reply_cap,
+                                        int32_t* n_replies, int32_t* consumed, uint8_t* data, long data_stride) {
+  if (n_streams < 0 || !len || !state || !n_replies || !consumed || stride < 0 || (!bytes && stride > 0) ||
+      reply_cap < 0 || (reply_cap > 0 && !replies) || data_stride < 0 || max_retries < 0)
+    return fail(WAM_E_INVALID, "bad argument");
+  int rc = select_device(device);
+  if (rc != WAM_OK) return rc;
+  if (n_streams == 0) return WAM_OK;
+  for (long s = 0; s < n_streams; s++)
+    if (len[s] < 0 || len[s] > stride) return fail(WAM_E_INVALID, "len[s] must be within 0..stride");
+  const size_t ns = (size_t)n_streams;
+  const size_t nb = (size_t)stride * ns, nrep = (size_t)reply_cap * ns, nd = data ? (size_t)data_stride * ns : 0;
+  DevBuf db, dl, ds, dr, dn, dc, dd;
+  if ((rc = db.alloc(nb)) || (rc = dl.alloc(sizeof(int32_t) * ns)) || (rc = ds.alloc(sizeof(wam_xmodem_rx_state) * ns)) ||
+      (rc = dr.alloc(nrep)) || (rc = dn.alloc(sizeof(int32_t) * ns)) || (rc = dc.alloc(sizeof(int32_t) * ns)) ||
+      (rc = dd.alloc(nd)))
+    return rc;
+  if (nb) CUDA_TRY(cudaMemcpy(db.p, bytes, nb, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dl.p, len, sizeof(int32_t) * ns, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(ds.p, state, sizeof(wam_xmodem_rx_state) * ns, cudaMemcpyHostToDevice));
+  if (nd) CUDA_TRY(cudaMemcpy(dd.p, data, nd, cudaMemcpyHostToDevice));  // payloads are appended to what is there
+  if (nrep) CUDA_TRY(cudaMemset(dr.p, 0, nrep));
+  rc = wam_xmodem_batch_receive_device((const uint8_t*)db.p, stride, (const int32_t*)dl.p, n_streams, max_retries,
+                                       (wam_xmodem_rx_state*)ds.p, (uint8_t*)dr.p, reply_cap, (int32_t*)dn.p,
+                                       (int32_t*)dc.p, nd ? (uint8_t*)dd.p : nullptr, data_stride, nullptr);
+  if (rc != WAM_OK) return rc;
+  CUDA_TRY(cudaMemcpy(state, ds.p, sizeof(wam_xmodem_rx_state) * ns, cudaMemcpyDeviceToHost));
+  if (nrep) CUDA_TRY(cudaMemcpy(replies, dr.p, nrep, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(n_replies, dn.p, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(consumed, dc.p, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost));
+  if (nd) CUDA_TRY(cudaMemcpy(data, dd.p, nd, cudaMemcpyDeviceToHost));
+  return WAM_OK;
+}
+
 extern "C" int wam_crc16_batch(int device, const uint8_t* bytes, long stride, const int32_t* len, long n_blocks,
                                uint16_t* crc_out) {
   if (n_blocks < 0 || !len || !crc_out || stride < 0 || (!bytes && stride > 0)) return fail(WAM_E_INVALID, "bad argument");
