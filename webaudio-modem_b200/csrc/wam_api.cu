@@ -14,6 +14,7 @@
 #include "crc_xmodem.cuh"
 #include "filters.cuh"
 #include "fsk_demod.cuh"
+#include "fsk_demod_pipe.cuh"
 #include "fsk_mod.cuh"
 #include "wam_common.cuh"
 
@@ -274,6 +275,7 @@ struct Group {
 
 struct wam_fsk_batch {
   int device = 0;
+  int sm_count = 148;
   long n_streams = 0;
   std::vector<Group> groups;
   std::vector<int32_t> stream_group, stream_local;
@@ -397,6 +399,8 @@ extern "C" int wam_fsk_batch_create(int device, long n_streams, const wam_fsk_co
   wam_fsk_batch* b = new (std::nothrow) wam_fsk_batch();
   if (!b) return fail(WAM_E_NOMEM, "host allocation failed");
   b->device = device;
+  if (cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || b->sm_count < 1)
+    b->sm_count = 148;
   b->n_streams = n_streams;
   b->groups.resize((size_t)n_cfgs);
   for (int i = 0; i < n_cfgs; i++) {
@@ -519,7 +523,15 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
   bool generic = wb || tap || (flags & WAM_BATCH_DEBUG_GENERIC_SM);
   auto flush = [&]() -> int {
     if (L.n_groups == 0) return WAM_OK;
-    if (aligned) { if (generic) launch_demod<true, true>(L, st); else launch_demod<true, false>(L, st); }
+    // Few streams (<= 5 three-warp CTAs per SM): the warp-specialised pipeline (fsk_demod_pipe.cuh) advances a
+    // stream at the longest of the three phase chains instead of their sum.  Many streams: the fused kernel,
+    // whose one-warp CTAs already hide the chains across warps.
+    const bool pipe = !generic && !(flags & WAM_BATCH_NO_PIPELINE) && L.block_begin[L.n_groups] <= 5 * b->sm_count &&
+                      n >= 8 * kTile;
+    if (pipe) {
+      if (aligned) fsk_demod_pipe_kernel<true><<<L.block_begin[L.n_groups], kPipeThreads, 0, st>>>(L);
+      else fsk_demod_pipe_kernel<false><<<L.block_begin[L.n_groups], kPipeThreads, 0, st>>>(L);
+    } else if (aligned) { if (generic) launch_demod<true, true>(L, st); else launch_demod<true, false>(L, st); }
     else         { if (generic) launch_demod<false, true>(L, st); else launch_demod<false, false>(L, st); }
     b->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -591,7 +603,7 @@ extern "C" int wam_fsk_batch_demodulate(wam_fsk_batch* b, float* samples, long s
   CUDA_TRY(cudaSetDevice(b->device));
   b->demodulation_calls += 1;
   b->total_samples += (double)n_samples;
-  flags &= (WAM_BATCH_WRITEBACK_AGC | WAM_BATCH_DEBUG_GENERIC_SM);
+  flags &= (WAM_BATCH_WRITEBACK_AGC | WAM_BATCH_DEBUG_GENERIC_SM | WAM_BATCH_NO_PIPELINE);
 
   // The call is cut into TIME slabs (all streams, samples [t0, t1)): the H2D copy of slab k+1 overlaps
   // the kernel of slab k (copy stream + compute stream, two staging buffers), and every slab launch
@@ -687,7 +699,7 @@ extern "C" int wam_fsk_batch_status(wam_fsk_batch* b, wam_fsk_status* st) {
       s.silenceThreshold = f[(size_t)F_SIL_THR * n + i];
       s.totalSamplesProcessed = b->total_samples;
       s.eodEvents = (double)u[(size_t)U_EOD_EV * n + i];
-      s.errorEvents = 0;
+      s.errorEvents = (double)u[(size_t)U_ERR * n + i];  // device-side error flags (WAM_ERR_*), 0 = none
       s.configuredEvents = b->configured_events;
     }
   }

@@ -75,6 +75,7 @@ def _status_dict(st: L.StatusStruct) -> dict:
         "silenceThreshold": st.silenceThreshold,
         "totalSamplesProcessed": int(st.totalSamplesProcessed),
         "eodEvents": int(st.eodEvents),
+        "errorEvents": int(st.errorEvents),  # device-side error flags (output overflow, pipeline time-out); 0 = none
     }
 
 
@@ -194,7 +195,7 @@ class FSKCore(EventEmitter):
         if not self._h:
             return {"ready": False, "frameStarted": False, "globalSampleCounter": 0, "receivedBitsLength": 0,
                     "byteBufferLength": 0, "demodulationCalls": 0, "syncDetections": 0, "silenceThreshold": 0.01,
-                    "totalSamplesProcessed": 0, "eodEvents": 0}
+                    "totalSamplesProcessed": 0, "eodEvents": 0, "errorEvents": 0}
         return _status_dict(self._status())
 
     def getSignalQuality(self) -> dict:  # fsk.ts:471-479 — the reference returns zeros
