@@ -226,7 +226,7 @@ __device__ __noinline__ double amp_ring_threshold(const float* __restrict__ arin
 template <bool GENERIC>
 __device__ __forceinline__ bool sm_step(A2State& s, BState& b, int bit, double amplitude, uint32_t ring_pos,
                                         bool ring_ready, uint32_t amp_next, uint32_t amp_len, const DemodArgs& a,
-                                        int li, uint8_t* out_row, bool& thr_changed) {
+                                        int li, uint8_t* out_row, bool& thr_changed, uint32_t* ring, long rstride) {
   const FskDerived& d = a.d;
   const long ns = a.n_local;
   // silence / EOD — fsk.ts:285-295
@@ -246,12 +246,11 @@ __device__ __forceinline__ bool sm_step(A2State& s, BState& b, int bit, double a
     // fsk.ts:297-328
     const bool due = d.check_period > 0 && b.gmod == 0u;
     if (due && ring_ready && d.total_bits > 0) {
-      uint32_t* ring = a.sync_ring + li;
       int matched;
       if (!GENERIC || !d.ring_fractional) {
         if ((b.ring_pos & 31u) != 0u)  // flush the register copy of the newest (partial) word
-          ring[(long)((b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns] = b.cur_word;
-        matched = (d.total_bits - d.dspb) - sync_mismatches(ring, ns, ring_pos, d);
+          ring[(long)((b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * rstride] = b.cur_word;
+        matched = (d.total_bits - d.dspb) - sync_mismatches(ring, rstride, ring_pos, d);
       } else {
         matched = sync_matched_fractional(a.f64 + li, ns, ring, d);
       }
@@ -307,7 +306,7 @@ __device__ __forceinline__ bool sm_sample_generic(A2State& s, BState& b, int bit
   b.amp_pos = (b.amp_pos + 1u == (uint32_t)d.amp_phys) ? 0u : b.amp_pos + 1u;
   b.amp_len = min(b.amp_len + 1u, (uint32_t)d.amp_cap);
   bool thr_changed = false;
-  return sm_step<true>(s, b, bit, amplitude, b.ring_pos, ready, b.amp_pos, b.amp_len, a, li, out_row, thr_changed);
+  return sm_step<true>(s, b, bit, amplitude, b.ring_pos, ready, b.amp_pos, b.amp_len, a, li, out_row, thr_changed, ring, ns);
 }
 
 // Event-driven state machine for one tile (integral ring, eod_count > 16).  `bits` holds the hard
@@ -315,10 +314,12 @@ __device__ __forceinline__ bool sm_sample_generic(A2State& s, BState& b, int bit
 // Returns the decimated index at which resetState() ran, or -1.
 __device__ __forceinline__ int sm_tile_events(A2State& s, BState& b, uint32_t bits, const double* __restrict__ amp,
                                               int b_from, int nk, uint32_t pos_t0, uint32_t len_t0, uint32_t slot_t0,
-                                              uint32_t alen_t0, const DemodArgs& a, int li, uint8_t* out_row) {
+                                              uint32_t alen_t0, const DemodArgs& a, int li, uint8_t* out_row,
+                                              uint32_t* ring, long rstride) {
+  // ring / rstride: this stream's bit-packed sync ring (word w at ring[w * rstride]) — the global state array
+  // (a.sync_ring + li, a.n_local) or a shared-memory copy of it
   const FskDerived& d = a.d;
   const long ns = a.n_local;
-  uint32_t* ring = a.sync_ring + li;
   float* aring = a.amp_ring + li;
   const uint32_t wmask = (uint32_t)(d.ring_words - 1);
 
@@ -327,15 +328,15 @@ __device__ __forceinline__ int sm_tile_events(A2State& s, BState& b, uint32_t bi
     const uint32_t p = pos_t0 + (uint32_t)b_from;
     if (b_from > 0) {
       // replay pass: the word holding position p may already have been flushed
-      ring[(long)((b.ring_pos >> 5) & wmask) * ns] = b.cur_word;
-      b.cur_word = ring[(long)((p >> 5) & wmask) * ns];
+      ring[(long)((b.ring_pos >> 5) & wmask) * rstride] = b.cur_word;
+      b.cur_word = ring[(long)((p >> 5) & wmask) * rstride];
     }
     const uint32_t cnt = (uint32_t)(nk - b_from);
     const uint32_t o = p & 31u;
     const uint32_t chunk = (bits >> b_from) & ((1u << cnt) - 1u);
     b.cur_word = (b.cur_word & ((1u << o) - 1u)) | (chunk << o);
     if (o + cnt >= 32u) {
-      ring[(long)((p >> 5) & wmask) * ns] = b.cur_word;
+      ring[(long)((p >> 5) & wmask) * rstride] = b.cur_word;
       b.cur_word = (o + cnt > 32u) ? (chunk >> (32u - o)) : 0u;
     }
     b.ring_pos = pos_t0 + (uint32_t)nk;
@@ -388,7 +389,7 @@ __device__ __forceinline__ int sm_tile_events(A2State& s, BState& b, uint32_t bi
     const uint32_t alen = min(alen_t0 + (uint32_t)k_evt + 1u, (uint32_t)d.amp_cap);
     bool thr_changed = false;
     if (sm_step<false>(s, b, (int)((bits >> k_evt) & 1u), amp[k_evt * 32], pos_k, ready, slot_next, alen, a, li, out_row,
-                thr_changed))
+                thr_changed, ring, rstride))
       return k_evt;
     if (thr_changed) {
       silent = 0u;
@@ -709,7 +710,8 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
         redo = false;
         int k_reset = -1;
         if (fast_sm) {
-          k_reset = sm_tile_events(s, b, bits, pbuf + lane, b_from, nk, pos_t0, len_t0, slot_t0, alen_t0, a, li, out_row);
+          k_reset = sm_tile_events(s, b, bits, pbuf + lane, b_from, nk, pos_t0, len_t0, slot_t0, alen_t0, a, li, out_row,
+                                   a.sync_ring + li, ns);
           if (k_reset < 0 || 2 * (k_reset + 1) >= v_hi) {
             b.ring_len = min(len_t0 + (uint32_t)nk, (uint32_t)d.ring_cap_int);
             const uint32_t sl = slot_t0 + (uint32_t)nk;

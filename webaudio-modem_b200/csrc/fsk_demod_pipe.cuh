@@ -67,7 +67,12 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
   for (int i = 1; i < kMaxGroupsPerLaunch; ++i)
     if (i < L.n_groups && (int)blockIdx.x >= L.block_begin[i]) gi = i;
   const DemodArgs& a = L.g[gi];
-  __shared__ __align__(128) PipeShared sh;
+  extern __shared__ __align__(128) unsigned char pipe_smem[];
+  PipeShared& sh = *reinterpret_cast<PipeShared*>(pipe_smem);
+  // B's copy of the bit-packed sync rings of the CTA's 32 streams, [ring_words][32] (when it fits): the frame
+  // search reads it 4 words at a time per check, and from L2 each of those rounds costs a full memory latency
+  uint32_t* ring_s = reinterpret_cast<uint32_t*>(pipe_smem + sizeof(PipeShared));
+  const bool ring_in_smem = L.pipe_ring_smem != 0;
 
   const int lane = threadIdx.x & 31;
   const int role = threadIdx.x >> 5;
@@ -85,6 +90,13 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
   const FskDerived& d = a.d;
   const long ns = a.n_local;
   const int n_tiles = (int)((a.n + kTile - 1) / kTile);
+#ifdef WAM_PHASE_TIMING
+  const bool timing = a.phase_cycles != nullptr;  // busy SM cycles of each role (waits excluded), per CTA
+#else
+  constexpr bool timing = false;
+#endif
+  unsigned long long busy = 0;
+  const long long clk_begin = timing ? clock64() : 0;
   const int dsc0 = active ? (int)a.u32[(long)U_DSC * ns + li] : 0;  // decimator phase: the same at every tile start
 
   if (role == 0) {
@@ -114,6 +126,7 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
       spins = 0;
       cp_async_wait<kStages - 1>();
       __syncwarp();
+      const long long c0 = timing ? clock64() : 0;
       const float* tile = sh.tiles[t % kStages];
       float* pfb = sh.pf[t % kPipePf];
       const int len = (int)min((long)kTile, a.n - (long)t * kTile);
@@ -141,8 +154,10 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
       __syncwarp();
       __threadfence_block();
       if (lane == 0) sh.a1_done = t + 1;
+      if (timing) busy += (unsigned long long)(clock64() - c0);
     }
     cp_async_wait<0>();
+    if (timing && lane == 0) a.phase_cycles[4ull * blockIdx.x + 0] += busy;
     if (active) {
       double* f = a.f64 + li;
       f[F_GAIN * ns] = a1.gain; f[F_PY1 * ns] = a1.py1; f[F_PY2 * ns] = a1.py2;
@@ -201,6 +216,7 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
       }
       spins = 0;
       __threadfence_block();
+      const long long c0 = timing ? clock64() : 0;
       if (lane_pos == cur) {
         const float* pfbuf = sh.pf[cur % kPipePf];
         double* pbuf = sh.amp[cur % kPipeDec];
@@ -219,6 +235,9 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
           s.lo_c *= f; s.lo_s *= f;
         }
         if (dsc0 == 0 && (v_hi & 1) == 0) {
+          // whole pairs only (two pairs per iteration: the biquad histories rotate in place and two atan2
+          // chains overlap).  Splitting the tile into passes (all I/Q sums, then 16 independent atan2, then the
+          // post-filter chain) was tried and is slower: 300 vs 222 cycles per sample (profiles/r01_notes.md).
 #pragma unroll 2
           for (int k = k_from; k < nk; ++k) {
             double yi0, yq0, yi1, yq1, pp;
@@ -254,7 +273,9 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
       }
       __syncwarp();
       __threadfence_block();
+      if (timing) busy += (unsigned long long)(clock64() - c0);
     }
+    if (timing && lane == 0) a.phase_cycles[4ull * blockIdx.x + 1] += busy;
     if (active) {
       double* f = a.f64 + li;
       f[F_LO_C * ns] = s.lo_c; f[F_LO_S * ns] = s.lo_s;
@@ -284,7 +305,12 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
         const uint32_t w = a.sync_ring[(long)((b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns + li];
         b.cur_word = w & ((1u << (b.ring_pos & 31u)) - 1u);
       }
+      if (ring_in_smem)
+        for (int w = 0; w < d.ring_words; ++w) ring_s[w * 32 + lane] = a.sync_ring[(long)w * ns + li];
     }
+    __syncwarp();
+    uint32_t* ring = ring_in_smem ? ring_s + lane : a.sync_ring + li;
+    const long rstride = ring_in_smem ? 32 : ns;
     uint8_t* out_row = active ? a.out + (long)row * a.out_stride : nullptr;
     A2State dummy;  // reset_state() inside the state machine also clears an A2State: the real one lives in warp 1
     int epoch = 0;
@@ -307,11 +333,12 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
         if (!alive) break;
         spins = 0;
         __threadfence_block();
+        const long long c0 = timing ? clock64() : 0;
         int k_reset = -1;
         if (lane_busy) {
           const uint32_t bits = sh.bits[t % kPipeDec][lane];
           k_reset = sm_tile_events(dummy, b, bits, sh.amp[t % kPipeDec] + lane, b_from, nk, pos_t0, len_t0, slot_t0,
-                                   alen_t0, a, li, out_row);
+                                   alen_t0, a, li, out_row, ring, rstride);
           if (k_reset < 0 || 2 * (k_reset + 1) >= v_hi) {
             // this lane is done with the tile: end-of-tile ring bookkeeping
             b.ring_len = min(len_t0 + (uint32_t)nk, (uint32_t)d.ring_cap_int);
@@ -334,6 +361,7 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
           if (lane == 0) sh.epoch_req = epoch;
           __syncwarp();
         }
+        if (timing) busy += (unsigned long long)(clock64() - c0);
         if (!__any_sync(0xffffffffu, lane_busy)) {
           if (any_reset) {
             // wait for the acknowledgement before moving on, so that the request slots can be reused
@@ -359,10 +387,16 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
       u[U_BITPOS * ns] = (uint32_t)b.bitpos; u[U_CURRENT * ns] = b.current; u[U_SIL_CNT * ns] = b.sil_cnt;
       u[U_RING_POS * ns] = b.ring_pos; u[U_RING_LEN * ns] = b.ring_len;
       u[U_AMP_POS * ns] = b.amp_pos; u[U_AMP_LEN * ns] = b.amp_len;
+      if (ring_in_smem)
+        for (int w = 0; w < d.ring_words; ++w) a.sync_ring[(long)w * ns + li] = ring_s[w * 32 + lane];
       if ((b.ring_pos & 31u) != 0u)
         a.sync_ring[(long)((b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns + li] = b.cur_word;
       a.out_len[row] = b.out_n < a.out_stride ? b.out_n : (int)a.out_stride;
       if (sh.abort_flag) u[(long)U_ERR * ns] |= WAM_ERR_PIPE_TIMEOUT;
+    }
+    if (timing && lane == 0) {
+      a.phase_cycles[4ull * blockIdx.x + 2] += busy;
+      a.phase_cycles[4ull * blockIdx.x + 3] += (unsigned long long)(clock64() - clk_begin);  // B's whole life
     }
   }
 }

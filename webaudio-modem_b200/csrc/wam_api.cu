@@ -276,6 +276,9 @@ struct Group {
 struct wam_fsk_batch {
   int device = 0;
   int sm_count = 148;
+  int pipe_per_sm[2] = {-1, -1};  // resident CTAs per SM of fsk_demod_pipe_kernel<unaligned / aligned>, -1 = not asked yet
+  size_t pipe_smem = 0;
+  int pipe_ring_smem = 0;
   long n_streams = 0;
   std::vector<Group> groups;
   std::vector<int32_t> stream_group, stream_local;
@@ -526,11 +529,27 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
     // Few streams (<= 5 three-warp CTAs per SM): the warp-specialised pipeline (fsk_demod_pipe.cuh) advances a
     // stream at the longest of the three phase chains instead of their sum.  Many streams: the fused kernel,
     // whose one-warp CTAs already hide the chains across warps.
-    const bool pipe = !generic && !(flags & WAM_BATCH_NO_PIPELINE) && L.block_begin[L.n_groups] <= 5 * b->sm_count &&
-                      n >= 8 * kTile;
+    bool pipe = !generic && !(flags & WAM_BATCH_NO_PIPELINE) && n >= 8 * kTile;
     if (pipe) {
-      if (aligned) fsk_demod_pipe_kernel<true><<<L.block_begin[L.n_groups], kPipeThreads, 0, st>>>(L);
-      else fsk_demod_pipe_kernel<false><<<L.block_begin[L.n_groups], kPipeThreads, 0, st>>>(L);
+      const int v = aligned ? 1 : 0;
+      auto kern = aligned ? fsk_demod_pipe_kernel<true> : fsk_demod_pipe_kernel<false>;
+      if (b->pipe_per_sm[v] < 0) {  // once per batch: shared-memory footprint and resident CTAs per SM
+        int ring_words = 0;
+        for (auto& g : b->groups) ring_words = std::max(ring_words, g.d.ring_words);
+        b->pipe_smem = sizeof(PipeShared) + (size_t)ring_words * 32 * sizeof(uint32_t);
+        b->pipe_ring_smem = 1;
+        if (b->pipe_smem > 72 * 1024) { b->pipe_smem = sizeof(PipeShared); b->pipe_ring_smem = 0; }  // very low baud: rings stay in HBM
+        int per_sm = 0;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->pipe_smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPipeThreads, b->pipe_smem));
+        b->pipe_per_sm[v] = per_sm;
+      }
+      L.pipe_ring_smem = b->pipe_ring_smem;
+      // one wave only: beyond it the fused kernel's one-warp CTAs hide the chains better
+      pipe = b->pipe_per_sm[v] > 0 && L.block_begin[L.n_groups] <= b->pipe_per_sm[v] * b->sm_count;
+      if (pipe) kern<<<L.block_begin[L.n_groups], kPipeThreads, b->pipe_smem, st>>>(L);
+    }
+    if (pipe) {
     } else if (aligned) { if (generic) launch_demod<true, true>(L, st); else launch_demod<true, false>(L, st); }
     else         { if (generic) launch_demod<false, true>(L, st); else launch_demod<false, false>(L, st); }
     b->launches++;

@@ -106,6 +106,7 @@ constexpr int kMaxGroupsPerLaunch = 4;
 struct DemodLaunch {
   int n_groups;
   int block_begin[kMaxGroupsPerLaunch + 1];  // first CTA of every group, then the total
+  int pipe_ring_smem;                        // fsk_demod_pipe_kernel: the sync rings are copied to shared memory
   DemodArgs g[kMaxGroupsPerLaunch];
 };
 
