@@ -145,6 +145,17 @@ int wam_fsk_batch_demodulate(wam_fsk_batch* b, float* samples, long stream_strid
 int wam_fsk_batch_demodulate_device(wam_fsk_batch* b, float* d_samples, long stream_stride, long n_samples,
                                     uint8_t* d_out, long out_stride, int32_t* d_out_len, float* d_tap,
                                     void* cuda_stream, uint32_t flags);
+/* Ragged batch: stream s receives demodulateData(samples[s][0 .. n_valid[s])) with 0 <= n_valid[s] <= n_samples;
+ * n_valid[s] < 0 means demodulateData() is NOT called on stream s in this round (state and counters untouched,
+ * out_len[s] = 0).  This is the entry point of a server that multiplexes many independent audio sessions, each
+ * delivering its own block sizes at its own pace (fsk-processor.ts:152-167 calls demodulateData once per
+ * 128-sample render quantum per session).  getStatus().demodulationCalls / totalSamplesProcessed are per stream. */
+int wam_fsk_batch_demodulate_ragged(wam_fsk_batch* b, float* samples, long stream_stride, long n_samples,
+                                    const int32_t* n_valid, uint8_t* out, long out_stride, int32_t* out_len,
+                                    uint32_t flags);
+int wam_fsk_batch_demodulate_ragged_device(wam_fsk_batch* b, float* d_samples, long stream_stride, long n_samples,
+                                           const int32_t* d_n_valid, uint8_t* d_out, long out_stride,
+                                           int32_t* d_out_len, void* cuda_stream, uint32_t flags);
 /* per-stream getStatus(); st: host array [n_streams] */
 int wam_fsk_batch_status(wam_fsk_batch* b, wam_fsk_status* st);
 /* profiling aid: per-phase SM cycle counters of the demodulator (A1, A2, B, other), summed over CTAs */

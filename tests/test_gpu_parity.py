@@ -283,3 +283,62 @@ def test_pipelined_kernel_equals_fused_and_oracle(gpu_wam, oracle, cfg, n, paylo
         for k in ["frameStarted", "globalSampleCounter", "receivedBitsLength", "syncDetections", "eodEvents"]:
             assert float(sa[i][k]) == float(ost[i][k]), (i, k)
     assert sum(s["eodEvents"] for s in sa) > 100 and sum(s["syncDetections"] for s in sa) > 100
+
+
+@pytest.mark.parametrize("force_fused", [False, True])
+def test_ragged_batches_match_one_fskcore_per_stream(gpu_wam, oracle, force_fused):
+    """wam_fsk_batch_demodulate_ragged: every stream receives its own number of samples per round (0, odd counts,
+    the maximum) or is not called at all (n_valid < 0) — the shape of a server multiplexing independent sessions.
+    Each stream must behave like its own FSKCore fed the same sequence of demodulateData() calls: bytes, state and
+    the per-stream debug counters.  Run through the few-stream pipeline and through the fused kernel."""
+    L = gpu_wam._lib
+    flags = L.WAM_BATCH_NO_PIPELINE if force_fused else 0
+    cfg = {}
+    n_streams, total = 40, 48000 * 2
+    rng = np.random.default_rng(99)
+    xs = np.stack([siggen.multi_frame_stream(cfg, total, 20, float(s % 5) * 4 - 2, seed=700 + s, max_gap=2500)[0]
+                   for s in range(n_streams)])
+    cores = []
+    for s in range(n_streams):
+        c = oracle.FSKCore()
+        c.configure(cfg)
+        cores.append(c)
+    b = gpu_wam.FSKBatch(n_streams, cfg)
+    pos = np.zeros(n_streams, dtype=np.int64)
+    want = [b""] * n_streams
+    got = [b""] * n_streams
+    calls = np.zeros(n_streams)
+    for rnd in range(14):
+        n_max = int(rng.choice([128, 1000, 4097, 9000]))
+        nv = np.zeros(n_streams, dtype=np.int32)
+        buf = np.zeros((n_streams, n_max), dtype=np.float32)
+        for s in range(n_streams):
+            kind = rng.integers(0, 6)
+            n = {0: -1, 1: 0, 2: n_max}.get(int(kind), int(rng.integers(1, n_max + 1)))
+            n = min(n, total - int(pos[s]))
+            nv[s] = n
+            if n > 0:
+                buf[s, :n] = xs[s, pos[s]:pos[s] + n]
+            if n >= 0:
+                want[s] += cores[s].demodulateData(xs[s, pos[s]:pos[s] + n].copy())
+                calls[s] += 1
+                pos[s] += n
+        part = b.demodulate_ragged(buf, nv, flags=flags)
+        for s in range(n_streams):
+            if nv[s] < 0:
+                assert part[s] == b""
+            got[s] += part[s]
+    assert got == want
+    assert sum(len(w) for w in want) > 200
+    st = b.status()
+    for s in range(n_streams):
+        o = cores[s].getStatus()
+        assert st[s]["demodulationCalls"] == calls[s] == o["demodulationCalls"], s
+        assert st[s]["totalSamplesProcessed"] == pos[s] == o["totalSamplesProcessed"], s
+        for k in ["frameStarted", "globalSampleCounter", "receivedBitsLength", "syncDetections", "eodEvents"]:
+            assert float(st[s][k]) == float(o[k]), (s, k)
+        assert st[s]["errorEvents"] == 0
+    # an empty round (n_max == 0) is a call with no samples on every stream that takes part
+    part = b.demodulate_ragged(np.zeros((n_streams, 0), dtype=np.float32), np.zeros(n_streams, dtype=np.int32), flags=flags)
+    assert part == [b""] * n_streams
+    assert b.status()[0]["demodulationCalls"] == calls[0] + 1

@@ -523,6 +523,26 @@ __device__ __forceinline__ void stage_tile(float* tile, const DemodArgs& a, cons
   }
 }
 
+// Ragged launches: n_valid[row] is the stream's sample count for the whole call (negative: the stream is not
+// called at all and nothing of it is touched except out_len = 0); this launch covers [offset, offset + a.n).
+__device__ __forceinline__ void ragged_count(const DemodArgs& a, int row, bool& active, long& n_l) {
+  const long v = (long)a.n_valid[row];
+  if (v < 0) {
+    active = false;
+    if (!a.append) a.out_len[row] = 0;
+    return;
+  }
+  const long r = v - a.n_valid_offset;
+  n_l = r < 0 ? 0 : (r < a.n ? r : a.n);
+}
+// per-stream debug counters of ragged calls (fsk.ts:195-196); uniform calls are counted on the host
+__device__ __forceinline__ void ragged_account(const DemodArgs& a, int li, long n_l) {
+  double* f = a.f64 + li;
+  const long ns = a.n_local;
+  if (a.count_call) f[F_RAGGED_CALLS * ns] += 1.0;
+  f[F_RAGGED_TOTAL * ns] += (double)n_l;
+}
+
 // Grid: one warp (32 streams) per CTA, so that 2048 warps spread evenly over 148 SMs.
 // GENERIC = false: the common case (no AGC write-back, no tap, integral sync ring, eod_count > 16) —
 // only the event-driven state machine is compiled in, which keeps the kernel's code footprint small.
@@ -544,10 +564,12 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
 
   const int lane = threadIdx.x;
   const int li = a.l_begin + ((int)blockIdx.x - L.block_begin[gi]) * 32 + lane;
-  const bool active = li < a.l_end;
+  bool active = li < a.l_end;
   int row = -1;
   if (active) row = (a.ids ? a.ids[li] : a.id0 + li) - a.row_base;
-  rows[lane] = row;
+  long n_l = a.n;  // this stream's samples in this launch (ragged launches run the GENERIC variant)
+  if (GENERIC && active && a.n_valid) ragged_count(a, row, active, n_l);
+  rows[lane] = active ? row : -1;
 
   const FskDerived& d = a.d;
   const long ns = a.n_local;
@@ -612,7 +634,8 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
     float* tile = tiles[t % kStages];
     double* pbuf = reinterpret_cast<double*>(tile);  // [k][lane] after A1
     const long t0 = t * kTile;
-    const int len = (int)min((long)kTile, a.n - t0);
+    const int len = GENERIC ? (int)max(0L, min((long)kTile, n_l - t0))  // per lane in ragged launches
+                            : (int)min((long)kTile, a.n - t0);
 
     // ---------------- A1: AGC + pre-filter ----------------
     long long clk0 = timing ? clock64() : 0;
@@ -657,11 +680,11 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
     int b_from = 0;                 // first decimated output B has to consume
     int v_lo = dsc0;                // first virtual sample present
     uint32_t bits = 0u;
-    bool redo = active;
+    bool redo = active && (!GENERIC || len > 0);
     // ring bookkeeping at the start of the tile (event-driven state machine)
     const uint32_t pos_t0 = park_u[10][lane], len_t0 = park_u[11][lane];
     const uint32_t slot_t0 = park_u[12][lane], alen_t0 = park_u[13][lane];
-    if (active) {
+    if (active && (!GENERIC || len > 0)) {
       // renormalise the LO rotation (one Newton step towards |(c, s)| = 1)
       const double m = fma(s.lo_c, s.lo_c, s.lo_s * s.lo_s);
       const double f = fma(-0.5, m, 1.5);
@@ -769,6 +792,7 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
     if (!d.ring_fractional && (b.ring_pos & 31u) != 0u)
       a.sync_ring[(long)((b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns + li] = b.cur_word;
     a.out_len[row] = b.out_n < a.out_stride ? b.out_n : (int)a.out_stride;
+    if (GENERIC && a.n_valid) ragged_account(a, li, n_l);
   }
 }
 

@@ -77,11 +77,22 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
   const int lane = threadIdx.x & 31;
   const int role = threadIdx.x >> 5;
   const int li = a.l_begin + ((int)blockIdx.x - L.block_begin[gi]) * 32 + lane;
-  const bool active = li < a.l_end;
+  bool active = li < a.l_end;
   int row = -1;
   if (active) row = (a.ids ? a.ids[li] : a.id0 + li) - a.row_base;
+  long n_l = a.n;  // this stream's samples in this launch (ragged launches: its own count)
+  if (active && a.n_valid) {
+    const long v = (long)a.n_valid[row];
+    if (v < 0) {  // demodulateData() is not called on this stream
+      active = false;
+      if (role == 2 && !a.append) a.out_len[row] = 0;
+    } else {
+      const long r = v - a.n_valid_offset;
+      n_l = r < 0 ? 0 : (r < a.n ? r : a.n);
+    }
+  }
   if (role == 0) {
-    sh.rows[lane] = row;
+    sh.rows[lane] = active ? row : -1;
     sh.reset_k[lane] = -1;
     if (lane == 0) { sh.a1_done = 0; sh.b_done = 0; sh.epoch_req = 0; sh.reset_tile = 0; sh.abort_flag = 0; sh.a2_pub = 0ull; }
   }
@@ -129,7 +140,7 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
       const long long c0 = timing ? clock64() : 0;
       const float* tile = sh.tiles[t % kStages];
       float* pfb = sh.pf[t % kPipePf];
-      const int len = (int)min((long)kTile, a.n - (long)t * kTile);
+      const int len = (int)max(0L, min((long)kTile, n_l - (long)t * kTile));
       if (active) {
         if (len == kTile) {
 #pragma unroll 1
@@ -220,7 +231,7 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
       if (lane_pos == cur) {
         const float* pfbuf = sh.pf[cur % kPipePf];
         double* pbuf = sh.amp[cur % kPipeDec];
-        const int len = (int)min((long)kTile, a.n - (long)cur * kTile);
+        const int len = (int)max(0L, min((long)kTile, n_l - (long)cur * kTile));
         const int v_hi = dsc0 + len;
         const int nk = v_hi >> 1;
         const int k_from = lane_kfrom;
@@ -228,7 +239,7 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
         uint32_t bits = 0u;
         if (k_from > 0) {
           bits = sh.bits[cur % kPipeDec][lane] & ((1u << k_from) - 1u);
-        } else {
+        } else if (len > 0) {
           // renormalise the LO rotation (one Newton step towards |(c, s)| = 1)
           const double m = fma(s.lo_c, s.lo_c, s.lo_s * s.lo_s);
           const double f = fma(-0.5, m, 1.5);
@@ -283,7 +294,7 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
       f[F_QX1 * ns] = s.qx1; f[F_QX2 * ns] = s.qx2; f[F_QY1 * ns] = s.qy1; f[F_QY2 * ns] = s.qy2;
       f[F_OX1 * ns] = s.ox1; f[F_OX2 * ns] = s.ox2; f[F_OY1 * ns] = s.oy1; f[F_OY2 * ns] = s.oy2;
       f[F_LAST_PHASE * ns] = s.last_phase; f[F_IACC * ns] = s.iacc; f[F_QACC * ns] = s.qacc;
-      a.u32[(long)U_DSC * ns + li] = (uint32_t)((dsc0 + a.n) & 1);
+      a.u32[(long)U_DSC * ns + li] = (uint32_t)((dsc0 + n_l) & 1);
     }
   } else {
     // =========================== B: decimated-rate state machine ===========================
@@ -317,12 +328,12 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
     unsigned spins = 0;
     bool alive = true;
     for (int t = 0; t < n_tiles && alive; ++t) {
-      const int len = (int)min((long)kTile, a.n - (long)t * kTile);
+      const int len = (int)max(0L, min((long)kTile, n_l - (long)t * kTile));
       const int v_hi = dsc0 + len;
       const int nk = v_hi >> 1;
       const uint32_t pos_t0 = b.ring_pos, len_t0 = b.ring_len, slot_t0 = b.amp_pos, alen_t0 = b.amp_len;
       int b_from = 0;
-      bool lane_busy = active;
+      bool lane_busy = active && len > 0;
       for (;;) {
         // tile t published by A2 for the current epoch?
         for (;;) {
@@ -392,6 +403,7 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
       if ((b.ring_pos & 31u) != 0u)
         a.sync_ring[(long)((b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns + li] = b.cur_word;
       a.out_len[row] = b.out_n < a.out_stride ? b.out_n : (int)a.out_stride;
+      if (a.n_valid) ragged_account(a, li, n_l);
       if (sh.abort_flag) u[(long)U_ERR * ns] |= WAM_ERR_PIPE_TIMEOUT;
     }
     if (timing && lane == 0) {

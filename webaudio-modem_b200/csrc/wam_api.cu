@@ -276,6 +276,8 @@ struct Group {
 struct wam_fsk_batch {
   int device = 0;
   int sm_count = 148;
+  int32_t* stage_nvalid = nullptr;
+  size_t stage_nvalid_bytes = 0;
   int pipe_per_sm[2] = {-1, -1};  // resident CTAs per SM of fsk_demod_pipe_kernel<unaligned / aligned>, -1 = not asked yet
   size_t pipe_smem = 0;
   int pipe_ring_smem = 0;
@@ -383,6 +385,7 @@ static void free_batch(wam_fsk_batch* b) {
     cudaFree(b->stage_samples[i]); cudaFree(b->stage_out[i]); cudaFree(b->stage_len[i]);
   }
   cudaFree(b->phase_cycles);
+  cudaFree(b->stage_nvalid);
   cudaFree(b->mod_prefix); cudaFree(b->mod_data); cudaFree(b->mod_out); cudaFree(b->mod_len);
   delete b;
 }
@@ -479,7 +482,8 @@ extern "C" int wam_fsk_batch_reset(wam_fsk_batch* b) {
   CUDA_TRY(cudaSetDevice(b->device));
   CUDA_TRY(cudaDeviceSynchronize());
   static const int f_zero[] = {F_LO_S, F_IX1, F_IX2, F_IY1, F_IY2, F_QX1, F_QX2, F_QY1, F_QY2, F_OX1, F_OX2,
-                               F_OY1, F_OY2, F_LAST_PHASE, F_IACC, F_QACC, F_RING_WI, F_RING_RI, F_RING_LEN};
+                               F_OY1, F_OY2, F_LAST_PHASE, F_IACC, F_QACC, F_RING_WI, F_RING_RI, F_RING_LEN,
+                               F_RAGGED_CALLS, F_RAGGED_TOTAL};
   static const int u_zero[] = {U_DSC, U_GSC, U_GMOD, U_BSC, U_NEXT_IDX, U_BIT_ACC, U_BIT_CNT, U_STARTED, U_BITPOS,
                                U_CURRENT, U_SIL_CNT, U_RING_POS, U_RING_LEN, U_SYNC_DET};
   for (auto& g : b->groups) {
@@ -517,12 +521,14 @@ static void launch_demod(const DemodLaunch& L, cudaStream_t st) {
 // kMaxGroupsPerLaunch per launch) so their one-warp CTAs share the SMs.
 static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base, float* d_samples, long stride, long n,
                               uint8_t* d_out, long out_stride, int32_t* d_out_len, float* d_tap, uint32_t flags,
-                              cudaStream_t st, bool append = false) {
+                              cudaStream_t st, bool append = false, const int32_t* d_n_valid = nullptr,
+                              long n_valid_offset = 0, bool count_call = true) {
   const bool aligned = ((reinterpret_cast<uintptr_t>(d_samples) & 15) == 0) && (stride % 4 == 0);
   const bool wb = (flags & WAM_BATCH_WRITEBACK_AGC) != 0;
   const bool tap = (flags & WAM_BATCH_TAP_PREFILTER) != 0 && d_tap != nullptr;
   DemodLaunch L;
   memset(&L, 0, sizeof(L));
+  const bool ragged = d_n_valid != nullptr;
   bool generic = wb || tap || (flags & WAM_BATCH_DEBUG_GENERIC_SM);
   auto flush = [&]() -> int {
     if (L.n_groups == 0) return WAM_OK;
@@ -550,8 +556,8 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
       if (pipe) kern<<<L.block_begin[L.n_groups], kPipeThreads, b->pipe_smem, st>>>(L);
     }
     if (pipe) {
-    } else if (aligned) { if (generic) launch_demod<true, true>(L, st); else launch_demod<true, false>(L, st); }
-    else         { if (generic) launch_demod<false, true>(L, st); else launch_demod<false, false>(L, st); }
+    } else if (aligned) { if (generic || ragged) launch_demod<true, true>(L, st); else launch_demod<true, false>(L, st); }
+    else         { if (generic || ragged) launch_demod<false, true>(L, st); else launch_demod<false, false>(L, st); }
     b->launches++;
     CUDA_TRY(cudaGetLastError());
     memset(&L, 0, sizeof(L));
@@ -577,6 +583,7 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
     if (g.d.ring_fractional || g.d.eod_count <= 16) generic = true;  // needs the per-sample state machine
     a.force_generic = (flags & WAM_BATCH_DEBUG_GENERIC_SM) ? 1 : 0;
     a.append = append ? 1 : 0;
+    a.n_valid = d_n_valid; a.n_valid_offset = n_valid_offset; a.count_call = count_call ? 1 : 0;
     a.phase_cycles = b->phase_cycles;
     L.block_begin[L.n_groups + 1] = L.block_begin[L.n_groups] + (int)((hi - lo + 31) / 32);
     L.n_groups++;
@@ -588,18 +595,35 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
   return flush();
 }
 
+static int demodulate_device_impl(wam_fsk_batch* b, float* d_samples, long stream_stride, long n_samples,
+                                  const int32_t* d_n_valid, bool ragged, uint8_t* d_out, long out_stride,
+                                  int32_t* d_out_len, float* d_tap, void* cuda_stream, uint32_t flags) {
+  if (!b) return fail(WAM_E_INVALID, "batch is NULL");
+  if (n_samples < 0 || stream_stride < n_samples || out_stride < 0 || !d_out_len || (!d_samples && n_samples > 0) ||
+      (!d_out && out_stride > 0) || (ragged && !d_n_valid))
+    return fail(WAM_E_INVALID, "bad buffer description");
+  CUDA_TRY(cudaSetDevice(b->device));
+  if (!ragged) {  // every stream receives the same call: counted once on the host (fsk.ts:195-196)
+    b->demodulation_calls += 1;
+    b->total_samples += (double)n_samples;
+  }
+  return launch_demod_range(b, 0, b->n_streams, 0, d_samples, stream_stride, n_samples, d_out, out_stride, d_out_len,
+                            d_tap, flags, (cudaStream_t)cuda_stream, false, ragged ? d_n_valid : nullptr, 0, true);
+}
+
 extern "C" int wam_fsk_batch_demodulate_device(wam_fsk_batch* b, float* d_samples, long stream_stride, long n_samples,
                                                uint8_t* d_out, long out_stride, int32_t* d_out_len, float* d_tap,
                                                void* cuda_stream, uint32_t flags) {
-  if (!b) return fail(WAM_E_INVALID, "batch is NULL");
-  if (n_samples < 0 || stream_stride < n_samples || out_stride < 0 || !d_out_len || (!d_samples && n_samples > 0) ||
-      (!d_out && out_stride > 0))
-    return fail(WAM_E_INVALID, "bad buffer description");
-  CUDA_TRY(cudaSetDevice(b->device));
-  b->demodulation_calls += 1;
-  b->total_samples += (double)n_samples;
-  return launch_demod_range(b, 0, b->n_streams, 0, d_samples, stream_stride, n_samples, d_out, out_stride, d_out_len,
-                            d_tap, flags, (cudaStream_t)cuda_stream);
+  return demodulate_device_impl(b, d_samples, stream_stride, n_samples, nullptr, false, d_out, out_stride, d_out_len,
+                                d_tap, cuda_stream, flags);
+}
+
+extern "C" int wam_fsk_batch_demodulate_ragged_device(wam_fsk_batch* b, float* d_samples, long stream_stride,
+                                                      long n_samples, const int32_t* d_n_valid, uint8_t* d_out,
+                                                      long out_stride, int32_t* d_out_len, void* cuda_stream,
+                                                      uint32_t flags) {
+  return demodulate_device_impl(b, d_samples, stream_stride, n_samples, d_n_valid, true, d_out, out_stride, d_out_len,
+                                nullptr, cuda_stream, flags & ~(uint32_t)WAM_BATCH_TAP_PREFILTER);
 }
 
 static int ensure(void** p, size_t* cur, size_t need) {
@@ -613,15 +637,27 @@ static int ensure(void** p, size_t* cur, size_t need) {
   return WAM_OK;
 }
 
-extern "C" int wam_fsk_batch_demodulate(wam_fsk_batch* b, float* samples, long stream_stride, long n_samples,
-                                        uint8_t* out, long out_stride, int32_t* out_len, uint32_t flags) {
+static int demodulate_host_impl(wam_fsk_batch* b, float* samples, long stream_stride, long n_samples,
+                                const int32_t* n_valid, bool ragged, uint8_t* out, long out_stride, int32_t* out_len,
+                                uint32_t flags) {
   if (!b) return fail(WAM_E_INVALID, "batch is NULL");
   if (n_samples < 0 || stream_stride < n_samples || out_stride < 0 || !out_len || (!samples && n_samples > 0) ||
-      (!out && out_stride > 0))
+      (!out && out_stride > 0) || (ragged && !n_valid))
     return fail(WAM_E_INVALID, "bad buffer description");
   CUDA_TRY(cudaSetDevice(b->device));
-  b->demodulation_calls += 1;
-  b->total_samples += (double)n_samples;
+  const int32_t* d_n_valid = nullptr;
+  if (ragged) {
+    for (long s = 0; s < b->n_streams; s++)
+      if (n_valid[s] > n_samples) return fail(WAM_E_INVALID, "n_valid[s] must not exceed n_samples");
+    int rc = ensure((void**)&b->stage_nvalid, &b->stage_nvalid_bytes, sizeof(int32_t) * (size_t)b->n_streams);
+    if (rc != WAM_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(b->stage_nvalid, n_valid, sizeof(int32_t) * (size_t)b->n_streams, cudaMemcpyHostToDevice,
+                             b->streams[1]));
+    d_n_valid = b->stage_nvalid;
+  } else {
+    b->demodulation_calls += 1;
+    b->total_samples += (double)n_samples;
+  }
   flags &= (WAM_BATCH_WRITEBACK_AGC | WAM_BATCH_DEBUG_GENERIC_SM | WAM_BATCH_NO_PIPELINE);
 
   // The call is cut into TIME slabs (all streams, samples [t0, t1)): the H2D copy of slab k+1 overlaps
@@ -678,7 +714,7 @@ extern "C" int wam_fsk_batch_demodulate(wam_fsk_batch* b, float* samples, long s
     CUDA_TRY(cudaEventRecord(b->ev_copied[k], copy_st));
     CUDA_TRY(cudaStreamWaitEvent(comp_st, b->ev_copied[k], 0));
     int rc = launch_demod_range(b, 0, b->n_streams, 0, b->stage_samples[k], dstride, len, b->stage_out[0], out_stride,
-                                b->stage_len[0], nullptr, flags, comp_st, /*append=*/true);
+                                b->stage_len[0], nullptr, flags, comp_st, /*append=*/true, d_n_valid, t0, nslab == 0);
     if (rc != WAM_OK) return rc;
     if (wb && len > 0)
       CUDA_TRY(cudaMemcpy2DAsync(samples + t0, sizeof(float) * (size_t)stream_stride, b->stage_samples[k],
@@ -693,6 +729,17 @@ extern "C" int wam_fsk_batch_demodulate(wam_fsk_batch* b, float* samples, long s
   CUDA_TRY(cudaStreamSynchronize(copy_st));
   CUDA_TRY(cudaStreamSynchronize(comp_st));
   return WAM_OK;
+}
+
+extern "C" int wam_fsk_batch_demodulate(wam_fsk_batch* b, float* samples, long stream_stride, long n_samples,
+                                        uint8_t* out, long out_stride, int32_t* out_len, uint32_t flags) {
+  return demodulate_host_impl(b, samples, stream_stride, n_samples, nullptr, false, out, out_stride, out_len, flags);
+}
+
+extern "C" int wam_fsk_batch_demodulate_ragged(wam_fsk_batch* b, float* samples, long stream_stride, long n_samples,
+                                               const int32_t* n_valid, uint8_t* out, long out_stride, int32_t* out_len,
+                                               uint32_t flags) {
+  return demodulate_host_impl(b, samples, stream_stride, n_samples, n_valid, true, out, out_stride, out_len, flags);
 }
 
 extern "C" int wam_fsk_batch_status(wam_fsk_batch* b, wam_fsk_status* st) {
@@ -713,10 +760,10 @@ extern "C" int wam_fsk_batch_status(wam_fsk_batch* b, wam_fsk_status* st) {
       s.globalSampleCounter = (double)u[(size_t)U_GSC * n + i];
       s.receivedBitsLength = g.d.ring_fractional ? f[(size_t)F_RING_LEN * n + i] : (double)u[(size_t)U_RING_LEN * n + i];
       s.byteBufferLength = 0;
-      s.demodulationCalls = b->demodulation_calls;
+      s.demodulationCalls = b->demodulation_calls + f[(size_t)F_RAGGED_CALLS * n + i];
       s.syncDetections = (double)u[(size_t)U_SYNC_DET * n + i];
       s.silenceThreshold = f[(size_t)F_SIL_THR * n + i];
-      s.totalSamplesProcessed = b->total_samples;
+      s.totalSamplesProcessed = b->total_samples + f[(size_t)F_RAGGED_TOTAL * n + i];
       s.eodEvents = (double)u[(size_t)U_EOD_EV * n + i];
       s.errorEvents = (double)u[(size_t)U_ERR * n + i];  // device-side error flags (WAM_ERR_*), 0 = none
       s.configuredEvents = b->configured_events;

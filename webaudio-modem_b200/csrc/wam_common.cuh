@@ -65,6 +65,7 @@ enum F64Field {
   F_IX1, F_IX2, F_IY1, F_IY2, F_QX1, F_QX2, F_QY1, F_QY2,
   F_OX1, F_OX2, F_OY1, F_OY2, F_LAST_PHASE, F_IACC, F_QACC, F_SIL_THR,
   F_RING_WI, F_RING_RI, F_RING_LEN,
+  F_RAGGED_CALLS, F_RAGGED_TOTAL,  // demodulateData() calls / samples received through ragged launches (per stream)
   F64_COUNT
 };
 enum U32Field {
@@ -89,7 +90,10 @@ struct DemodArgs {
   // data
   float* samples;       // [rows][stride]
   long stride;
-  long n;               // samples per stream this call
+  long n;               // samples per stream this call (ragged launches: the maximum)
+  const int32_t* n_valid;  // nullable [rows]: stream's own sample count for the whole call, < 0 = stream not called
+  long n_valid_offset;     // samples of the call consumed by earlier slabs: this launch sees n_valid[row] - offset
+  int count_call;          // ragged launches: this launch is the first slab of a call (debug.demodulationCalls++)
   uint8_t* out;         // [rows][out_stride]
   long out_stride;
   int32_t* out_len;     // [rows]

@@ -268,6 +268,22 @@ class FSKBatch:
             (L.WAM_BATCH_WRITEBACK_AGC if writeback_agc else 0) | flags))
         return out, out_len
 
+    def demodulate_ragged(self, samples: np.ndarray, n_valid, flags: int = 0) -> list[bytes]:
+        """samples float32 [n_streams, n_max]; stream s receives demodulateData(samples[s, :n_valid[s]]), a negative
+        n_valid[s] means the stream is not called in this round.  Returns the bytes completed per stream."""
+        assert samples.dtype == np.float32 and samples.ndim == 2 and samples.shape[0] == self.n_streams
+        assert samples.strides[1] == 4 or samples.shape[1] == 0
+        n = samples.shape[1]
+        nv = np.ascontiguousarray(n_valid, dtype=np.int32)
+        assert nv.shape == (self.n_streams,)
+        cap = self.out_capacity(n)
+        out = np.zeros((self.n_streams, cap), dtype=np.uint8)
+        out_len = np.zeros(self.n_streams, dtype=np.int32)
+        L.check(self._lib.wam_fsk_batch_demodulate_ragged(
+            self._h, samples.ctypes.data if n else None, max(samples.strides[0] // 4, n), n, nv.ctypes.data, out.ctypes.data, cap,
+            out_len.ctypes.data, flags))
+        return [bytes(out[i, : out_len[i]]) for i in range(self.n_streams)]
+
     def demodulate_bytes(self, samples: np.ndarray, writeback_agc: bool = False, flags: int = 0) -> list[bytes]:
         out, out_len = self.demodulate(samples, writeback_agc, flags)
         return [bytes(out[i, : out_len[i]]) for i in range(self.n_streams)]
