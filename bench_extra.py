@@ -76,9 +76,40 @@ def bench_frames(n=1_000_000):
     line("xmodem_check_kernel", "Mpackets/s", n, ms, n * (134 + 28.0), {"workload": f"{n} packets of 134 bytes (128-byte payload)"})
 
 
+def bench_mux(n_sessions=4096, block=128, ticks=200):
+    """Session multiplexer (wam_fsk_mux_*): every session pushes one 128-sample render quantum per tick
+    (FSKProcessor.process(), 2.67 ms of audio at 48 kHz), one flush per tick = H2D + one ragged batch + D2H."""
+    import time
+    rng = np.random.default_rng(7)
+    mux = wam.FSKSessionMux(n_sessions, {}, max_block=block)
+    x = (rng.standard_normal((n_sessions, block)) * 0.1).astype(np.float32)
+    lib_ = wam.lib()
+    push = lib_.wam_fsk_mux_push
+    t_push = t_flush = 0.0
+    for t in range(ticks + 20):
+        t0 = time.perf_counter()
+        for s in range(0, n_sessions):
+            push(mux._h, s, x[s].ctypes.data, block)
+        t1 = time.perf_counter()
+        mux.flush_raw()
+        t2 = time.perf_counter()
+        if t >= 20:
+            t_push += t1 - t0
+            t_flush += t2 - t1
+    ms_flush = 1e3 * t_flush / ticks
+    d = {"kernel": "wam_fsk_mux_flush (H2D + ragged demodulate + D2H)", "n_sessions": n_sessions, "block": block,
+         "ms_per_flush": ms_flush, "value": n_sessions * block / (ms_flush * 1e-3) / 1e6, "unit": "Msamples/s",
+         "audio_ms_per_tick": 1e3 * block / 48000.0, "realtime_factor": (1e3 * block / 48000.0) / ms_flush,
+         "ms_per_tick_pushes_python_loop": 1e3 * t_push / ticks}
+    print(json.dumps(d), flush=True)
+    mux.close()
+
+
 def main():
     bench_modulate()
     bench_frames()
+    bench_mux(4096)
+    bench_mux(32768)
 
 
 if __name__ == "__main__":

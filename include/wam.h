@@ -156,6 +156,21 @@ int wam_fsk_batch_demodulate_ragged(wam_fsk_batch* b, float* samples, long strea
 int wam_fsk_batch_demodulate_ragged_device(wam_fsk_batch* b, float* d_samples, long stream_stride, long n_samples,
                                            const int32_t* d_n_valid, uint8_t* d_out, long out_stride,
                                            int32_t* d_out_len, void* cuda_stream, uint32_t flags);
+/* Session multiplexer: the host adapter for many concurrent block-wise callers.  In the reference every audio
+ * session owns an FSKCore and FSKProcessor.process() hands it one 128-sample render quantum at a time
+ * (fsk-processor.ts:152-167, :296-322).  Here n_sessions such callers push their blocks into pinned staging
+ * (wam_fsk_mux_push, up to max_block samples per session between flushes) and one wam_fsk_mux_flush runs a single
+ * ragged batch over the sessions that pushed: one flush = one demodulateData() call per such session over what it
+ * pushed; sessions that pushed nothing are not called.  Not re-entrant: push/flush from one thread (or lock). */
+typedef struct wam_fsk_mux wam_fsk_mux;
+int wam_fsk_mux_create(int device, long n_sessions, const wam_fsk_config* cfgs, int n_cfgs, const int32_t* cfg_index,
+                       long max_block, wam_fsk_mux** out);
+int wam_fsk_mux_destroy(wam_fsk_mux* m);
+int wam_fsk_mux_push(wam_fsk_mux* m, long session, const float* samples, long n);
+long wam_fsk_mux_pending(wam_fsk_mux* m, long session);
+long wam_fsk_mux_out_capacity(wam_fsk_mux* m);   /* bytes one flush can produce per session at most */
+int wam_fsk_mux_flush(wam_fsk_mux* m, uint8_t* out, long out_stride, int32_t* out_len);
+wam_fsk_batch* wam_fsk_mux_batch(wam_fsk_mux* m); /* the sessions' FSKCore instances (status, reset); owned by the mux */
 /* per-stream getStatus(); st: host array [n_streams] */
 int wam_fsk_batch_status(wam_fsk_batch* b, wam_fsk_status* st);
 /* profiling aid: per-phase SM cycle counters of the demodulator (A1, A2, B, other), summed over CTAs */

@@ -342,3 +342,51 @@ def test_ragged_batches_match_one_fskcore_per_stream(gpu_wam, oracle, force_fuse
     part = b.demodulate_ragged(np.zeros((n_streams, 0), dtype=np.float32), np.zeros(n_streams, dtype=np.int32), flags=flags)
     assert part == [b""] * n_streams
     assert b.status()[0]["demodulationCalls"] == calls[0] + 1
+
+
+def test_session_mux_matches_one_fskcore_per_session(gpu_wam, oracle):
+    """wam_fsk_mux_*: sessions deliver 128-sample render quanta at their own pace (every tick, every other tick,
+    two quanta per tick, pauses); one flush per tick.  Every session must decode exactly what its own FSKCore decodes
+    when it is fed the same samples (one demodulateData() per flush over what the session pushed)."""
+    cfgs = [{}, siggen.V21_CH2]
+    n_sessions, total = 24, 48000
+    idx = np.array([s % 2 for s in range(n_sessions)], dtype=np.int32)
+    xs = [siggen.multi_frame_stream(cfgs[idx[s]], total, 8 if idx[s] == 0 else 3, 12.0, seed=300 + s, max_gap=1500)[0]
+          for s in range(n_sessions)]
+    cores = []
+    for s in range(n_sessions):
+        c = oracle.FSKCore()
+        c.configure(cfgs[idx[s]])
+        cores.append(c)
+    mux = gpu_wam.FSKSessionMux(n_sessions, cfgs, idx, max_block=256)
+    pos = [0] * n_sessions
+    want, got = [b""] * n_sessions, [b""] * n_sessions
+    tick = 0
+    while min(pos) < total and tick < 2000:
+        for s in range(n_sessions):
+            quanta = {0: 1, 1: (tick + s) % 2, 2: 2, 3: 0 if (tick // 7) % 2 else 1}[s % 4]
+            n_call = 0
+            for _ in range(quanta):
+                n = min(128, total - pos[s])
+                if n <= 0:
+                    break
+                mux.push(s, xs[s][pos[s]:pos[s] + n])
+                pos[s] += n
+                n_call += n
+            if n_call:
+                want[s] += cores[s].demodulateData(xs[s][pos[s] - n_call:pos[s]].copy())
+        assert mux.pending(2) in (0, 128, 256)
+        part = mux.flush()
+        got = [g + p for g, p in zip(got, part)]
+        tick += 1
+    assert got == want
+    assert sum(len(w) for w in want) > 50
+    st = mux.status()
+    for s in range(n_sessions):
+        o = cores[s].getStatus()
+        for k in ["frameStarted", "globalSampleCounter", "syncDetections", "eodEvents", "demodulationCalls", "totalSamplesProcessed"]:
+            assert float(st[s][k]) == float(o[k]), (s, k)
+    with pytest.raises(gpu_wam.WamError):
+        for _ in range(3):
+            mux.push(0, np.zeros(128, dtype=np.float32))  # more than max_block between flushes
+    mux.close()

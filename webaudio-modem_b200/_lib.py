@@ -98,6 +98,13 @@ SYMBOLS = {
     "wam_fsk_batch_demodulate_device": (C.c_int, [_vp, _vp, C.c_long, C.c_long, _vp, C.c_long, _vp, _vp, _vp, C.c_uint32]),
     "wam_fsk_batch_demodulate_ragged": (C.c_int, [_vp, _vp, C.c_long, C.c_long, _vp, _vp, C.c_long, _vp, C.c_uint32]),
     "wam_fsk_batch_demodulate_ragged_device": (C.c_int, [_vp, _vp, C.c_long, C.c_long, _vp, _vp, C.c_long, _vp, _vp, C.c_uint32]),
+    "wam_fsk_mux_create": (C.c_int, [C.c_int, C.c_long, _cfgp, C.c_int, _i32p, C.c_long, C.POINTER(_vp)]),
+    "wam_fsk_mux_destroy": (C.c_int, [_vp]),
+    "wam_fsk_mux_push": (C.c_int, [_vp, C.c_long, _vp, C.c_long]),
+    "wam_fsk_mux_pending": (C.c_long, [_vp, C.c_long]),
+    "wam_fsk_mux_out_capacity": (C.c_long, [_vp]),
+    "wam_fsk_mux_flush": (C.c_int, [_vp, _vp, C.c_long, _vp]),
+    "wam_fsk_mux_batch": (_vp, [_vp]),
     "wam_fsk_batch_status": (C.c_int, [_vp, _stp]),
     "wam_fsk_batch_launch_count": (C.c_long, [_vp]),
     "wam_fsk_batch_debug_phase_cycles": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_long]),

@@ -1290,6 +1290,104 @@ extern "C" int wam_debug_fastmath(int device, const double* y, const double* x, 
   return WAM_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// session multiplexer: many independent block-wise callers -> one ragged batch per flush
+// ------------------------------------------------------------------------------------------
+struct wam_fsk_mux {
+  wam_fsk_batch* b = nullptr;
+  long n_sessions = 0, max_block = 0, out_cap = 0;
+  float* h_samples = nullptr;   // pinned [n_sessions][max_block]: blocks pushed since the last flush
+  int32_t* h_pending = nullptr; // pinned [n_sessions]: samples pending per session (0 = nothing pushed)
+  int32_t* h_nvalid = nullptr;  // pinned [n_sessions]: n_valid of the flush in flight
+  uint8_t* h_out = nullptr;     // pinned [n_sessions][out_cap]
+  int32_t* h_out_len = nullptr; // pinned [n_sessions]
+  double flushes = 0, blocks = 0;
+};
+
+extern "C" int wam_fsk_mux_destroy(wam_fsk_mux* m) {
+  if (!m) return WAM_OK;
+  if (m->b) cudaSetDevice(m->b->device);
+  cudaFreeHost(m->h_samples); cudaFreeHost(m->h_pending); cudaFreeHost(m->h_nvalid);
+  cudaFreeHost(m->h_out); cudaFreeHost(m->h_out_len);
+  free_batch(m->b);
+  delete m;
+  return WAM_OK;
+}
+
+extern "C" int wam_fsk_mux_create(int device, long n_sessions, const wam_fsk_config* cfgs, int n_cfgs,
+                                  const int32_t* cfg_index, long max_block, wam_fsk_mux** out) {
+  if (!out) return fail(WAM_E_INVALID, "out is NULL");
+  *out = nullptr;
+  if (n_sessions <= 0 || max_block <= 0) return fail(WAM_E_INVALID, "n_sessions and max_block must be positive");
+  wam_fsk_mux* m = new (std::nothrow) wam_fsk_mux();
+  if (!m) return fail(WAM_E_NOMEM, "host allocation failed");
+  int rc = wam_fsk_batch_create(device, n_sessions, cfgs, n_cfgs, cfg_index, &m->b);
+  if (rc != WAM_OK) { delete m; return rc; }
+  m->n_sessions = n_sessions;
+  m->max_block = (max_block + 3) / 4 * 4;
+  m->out_cap = wam_fsk_batch_out_capacity(m->b, m->max_block);
+  const size_t ns = (size_t)n_sessions;
+  cudaError_t e = cudaMallocHost(&m->h_samples, sizeof(float) * ns * (size_t)m->max_block);
+  if (e == cudaSuccess) e = cudaMallocHost(&m->h_pending, sizeof(int32_t) * ns);
+  if (e == cudaSuccess) e = cudaMallocHost(&m->h_nvalid, sizeof(int32_t) * ns);
+  if (e == cudaSuccess) e = cudaMallocHost(&m->h_out, ns * (size_t)m->out_cap);
+  if (e == cudaSuccess) e = cudaMallocHost(&m->h_out_len, sizeof(int32_t) * ns);
+  if (e != cudaSuccess) {
+    wam_fsk_mux_destroy(m);
+    return fail(WAM_E_NOMEM, std::string("pinned allocation: ") + cudaGetErrorString(e));
+  }
+  memset(m->h_pending, 0, sizeof(int32_t) * ns);
+  *out = m;
+  return WAM_OK;
+}
+
+extern "C" int wam_fsk_mux_push(wam_fsk_mux* m, long session, const float* samples, long n) {
+  if (!m || session < 0 || session >= m->n_sessions || n < 0 || (n > 0 && !samples)) return fail(WAM_E_INVALID, "bad argument");
+  const long have = m->h_pending[session];
+  if (have + n > m->max_block) return fail(WAM_E_CAPACITY, "session block buffer full: flush first (max_block samples per flush)");
+  if (n > 0) memcpy(m->h_samples + (size_t)session * (size_t)m->max_block + have, samples, sizeof(float) * (size_t)n);
+  m->h_pending[session] = (int32_t)(have + n);
+  m->blocks += 1;
+  return WAM_OK;
+}
+
+extern "C" long wam_fsk_mux_pending(wam_fsk_mux* m, long session) {
+  if (!m || session < 0 || session >= m->n_sessions) return fail(WAM_E_INVALID, "bad argument");
+  return m->h_pending[session];
+}
+
+extern "C" long wam_fsk_mux_out_capacity(wam_fsk_mux* m) { return m ? m->out_cap : fail(WAM_E_INVALID, "mux is NULL"); }
+extern "C" wam_fsk_batch* wam_fsk_mux_batch(wam_fsk_mux* m) { return m ? m->b : nullptr; }
+
+// One ragged batch over every session that pushed since the last flush (the others are not called).
+// out [n_sessions][out_stride] (out_stride >= wam_fsk_mux_out_capacity), out_len[s] bytes completed for session s.
+extern "C" int wam_fsk_mux_flush(wam_fsk_mux* m, uint8_t* out, long out_stride, int32_t* out_len) {
+  if (!m || !out_len || out_stride < 0 || (!out && out_stride > 0)) return fail(WAM_E_INVALID, "bad argument");
+  long n_max = 0;
+  for (long s = 0; s < m->n_sessions; s++) {
+    const int32_t p = m->h_pending[s];
+    m->h_nvalid[s] = p > 0 ? p : -1;
+    n_max = std::max<long>(n_max, p);
+    m->h_pending[s] = 0;
+  }
+  if (n_max == 0) {
+    memset(out_len, 0, sizeof(int32_t) * (size_t)m->n_sessions);
+    return WAM_OK;
+  }
+  n_max = (n_max + 3) / 4 * 4;
+  int rc = demodulate_host_impl(m->b, m->h_samples, m->max_block, std::min(n_max, m->max_block), m->h_nvalid, true,
+                                m->h_out, m->out_cap, m->h_out_len, 0);
+  if (rc != WAM_OK) return rc;
+  for (long s = 0; s < m->n_sessions; s++) {
+    const int32_t n = m->h_out_len[s];
+    if (n > out_stride) return fail(WAM_E_CAPACITY, "out_stride smaller than the bytes a session produced");
+    out_len[s] = n;
+    if (n > 0) memcpy(out + (size_t)s * (size_t)out_stride, m->h_out + (size_t)s * (size_t)m->out_cap, (size_t)n);
+  }
+  m->flushes += 1;
+  return WAM_OK;
+}
+
 extern "C" int wam_host_alloc(void** p, size_t bytes) {
   if (!p) return fail(WAM_E_INVALID, "p is NULL");
   CUDA_TRY(cudaMallocHost(p, bytes ? bytes : 16));

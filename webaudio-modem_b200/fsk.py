@@ -323,3 +323,67 @@ class FSKBatch:
         st = (L.StatusStruct * self.n_streams)()
         L.check(self._lib.wam_fsk_batch_status(self._h, st))
         return [_status_dict(st[i]) for i in range(self.n_streams)]
+
+
+class FSKSessionMux:
+    """Host adapter for many concurrent block-wise callers (wam_fsk_mux_*): every session pushes its render quanta
+    (FSKProcessor.process() delivers 128 samples per call, fsk-processor.ts:152-167), one flush() runs a single ragged
+    GPU batch over the sessions that pushed and returns each session's decoded bytes.  Sessions that pushed nothing
+    are not called."""
+
+    def __init__(self, n_sessions: int, configs, cfg_index=None, max_block: int = 1024, device: int = 0):
+        self._lib = L.lib()
+        if isinstance(configs, dict) or configs is None:
+            configs = [configs or {}]
+        self.configs = [normalize_config(c) for c in configs]
+        self.n_sessions = int(n_sessions)
+        structs = (L.FSKConfigStruct * len(self.configs))()
+        self._keep = []
+        for i, c in enumerate(self.configs):
+            st, k = config_struct(c)
+            structs[i] = st
+            self._keep.append(k)
+        idx = None
+        if cfg_index is not None:
+            idx = np.ascontiguousarray(cfg_index, dtype=np.int32)
+            assert idx.shape == (self.n_sessions,)
+        self._h = C.c_void_p()
+        L.check(self._lib.wam_fsk_mux_create(device, self.n_sessions, structs, len(self.configs),
+                                             idx.ctypes.data_as(C.POINTER(C.c_int32)) if idx is not None else None,
+                                             max_block, C.byref(self._h)))
+        self._cap = int(L.check(self._lib.wam_fsk_mux_out_capacity(self._h)))
+        self._out = np.zeros((self.n_sessions, self._cap), dtype=np.uint8)
+        self._out_len = np.zeros(self.n_sessions, dtype=np.int32)
+
+    def close(self):
+        if self._h:
+            self._lib.wam_fsk_mux_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def push(self, session: int, samples: np.ndarray):
+        a = np.ascontiguousarray(samples, dtype=np.float32)
+        L.check(self._lib.wam_fsk_mux_push(self._h, session, a.ctypes.data if a.size else None, a.size))
+
+    def pending(self, session: int) -> int:
+        return int(L.check(self._lib.wam_fsk_mux_pending(self._h, session)))
+
+    def flush(self) -> list[bytes]:
+        L.check(self._lib.wam_fsk_mux_flush(self._h, self._out.ctypes.data, self._cap, self._out_len.ctypes.data))
+        return [bytes(self._out[i, : self._out_len[i]]) for i in range(self.n_sessions)]
+
+    def flush_raw(self):
+        """flush() without building Python objects: (out uint8 [n_sessions, cap], out_len int32 [n_sessions]) views."""
+        L.check(self._lib.wam_fsk_mux_flush(self._h, self._out.ctypes.data, self._cap, self._out_len.ctypes.data))
+        return self._out, self._out_len
+
+    def status(self) -> list[dict]:
+        st = (L.StatusStruct * self.n_sessions)()
+        L.check(self._lib.wam_fsk_batch_status(self._lib.wam_fsk_mux_batch(self._h), st))
+        return [_status_dict(st[i]) for i in range(self.n_sessions)]
+
