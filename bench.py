@@ -279,7 +279,8 @@ def run_gpu(args):
 
     def step():
         batch.renew(sp)
-        batch.demodulate_device(x.data_ptr(), N_SAMPLES, N_SAMPLES, d_out.data_ptr(), cap, d_len.data_ptr(), stream=sp)
+        batch.demodulate_device(x.data_ptr(), N_SAMPLES, N_SAMPLES, d_out.data_ptr(), cap, d_len.data_ptr(), stream=sp,
+                                flags=args.demod_flags)
 
     def barrier():
         if world > 1:
@@ -302,7 +303,8 @@ def run_gpu(args):
     for k in range(args.steps):
         batch.renew(sp)
         kev[k][0].record(stream)
-        batch.demodulate_device(x.data_ptr(), N_SAMPLES, N_SAMPLES, d_out.data_ptr(), cap, d_len.data_ptr(), stream=sp)
+        batch.demodulate_device(x.data_ptr(), N_SAMPLES, N_SAMPLES, d_out.data_ptr(), cap, d_len.data_ptr(), stream=sp,
+                                flags=args.demod_flags)
         kev[k][1].record(stream)
     ev1.record(stream)
     barrier()
@@ -413,6 +415,7 @@ def main():
     ap.add_argument("--streams", type=int, default=65536, help="streams per GPU (config 2: 65536)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--demod-flags", type=int, default=0, help="A/B experiments: WAM_BATCH_* flags for the device-resident step (16 = no TMA)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()

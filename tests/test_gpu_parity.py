@@ -390,3 +390,27 @@ def test_session_mux_matches_one_fskcore_per_session(gpu_wam, oracle):
         for _ in range(3):
             mux.push(0, np.zeros(128, dtype=np.float32))  # more than max_block between flushes
     mux.close()
+
+
+def test_tma_staging_equals_cp_async_staging(gpu_wam, oracle):
+    """Many-stream launches stage their input tiles with TMA (cp.async.bulk.tensor, 128-byte swizzle) when the rows of
+    a configuration group are contiguous; WAM_BATCH_NO_TMA forces the per-lane cp.async path.  Same bytes and state,
+    including ragged tails (n not a multiple of 32), a stream count that is not a multiple of 32 and several calls."""
+    L = gpu_wam._lib
+    n_streams, n = 32 * 23 + 5, 20000 + 13
+    cfg = siggen.V21_CH2
+    x, _ = siggen.noisy_streams(cfg, n_streams, n, 4, np.linspace(-6, 20, n_streams), seed=31)
+    flags_fused = L.WAM_BATCH_NO_PIPELINE
+    a = gpu_wam.FSKBatch(n_streams, cfg)
+    b = gpu_wam.FSKBatch(n_streams, cfg)
+    got_a, got_b = [b""] * n_streams, [b""] * n_streams
+    for lo, hi in ((0, 7001), (7001, 7001 + 4096), (7001 + 4096, n)):
+        part = np.ascontiguousarray(x[:, lo:hi])
+        pa = a.demodulate_bytes(part, flags=flags_fused)
+        pb = b.demodulate_bytes(part, flags=flags_fused | L.WAM_BATCH_NO_TMA)
+        got_a = [u + v for u, v in zip(got_a, pa)]
+        got_b = [u + v for u, v in zip(got_b, pb)]
+    assert got_a == got_b
+    assert a.status() == b.status()
+    want, _ = oracle.batch_demodulate([cfg], None, x.copy(), n_threads=8)
+    assert got_a == want and sum(len(w) for w in want) > 100

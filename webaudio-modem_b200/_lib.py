@@ -25,6 +25,7 @@ WAM_BATCH_WRITEBACK_AGC = 1
 WAM_BATCH_TAP_PREFILTER = 2
 WAM_BATCH_DEBUG_GENERIC_SM = 4
 WAM_BATCH_NO_PIPELINE = 8
+WAM_BATCH_NO_TMA = 16
 
 
 class WamError(RuntimeError):

@@ -223,12 +223,15 @@ __device__ __noinline__ double amp_ring_threshold(const float* __restrict__ arin
 // One decimated sample of FSKCore.processDownsampledBit (fsk.ts:278-344) AFTER the ring puts:
 // silence/EOD, sync search or vote/bit decision.  ring_pos / amp_next describe the rings including
 // this sample.  Returns true when resetState() ran.
-template <bool GENERIC>
+template <bool GENERIC, bool RING_ARG>
 __device__ __forceinline__ bool sm_step(A2State& s, BState& b, int bit, double amplitude, uint32_t ring_pos,
                                         bool ring_ready, uint32_t amp_next, uint32_t amp_len, const DemodArgs& a,
-                                        int li, uint8_t* out_row, bool& thr_changed, uint32_t* ring, long rstride) {
+                                        int li, uint8_t* out_row, bool& thr_changed, uint32_t* ring_arg, long rstride_arg) {
   const FskDerived& d = a.d;
   const long ns = a.n_local;
+  // RING_ARG: the caller keeps this stream's sync ring somewhere else (shared memory); otherwise the state array
+  uint32_t* ring = RING_ARG ? ring_arg : a.sync_ring + li;
+  const long rstride = RING_ARG ? rstride_arg : ns;
   // silence / EOD — fsk.ts:285-295
   b.gsc++;
   b.gmod = (b.gmod + 1u == (uint32_t)d.check_period) ? 0u : b.gmod + 1u;
@@ -306,20 +309,24 @@ __device__ __forceinline__ bool sm_sample_generic(A2State& s, BState& b, int bit
   b.amp_pos = (b.amp_pos + 1u == (uint32_t)d.amp_phys) ? 0u : b.amp_pos + 1u;
   b.amp_len = min(b.amp_len + 1u, (uint32_t)d.amp_cap);
   bool thr_changed = false;
-  return sm_step<true>(s, b, bit, amplitude, b.ring_pos, ready, b.amp_pos, b.amp_len, a, li, out_row, thr_changed, ring, ns);
+  return sm_step<true, false>(s, b, bit, amplitude, b.ring_pos, ready, b.amp_pos, b.amp_len, a, li, out_row, thr_changed,
+                              nullptr, 0);
 }
 
 // Event-driven state machine for one tile (integral ring, eod_count > 16).  `bits` holds the hard
 // decisions of decimated samples 0..nk-1 of the tile, amp[k*32] their amplitudes (f64, smem).
 // Returns the decimated index at which resetState() ran, or -1.
+template <bool RING_ARG>
 __device__ __forceinline__ int sm_tile_events(A2State& s, BState& b, uint32_t bits, const double* __restrict__ amp,
                                               int b_from, int nk, uint32_t pos_t0, uint32_t len_t0, uint32_t slot_t0,
                                               uint32_t alen_t0, const DemodArgs& a, int li, uint8_t* out_row,
-                                              uint32_t* ring, long rstride) {
-  // ring / rstride: this stream's bit-packed sync ring (word w at ring[w * rstride]) — the global state array
-  // (a.sync_ring + li, a.n_local) or a shared-memory copy of it
+                                              uint32_t* ring_arg, long rstride_arg) {
+  // this stream's bit-packed sync ring (word w at ring[w * rstride]): the global state array, or with RING_ARG
+  // the caller's copy (shared memory in fsk_demod_pipe_kernel)
   const FskDerived& d = a.d;
   const long ns = a.n_local;
+  uint32_t* ring = RING_ARG ? ring_arg : a.sync_ring + li;
+  const long rstride = RING_ARG ? rstride_arg : ns;
   float* aring = a.amp_ring + li;
   const uint32_t wmask = (uint32_t)(d.ring_words - 1);
 
@@ -388,8 +395,8 @@ __device__ __forceinline__ int sm_tile_events(A2State& s, BState& b, uint32_t bi
     if (slot_next >= (uint32_t)d.amp_phys) slot_next -= (uint32_t)d.amp_phys;
     const uint32_t alen = min(alen_t0 + (uint32_t)k_evt + 1u, (uint32_t)d.amp_cap);
     bool thr_changed = false;
-    if (sm_step<false>(s, b, (int)((bits >> k_evt) & 1u), amp[k_evt * 32], pos_k, ready, slot_next, alen, a, li, out_row,
-                thr_changed, ring, rstride))
+    if (sm_step<false, RING_ARG>(s, b, (int)((bits >> k_evt) & 1u), amp[k_evt * 32], pos_k, ready, slot_next, alen, a, li,
+                                 out_row, thr_changed, ring_arg, rstride_arg))
       return k_evt;
     if (thr_changed) {
       silent = 0u;
@@ -543,11 +550,39 @@ __device__ __forceinline__ void ragged_account(const DemodArgs& a, int li, long 
   f[F_RAGGED_TOTAL * ns] += (double)n_l;
 }
 
+// ---- TMA staging (cp.async.bulk.tensor): one instruction by one lane moves a whole 32-stream x 32-sample tile
+// from the [rows][stride] sample buffer into shared memory, already in the 128-byte swizzle that tile_index()
+// describes (16-byte chunk index XOR (row & 7)); completion is signalled on an mbarrier.  Out-of-range rows and
+// samples are zero-filled by the hardware.
+__device__ __forceinline__ void tma_bar_init(uint64_t* bar) {
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(b) : "memory");
+}
+__device__ __forceinline__ void tma_load_tile(float* dst, const CUtensorMap* tmap, uint64_t* bar, int x, int y) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+  // the buffer was last touched through the generic proxy (it doubles as the amplitude buffer of an earlier tile)
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(b), "r"(kTile * kTile * 4) : "memory");
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+               ::"r"(d), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void tma_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(b), "r"(parity) : "memory");
+  } while (!done);
+}
+
 // Grid: one warp (32 streams) per CTA, so that 2048 warps spread evenly over 148 SMs.
 // GENERIC = false: the common case (no AGC write-back, no tap, integral sync ring, eod_count > 16) —
 // only the event-driven state machine is compiled in, which keeps the kernel's code footprint small.
 // GENERIC = true: write-back / tap by run-time flag and the per-sample state machine as fallback.
-template <bool ALIGNED, bool GENERIC>
+// STAGE_TMA: tiles arrive by TMA instead of per-lane cp.async (rows of the group contiguous, buffer 16-byte aligned).
+template <bool ALIGNED, bool GENERIC, bool STAGE_TMA = false>
 __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kernel(const __grid_constant__ DemodLaunch L) {
   int gi = 0;
 #pragma unroll
@@ -556,7 +591,8 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
   const DemodArgs& a = L.g[gi];
   // stage buffers: input tile (swizzled f32 [32][32]); after A1 the same 4 KiB hold the squared
   // magnitudes / amplitudes of the tile as f64 [16][32]
-  __shared__ __align__(128) float tiles[kStages][kTile * kTile];
+  __shared__ __align__(1024) float tiles[kStages][kTile * kTile];  // 1024: the 128-byte swizzle atom of TMA
+  __shared__ __align__(8) uint64_t tma_bar[kStages];
   __shared__ __align__(128) float pfbuf[kTile * 32];  // pre-filtered samples [i][lane]
   __shared__ double park_d[kParkD][32];
   __shared__ uint32_t park_u[kParkU][32];
@@ -621,15 +657,34 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
 #endif
   const long long clk_begin = timing ? clock64() : 0;
   const long n_tiles = (a.n + kTile - 1) / kTile;
+  const int tma_row0 = a.id0 + a.l_begin + ((int)blockIdx.x - L.block_begin[gi]) * 32 - a.row_base;
+  if (STAGE_TMA) {
+    if (lane == 0) {
+#pragma unroll
+      for (int p = 0; p < kStages; ++p) tma_bar_init(&tma_bar[p]);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncwarp();
+  }
   for (int p = 0; p < kStages - 1; ++p) {
-    if (p < n_tiles) stage_tile<ALIGNED>(tiles[p], a, rows, (long)p * kTile, lane);
-    cp_async_commit();
+    if (STAGE_TMA) {
+      if (p < n_tiles && lane == 0) tma_load_tile(tiles[p], &L.tmap[gi], &tma_bar[p], p * kTile, tma_row0);
+    } else {
+      if (p < n_tiles) stage_tile<ALIGNED>(tiles[p], a, rows, (long)p * kTile, lane);
+      cp_async_commit();
+    }
   }
   for (long t = 0; t < n_tiles; ++t) {
     const long tn = t + kStages - 1;
-    if (tn < n_tiles) stage_tile<ALIGNED>(tiles[tn % kStages], a, rows, tn * kTile, lane);
-    cp_async_commit();
-    cp_async_wait<kStages - 1>();
+    if (STAGE_TMA) {
+      if (tn < n_tiles && lane == 0)
+        tma_load_tile(tiles[tn % kStages], &L.tmap[gi], &tma_bar[tn % kStages], (int)(tn * kTile), tma_row0);
+      tma_wait(&tma_bar[t % kStages], (uint32_t)((t / kStages) & 1));
+    } else {
+      if (tn < n_tiles) stage_tile<ALIGNED>(tiles[tn % kStages], a, rows, tn * kTile, lane);
+      cp_async_commit();
+      cp_async_wait<kStages - 1>();
+    }
     __syncwarp();
     float* tile = tiles[t % kStages];
     double* pbuf = reinterpret_cast<double*>(tile);  // [k][lane] after A1
@@ -733,8 +788,8 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
         redo = false;
         int k_reset = -1;
         if (fast_sm) {
-          k_reset = sm_tile_events(s, b, bits, pbuf + lane, b_from, nk, pos_t0, len_t0, slot_t0, alen_t0, a, li, out_row,
-                                   a.sync_ring + li, ns);
+          k_reset = sm_tile_events<false>(s, b, bits, pbuf + lane, b_from, nk, pos_t0, len_t0, slot_t0, alen_t0, a, li,
+                                          out_row, nullptr, 0);
           if (k_reset < 0 || 2 * (k_reset + 1) >= v_hi) {
             b.ring_len = min(len_t0 + (uint32_t)nk, (uint32_t)d.ring_cap_int);
             const uint32_t sl = slot_t0 + (uint32_t)nk;
@@ -759,9 +814,11 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
         if (timing) { const long long c = clock64(); cyc_b += (unsigned long long)(c - clk0); clk0 = c; }
       }
     }
+    // every lane's generic-proxy accesses to this tile's buffer are ordered before the TMA write that recycles it
+    if (STAGE_TMA) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncwarp();
   }
-  cp_async_wait<0>();
+  if (!STAGE_TMA) cp_async_wait<0>();
   if (timing && lane == 0) {
     unsigned long long* pc = a.phase_cycles + 4ull * blockIdx.x;
     pc[0] += cyc_a1; pc[1] += cyc_a2; pc[2] += cyc_b;

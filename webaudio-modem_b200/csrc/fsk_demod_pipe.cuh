@@ -348,8 +348,8 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
         int k_reset = -1;
         if (lane_busy) {
           const uint32_t bits = sh.bits[t % kPipeDec][lane];
-          k_reset = sm_tile_events(dummy, b, bits, sh.amp[t % kPipeDec] + lane, b_from, nk, pos_t0, len_t0, slot_t0,
-                                   alen_t0, a, li, out_row, ring, rstride);
+          k_reset = sm_tile_events<true>(dummy, b, bits, sh.amp[t % kPipeDec] + lane, b_from, nk, pos_t0, len_t0, slot_t0,
+                                         alen_t0, a, li, out_row, ring, rstride);
           if (k_reset < 0 || 2 * (k_reset + 1) >= v_hi) {
             // this lane is done with the tile: end-of-tile ring bookkeeping
             b.ring_len = min(len_t0 + (uint32_t)nk, (uint32_t)d.ring_cap_int);

@@ -516,6 +516,33 @@ static void launch_demod(const DemodLaunch& L, cudaStream_t st) {
   fsk_demod_exact_kernel<A, G><<<L.block_begin[L.n_groups], 32, 0, st>>>(L);
 }
 
+// cuTensorMapEncodeTiled through the runtime (libwam links only cudart)
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder() {
+  static tmap_encode_fn fn = []() -> tmap_encode_fn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (tmap_encode_fn)p;
+  }();
+  return fn;
+}
+// {n, rows} float32 view of a sample buffer, 32 x 32 boxes, 128-byte swizzle, zero fill outside
+static bool make_sample_tmap(CUtensorMap* m, float* d_samples, long stride, long n, long rows) {
+  tmap_encode_fn enc = tmap_encoder();
+  if (!enc || n <= 0 || rows <= 0 || n > 0xffffffffL) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)stride * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kTile, (cuuint32_t)kTile};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_samples, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // launch the demodulator for all streams of `b` whose global id lies in [s0, s1); row 0 of the
 // buffers is stream `row_base`.  All configuration groups go into one launch (up to
 // kMaxGroupsPerLaunch per launch) so their one-warp CTAs share the SMs.
@@ -530,6 +557,7 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
   memset(&L, 0, sizeof(L));
   const bool ragged = d_n_valid != nullptr;
   bool generic = wb || tap || (flags & WAM_BATCH_DEBUG_GENERIC_SM);
+  bool tma_ok = aligned;  // every group of the launch has contiguous rows and a TMA descriptor
   auto flush = [&]() -> int {
     if (L.n_groups == 0) return WAM_OK;
     // Few streams (<= 5 three-warp CTAs per SM): the warp-specialised pipeline (fsk_demod_pipe.cuh) advances a
@@ -556,12 +584,15 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
       if (pipe) kern<<<L.block_begin[L.n_groups], kPipeThreads, b->pipe_smem, st>>>(L);
     }
     if (pipe) {
+    } else if (aligned && !generic && !ragged && tma_ok && !(flags & WAM_BATCH_NO_TMA)) {
+      fsk_demod_exact_kernel<true, false, true><<<L.block_begin[L.n_groups], 32, 0, st>>>(L);
     } else if (aligned) { if (generic || ragged) launch_demod<true, true>(L, st); else launch_demod<true, false>(L, st); }
     else         { if (generic || ragged) launch_demod<false, true>(L, st); else launch_demod<false, false>(L, st); }
     b->launches++;
     CUDA_TRY(cudaGetLastError());
     memset(&L, 0, sizeof(L));
     generic = wb || tap || (flags & WAM_BATCH_DEBUG_GENERIC_SM);
+    tma_ok = aligned;
     return WAM_OK;
   };
   for (auto& g : b->groups) {
@@ -585,6 +616,8 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
     a.append = append ? 1 : 0;
     a.n_valid = d_n_valid; a.n_valid_offset = n_valid_offset; a.count_call = count_call ? 1 : 0;
     a.phase_cycles = b->phase_cycles;
+    if (tma_ok && !generic && !ragged)
+      tma_ok = g.contiguous && make_sample_tmap(&L.tmap[L.n_groups], d_samples, stride, n, s1 - row_base);
     L.block_begin[L.n_groups + 1] = L.block_begin[L.n_groups] + (int)((hi - lo + 31) / 32);
     L.n_groups++;
     if (L.n_groups == kMaxGroupsPerLaunch) {
@@ -658,7 +691,7 @@ static int demodulate_host_impl(wam_fsk_batch* b, float* samples, long stream_st
     b->demodulation_calls += 1;
     b->total_samples += (double)n_samples;
   }
-  flags &= (WAM_BATCH_WRITEBACK_AGC | WAM_BATCH_DEBUG_GENERIC_SM | WAM_BATCH_NO_PIPELINE);
+  flags &= (WAM_BATCH_WRITEBACK_AGC | WAM_BATCH_DEBUG_GENERIC_SM | WAM_BATCH_NO_PIPELINE | WAM_BATCH_NO_TMA);
 
   // The call is cut into TIME slabs (all streams, samples [t0, t1)): the H2D copy of slab k+1 overlaps
   // the kernel of slab k (copy stream + compute stream, two staging buffers), and every slab launch

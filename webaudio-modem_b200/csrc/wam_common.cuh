@@ -1,6 +1,7 @@
 // wam_common.cuh — shared host/device definitions for libwam.so (B200 / sm_100a).
 #pragma once
 
+#include <cuda.h>  // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -108,6 +109,9 @@ struct DemodArgs {
 // so that their CTAs fill the SMs together.
 constexpr int kMaxGroupsPerLaunch = 4;
 struct DemodLaunch {
+  // TMA descriptors of the groups' sample buffers ({n, rows} float32, 32 x 32 boxes, 128-byte swizzle), used by
+  // the STAGE_TMA variant of fsk_demod_exact_kernel; first member so that each one is 64-byte aligned
+  alignas(64) CUtensorMap tmap[kMaxGroupsPerLaunch];
   int n_groups;
   int block_begin[kMaxGroupsPerLaunch + 1];  // first CTA of every group, then the total
   int pipe_ring_smem;                        // fsk_demod_pipe_kernel: the sync rings are copied to shared memory
