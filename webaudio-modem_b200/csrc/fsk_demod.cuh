@@ -33,7 +33,26 @@
 #include "fastmath.cuh"
 #include "wam_common.cuh"
 
+// unroll factors of the two DSP loops (A/B-tuned on B200, profiles/r01_notes.md)
+#ifndef WAM_A1_CHUNKS
+#define WAM_A1_CHUNKS 2  // float4 chunks (4 samples each) per iteration of the AGC + pre-filter loop
+#endif
+#ifndef WAM_A2_UNROLL
+#define WAM_A2_UNROLL 4  // pairs per iteration of the I/Q + discriminator loop
+#endif
+
+// unroll factors of the two DSP loops (A/B-tuned on B200, profiles/r01_notes.md)
+#ifndef WAM_A1_CHUNKS
+#define WAM_A1_CHUNKS 2  // float4 chunks (4 samples each) per iteration of the AGC + pre-filter loop
+#endif
+#ifndef WAM_A2_UNROLL
+#define WAM_A2_UNROLL 4  // pairs per iteration of the I/Q + discriminator loop
+#endif
+
 namespace wam {
+
+constexpr int kA1Chunks = WAM_A1_CHUNKS;
+constexpr int kA2Unroll = WAM_A2_UNROLL;
 
 struct A1State {  // AGC + pre-filter (never reset)
   double gain, py1, py2;
@@ -330,6 +349,7 @@ __device__ __forceinline__ int sm_tile_events(A2State& s, BState& b, uint32_t bi
   float* aring = a.amp_ring + li;
   const uint32_t wmask = (uint32_t)(d.ring_words - 1);
 
+  uint32_t silent = 0u;
   // ---- bulk ring puts for samples [b_from, nk) — fsk.ts:281-282
   {
     const uint32_t p = pos_t0 + (uint32_t)b_from;
@@ -349,14 +369,22 @@ __device__ __forceinline__ int sm_tile_events(A2State& s, BState& b, uint32_t bi
     b.ring_pos = pos_t0 + (uint32_t)nk;
     uint32_t slot = slot_t0 + (uint32_t)b_from;
     if (slot >= (uint32_t)d.amp_phys) slot -= (uint32_t)d.amp_phys;
-    for (int k = b_from; k < nk; ++k) {
-      aring[(long)slot * ns] = (float)amp[k * 32];
-      slot = (slot + 1u == (uint32_t)d.amp_phys) ? 0u : slot + 1u;
+    {
+      // amplitude-ring puts (fsk.ts:282, Float32Array store) and the silence flags for the current threshold
+      // (fsk.ts:286) from the same shared-memory reads; the ring wraps at most once inside a tile
+      const double thr = b.sil_thr;
+      float* p = aring + (long)slot * ns;
+      int until_wrap = d.amp_phys - (int)slot;
+#pragma unroll 4
+      for (int k = b_from; k < nk; ++k) {
+        const double av = amp[k * 32];
+        *p = (float)av;
+        p += ns;
+        if (--until_wrap == 0) p = aring;
+        silent |= (av < thr ? 1u : 0u) << k;
+      }
     }
   }
-  // silence flags for the current threshold — fsk.ts:286
-  uint32_t silent = 0u;
-  for (int k = b_from; k < nk; ++k) silent |= (amp[k * 32] < b.sil_thr ? 1u : 0u) << k;
 
   int k = b_from;
   while (k < nk) {
@@ -701,15 +729,18 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
       const double att = d.agc_attack, rel = d.agc_release;
       if (len == kTile && !WRITEBACK && !TAP) {
 #pragma unroll 1
-        for (int ch = 0; ch < 8; ++ch) {
-          const float4 v = *reinterpret_cast<const float4*>(tile + tile_index(lane, ch * 4));
-          float sg;
-          const float p0 = phase_a1_sample(a1, v.x, d, agc, att, rel, sg);
-          const float p1 = phase_a1_sample(a1, v.y, d, agc, att, rel, sg);
-          const float p2 = phase_a1_sample(a1, v.z, d, agc, att, rel, sg);
-          const float p3 = phase_a1_sample(a1, v.w, d, agc, att, rel, sg);
-          float* pfp = pfbuf + (ch * 4) * 32 + lane;
-          pfp[0] = p0; pfp[32] = p1; pfp[64] = p2; pfp[96] = p3;
+        for (int ch = 0; ch < 8; ch += kA1Chunks) {
+#pragma unroll
+          for (int c = 0; c < kA1Chunks; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(tile + tile_index(lane, (ch + c) * 4));
+            float sg;
+            const float p0 = phase_a1_sample(a1, v.x, d, agc, att, rel, sg);
+            const float p1 = phase_a1_sample(a1, v.y, d, agc, att, rel, sg);
+            const float p2 = phase_a1_sample(a1, v.z, d, agc, att, rel, sg);
+            const float p3 = phase_a1_sample(a1, v.w, d, agc, att, rel, sg);
+            float* pfp = pfbuf + ((ch + c) * 4) * 32 + lane;
+            pfp[0] = p0; pfp[32] = p1; pfp[64] = p2; pfp[96] = p3;
+          }
         }
       } else {
 #pragma unroll 1
@@ -751,7 +782,7 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
         if (dsc0 == 0 && (v_hi & 1) == 0) {
           // fast path: every pair is complete (two pairs per iteration: the biquad histories rotate in
           // place and two atan2 chains overlap)
-#pragma unroll 2
+#pragma unroll kA2Unroll
           for (int k = k_from; k < nk; ++k) {
             double yi0, yq0, yi1, yq1, pp;
             const float* pfp = pfbuf + (2 * k) * 32 + lane;
