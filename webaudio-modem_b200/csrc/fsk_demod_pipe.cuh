@@ -35,6 +35,14 @@ namespace wam {
 constexpr int kPipePf = 4;    // pf ring depth (tiles)
 constexpr int kPipeDec = 4;   // dec ring depth (tiles)
 constexpr int kPipeThreads = 96;
+#ifndef WAM_PIPE_A1_CHUNKS
+#define WAM_PIPE_A1_CHUNKS 1
+#endif
+#ifndef WAM_PIPE_A2_UNROLL
+#define WAM_PIPE_A2_UNROLL 2
+#endif
+constexpr int kPipeA1Chunks = WAM_PIPE_A1_CHUNKS;  // float4 chunks per iteration of the A1 loop
+constexpr int kPipeA2Unroll = WAM_PIPE_A2_UNROLL;  // pairs per iteration of the A2 loop
 constexpr unsigned kPipeSpinLimit = 1u << 24;
 #define WAM_ERR_PIPE_TIMEOUT 2u
 
@@ -144,15 +152,18 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
       if (active) {
         if (len == kTile) {
 #pragma unroll 1
-          for (int ch = 0; ch < 8; ++ch) {
-            const float4 v = *reinterpret_cast<const float4*>(tile + tile_index(lane, ch * 4));
-            float sg;
-            const float p0 = phase_a1_sample(a1, v.x, d, agc, att, rel, sg);
-            const float p1 = phase_a1_sample(a1, v.y, d, agc, att, rel, sg);
-            const float p2 = phase_a1_sample(a1, v.z, d, agc, att, rel, sg);
-            const float p3 = phase_a1_sample(a1, v.w, d, agc, att, rel, sg);
-            float* pfp = pfb + (ch * 4) * 32 + lane;
-            pfp[0] = p0; pfp[32] = p1; pfp[64] = p2; pfp[96] = p3;
+          for (int ch = 0; ch < 8; ch += kPipeA1Chunks) {
+#pragma unroll
+            for (int c = 0; c < kPipeA1Chunks; ++c) {
+              const float4 v = *reinterpret_cast<const float4*>(tile + tile_index(lane, (ch + c) * 4));
+              float sg;
+              const float p0 = phase_a1_sample(a1, v.x, d, agc, att, rel, sg);
+              const float p1 = phase_a1_sample(a1, v.y, d, agc, att, rel, sg);
+              const float p2 = phase_a1_sample(a1, v.z, d, agc, att, rel, sg);
+              const float p3 = phase_a1_sample(a1, v.w, d, agc, att, rel, sg);
+              float* pfp = pfb + ((ch + c) * 4) * 32 + lane;
+              pfp[0] = p0; pfp[32] = p1; pfp[64] = p2; pfp[96] = p3;
+            }
           }
         } else {
 #pragma unroll 1
@@ -249,7 +260,7 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
           // whole pairs only (two pairs per iteration: the biquad histories rotate in place and two atan2
           // chains overlap).  Splitting the tile into passes (all I/Q sums, then 16 independent atan2, then the
           // post-filter chain) was tried and is slower: 300 vs 222 cycles per sample (profiles/r01_notes.md).
-#pragma unroll 2
+#pragma unroll kPipeA2Unroll
           for (int k = k_from; k < nk; ++k) {
             double yi0, yq0, yi1, yq1, pp;
             const float* pfp = pfbuf + (2 * k) * 32 + lane;
