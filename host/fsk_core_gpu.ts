@@ -98,3 +98,42 @@ export class FSKBatchGPU {
     return native.batchModulate(this.handle, data, nBytes);
   }
 }
+
+/**
+ * Session multiplexer (wam_fsk_mux_*): many FSKProcessor.process() callers, each delivering one 128-sample render
+ * quantum per call (fsk-processor.ts:152-167), share one ragged GPU batch per tick.  Not executed in this image.
+ */
+export class FSKSessionMuxGPU {
+  private readonly handle: object;
+  constructor(readonly nSessions: number, configs: FSKConfigInput[] | FSKConfigInput, cfgIndex?: Int32Array, maxBlock = 1024, device = 0) {
+    const list = (Array.isArray(configs) ? configs : [configs]).map((c) => ({ ...DEFAULT_FSK_CONFIG, ...c }) as FSKConfig);
+    this.handle = native.muxCreate(device, nSessions, list, cfgIndex, maxBlock); // wam_fsk_mux_create
+  }
+  /** called from a session's process(): copies the quantum into pinned staging (wam_fsk_mux_push) */
+  push(session: number, quantum: Float32Array): void {
+    native.muxPush(this.handle, session, quantum);
+  }
+  /** one ragged batch over the sessions that pushed since the last flush (wam_fsk_mux_flush) */
+  async flush(): Promise<Uint8Array[]> {
+    const { bytes, lengths, stride } = await native.muxFlush(this.handle);
+    return Array.from(lengths, (n: number, s: number) => bytes.subarray(s * stride, s * stride + n));
+  }
+}
+
+/**
+ * Receive side of XModemTransport for n sessions (wam_xmodem_batch_receive; xmodem.ts:232-321): feed every session's
+ * demodulated bytes, get the ACK / NAK bytes to send back and the reassembled payloads.  The transport's timers,
+ * its send side and the half-duplex turn-taking stay in XModemTransport on the host.
+ */
+export class XModemBatchReceiverGPU {
+  private readonly handle: object;
+  constructor(readonly nSessions: number, maxRetries = 10, device = 0) {
+    this.handle = native.xmodemReceiverCreate(device, nSessions, maxRetries);
+  }
+  async feed(bursts: Uint8Array[]): Promise<Uint8Array[]> {
+    return native.xmodemReceiverFeed(this.handle, bursts); // replies per session: 0x06 ACK / 0x15 NAK in order
+  }
+  received(session: number): Uint8Array {
+    return native.xmodemReceiverData(this.handle, session); // assembleData(receive.data), xmodem.ts:323-334
+  }
+}
