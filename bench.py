@@ -388,8 +388,9 @@ def run_gpu(args):
                      "launches_per_step": launches / args.steps,
                      "achieved_per_launch_bytes": S * N_SAMPLES * BYTES_PER_SAMPLE, "kernel_ms": k_ms,
                      "note": "algorithmic 4 B/input sample x samples per launch / CUDA-event time of the launch "
-                             "(both V.21 channels in one launch); the kernel is instruction-issue/latency bound, "
-                             "see profiles/r01_notes.md for issue-slot utilisation"},
+                             "(both V.21 channels in one launch, input tiles staged by TMA); the kernel is "
+                             "instruction-issue/latency bound (float64, reference-faithful), see profiles/r01_notes.md "
+                             "for issue-slot utilisation"},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
