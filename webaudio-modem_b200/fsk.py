@@ -258,13 +258,14 @@ class FSKBatch:
     def demodulate(self, samples: np.ndarray, writeback_agc: bool = False, flags: int = 0):
         """samples float32 [n_streams, n]; returns (out uint8 [n_streams, cap], out_len int32 [n_streams])."""
         assert samples.dtype == np.float32 and samples.ndim == 2 and samples.shape[0] == self.n_streams
-        assert samples.strides[1] == 4
         n = samples.shape[1]
+        assert n == 0 or samples.strides[1] == 4
         cap = self.out_capacity(n)
         out = np.zeros((self.n_streams, cap), dtype=np.uint8)
         out_len = np.zeros(self.n_streams, dtype=np.int32)
         L.check(self._lib.wam_fsk_batch_demodulate(
-            self._h, samples.ctypes.data, samples.strides[0] // 4, n, out.ctypes.data, cap, out_len.ctypes.data,
+            self._h, samples.ctypes.data if n else None, max(samples.strides[0] // 4, n), n, out.ctypes.data, cap,
+            out_len.ctypes.data,
             (L.WAM_BATCH_WRITEBACK_AGC if writeback_agc else 0) | flags))
         return out, out_len
 
