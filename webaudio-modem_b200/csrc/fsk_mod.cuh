@@ -8,6 +8,8 @@
 //       frac(spb * (marks_before*f_mark + spaces_before*f_space) / fs), evaluated in float64 (the
 //       products are exact integers for integral tone frequencies), stored as a 31-bit binary
 //       fraction with the bit's value in bit 0.  The table is 1/spb of the output in size.
+//   (fsk_modulate_fused_kernel does both in one launch with the table in shared memory; the two-kernel form below
+//   remains for frames whose table does not fit and for rows that are not float4-aligned)
 //   kernel 2 (modulate): HBM-write bound.  One thread per float4 of output, a warp per 512
 //       contiguous bytes; the phase inside a bit advances in 32-bit fixed point (wraps modulo one
 //       cycle for free), so a sample costs IMAD + I2F + FMUL + MUFU.SIN.
@@ -83,22 +85,21 @@ __device__ __forceinline__ int framed_ones_before(const FskDerived& d, int byte,
 
 constexpr int kPhaseThreads = 128;
 
-// one CTA per stream; bytes in chunks of kPhaseThreads: a block scan gives the mark bits before every byte
-// of the chunk, then the threads fill the chunk's table words one line bit each (coalesced stores)
-__global__ void __launch_bounds__(kPhaseThreads) fsk_bit_phase_kernel(const __grid_constant__ ModArgs a) {
-  __shared__ uint32_t s_pre[kPhaseThreads];
-  __shared__ uint8_t s_byte[kPhaseThreads];
-  __shared__ uint32_t s_wsum[kPhaseThreads / 32];
-  const int s = blockIdx.x;
+// Table words of one stream (see the header): NT threads of one CTA; bytes in chunks of NT — a block scan gives the
+// mark bits before every byte of the chunk, then the threads fill the chunk's words one line bit each.
+// tab: global (fsk_bit_phase_kernel) or shared memory (fsk_modulate_fused_kernel).
+template <int NT>
+__device__ __forceinline__ void bit_phase_fill(const ModArgs& a, int s, uint32_t* tab, uint32_t* s_pre, uint8_t* s_byte,
+                                               uint32_t* s_wsum) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const FskDerived& d = a.d;
   const int nbytes = a.data_len ? a.data_len[s] : a.nbytes;
   const int total = d.n_preamble + d.n_sfd + nbytes;
   const uint8_t* row = a.data + (long)s * a.data_stride;
-  uint32_t* tab = a.bittab + (long)s * a.tab_stride;
   const double spb_d = (double)d.spb, inv_fs = 1.0 / d.fs;
+  const uint32_t bpb_magic = 65536u / (uint32_t)d.bpb + 1u;  // i / bpb for i < 65536 / bpb
   uint32_t carry = 0;
-  for (int base = 0; base < total; base += kPhaseThreads) {
+  for (int base = 0; base < total; base += NT) {
     const int k = base + tid;
     const int byte = (k < total) ? frame_byte(a, row, k) : 0;
     const uint32_t v = (k < total) ? (uint32_t)framed_ones(d, byte) : 0u;
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(kPhaseThreads) fsk_bit_phase_kernel(const __gr
     __syncthreads();
     uint32_t woff = 0, wtot = 0;
 #pragma unroll
-    for (int w = 0; w < kPhaseThreads / 32; ++w) {
+    for (int w = 0; w < NT / 32; ++w) {
       const uint32_t t = s_wsum[w];
       if (w < wid) woff += t;
       wtot += t;
@@ -120,9 +121,8 @@ __global__ void __launch_bounds__(kPhaseThreads) fsk_bit_phase_kernel(const __gr
     s_pre[tid] = carry + woff + incl - v;
     s_byte[tid] = (uint8_t)byte;
     __syncthreads();
-    const int nb = min(kPhaseThreads, total - base);
-    const uint32_t bpb_magic = 65536u / (uint32_t)d.bpb + 1u;  // i / bpb for i < 65536 / bpb
-    for (int i = tid; i < nb * d.bpb; i += kPhaseThreads) {
+    const int nb = min(NT, total - base);
+    for (int i = tid; i < nb * d.bpb; i += NT) {
       const int kk = (int)(((uint32_t)i * bpb_magic) >> 16);
       const int b = i - kk * d.bpb;
       const int by = s_byte[kk];
@@ -139,6 +139,16 @@ __global__ void __launch_bounds__(kPhaseThreads) fsk_bit_phase_kernel(const __gr
     carry += wtot;
     __syncthreads();
   }
+}
+
+// one CTA per stream: the table in global memory (frames whose table does not fit in shared memory, or rows
+// that are not float4-aligned)
+__global__ void __launch_bounds__(kPhaseThreads) fsk_bit_phase_kernel(const __grid_constant__ ModArgs a) {
+  __shared__ uint32_t s_pre[kPhaseThreads];
+  __shared__ uint8_t s_byte[kPhaseThreads];
+  __shared__ uint32_t s_wsum[kPhaseThreads / 32];
+  const int s = blockIdx.x;
+  bit_phase_fill<kPhaseThreads>(a, s, a.bittab + (long)s * a.tab_stride, s_pre, s_byte, s_wsum);
 }
 
 constexpr int kModThreads = 256;
@@ -270,6 +280,64 @@ __global__ void __launch_bounds__(kModThreads) fsk_modulate_kernel(const __grid_
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         if (k0 + i < lim) out[k0 + i] = w[i];
+    }
+  }
+}
+
+// Both steps in one launch (the common case: float4-aligned rows, spb % 4 == 0, table <= 40 KB): every CTA builds
+// the table of ITS stream in shared memory, then walks its part of the row.  No table traffic through HBM, no
+// second launch; with one CTA per row (many rows) the table is built exactly once per row.
+__global__ void __launch_bounds__(kModThreads) fsk_modulate_fused_kernel(const __grid_constant__ ModArgs a) {
+  extern __shared__ uint32_t s_tab[];
+  __shared__ uint32_t s_pre[kModThreads];
+  __shared__ uint8_t s_byte[kModThreads];
+  __shared__ uint32_t s_wsum[kModThreads / 32];
+  const int s = blockIdx.y;
+  bit_phase_fill<kModThreads>(a, s, s_tab, s_pre, s_byte, s_wsum);  // ends with __syncthreads()
+  const FskDerived& d = a.d;
+  const int nbytes = a.data_len ? a.data_len[s] : a.nbytes;
+  const uint32_t spb = (uint32_t)d.spb;
+  const uint32_t total_bytes = (uint32_t)(d.n_preamble + d.n_sfd + nbytes);
+  const uint32_t pad = total_bytes > 0 ? 2u * spb : 0u;  // fsk.ts:392
+  const uint32_t body_end = pad + total_bytes * (uint32_t)d.bpb * spb;
+  const uint32_t total = body_end + (uint32_t)d.bpb * spb;
+  const uint32_t lim = (long)total < a.out_stride ? total : (uint32_t)a.out_stride;
+  float* __restrict__ out = a.out + (long)s * a.out_stride;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.out_len) a.out_len[s] = (int32_t)lim;
+  const uint32_t st0 = a.step_fix[0], st1 = a.step_fix[1];
+  const uint32_t stride = gridDim.x * (uint32_t)(4 * kModThreads);
+  uint32_t k0 = (blockIdx.x * (uint32_t)kModThreads + threadIdx.x) * 4u;
+  uint32_t q, r, dq, dr;
+  mod_divmod(stride, spb, a.spb_magic, dq, dr);
+  mod_divmod(k0, spb, a.spb_magic, q, r);  // pad is 0 or 2 * spb: divide k0 itself, shift the bit index by pad / spb
+  const uint32_t* tabq = s_tab - (pad ? 2 : 0);
+  const uint32_t body_len = body_end - pad;
+  const uint32_t lim4 = lim & ~3u;
+  float* po = out + k0;
+  for (; k0 < lim4; k0 += stride, po += stride) {
+    float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // lead padding / tail silence stay zero (fsk.ts:392-395)
+    if (k0 - pad < body_len) {  // unsigned: also false for k0 < pad
+      const uint32_t e = tabq[q];
+      const uint32_t st = (e & 1u) ? st1 : st0;
+      const uint32_t p0 = (e & ~1u) + r * st;
+      v.x = sin_fix(p0); v.y = sin_fix(p0 + st); v.z = sin_fix(p0 + 2u * st); v.w = sin_fix(p0 + 3u * st);
+    }
+    __stcs(reinterpret_cast<float4*>(po), v);
+    q += dq; r += dr;
+    if (r >= spb) { r -= spb; ++q; }
+  }
+  // a row cut short by out_stride can end inside a float4
+  if (k0 < lim) {
+    float w[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    uint32_t qq, rr;
+    for (uint32_t i = 0; k0 + i < lim; ++i) {
+      const uint32_t k = k0 + i;
+      if (k - pad < body_len) {
+        mod_divmod(k - pad, spb, a.spb_magic, qq, rr);
+        const uint32_t e = s_tab[qq];
+        w[i] = sin_fix((e & ~1u) + rr * ((e & 1u) ? st1 : st0));
+      }
+      out[k] = w[i];
     }
   }
 }

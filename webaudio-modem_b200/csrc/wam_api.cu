@@ -863,8 +863,6 @@ static int modulate_device_group(wam_fsk_batch* b, const Group& g, const uint8_t
   a.step_fix[0] = (uint32_t)(unsigned long long)llround(fmod(g.d.space / g.d.fs, 1.0) * 4294967296.0);
   a.step_fix[1] = (uint32_t)(unsigned long long)llround(fmod(g.d.mark / g.d.fs, 1.0) * 4294967296.0);
   a.spb_magic = g.d.spb >= 2 ? (uint32_t)(4294967296ull / (unsigned long long)g.d.spb) : 0xffffffffu;
-  fsk_bit_phase_kernel<<<(unsigned)n_rows, kPhaseThreads, 0, st>>>(a);
-  CUDA_TRY(cudaGetLastError());
   const long max_total = std::min(modulate_size(g.d, max_bytes), out_stride);
   // blocks per row: whole rows per block when there are enough rows to fill the GPU, otherwise split rows
   const long per_pass = (long)kModThreads * 4;
@@ -872,6 +870,16 @@ static int modulate_device_group(wam_fsk_batch* b, const Group& g, const uint8_t
   long bx = (8L * 148 + n_rows - 1) / n_rows;
   bx = std::max(1L, std::min(bx, passes));
   dim3 grid((unsigned)bx, (unsigned)n_rows);
+  const size_t tab_bytes = sizeof(uint32_t) * (size_t)tab_stride;
+  if (a.vec_ok && g.d.spb % 4 == 0 && tab_bytes <= 40 * 1024 && g.d.bpb < 64) {
+    // one launch: every CTA builds its stream's phase table in shared memory
+    fsk_modulate_fused_kernel<<<grid, kModThreads, tab_bytes, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    b->launches += 1;
+    return WAM_OK;
+  }
+  fsk_bit_phase_kernel<<<(unsigned)n_rows, kPhaseThreads, 0, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
   if (a.vec_ok && g.d.spb % 4 == 0) fsk_modulate_kernel<true><<<grid, kModThreads, 0, st>>>(a);
   else fsk_modulate_kernel<false><<<grid, kModThreads, 0, st>>>(a);
   CUDA_TRY(cudaGetLastError());
