@@ -214,8 +214,7 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
         const int rk = sh.reset_k[lane];
         if (rk >= 0) {
           // FSKCore.resetState(), DSP side (fsk.ts:175-188): the lane restarts right after decimated sample rk
-          BState dummy;
-          reset_state(s, dummy);
+          reset_state_a2(s);
           lane_pos = sh.reset_tile;
           lane_kfrom = rk + 1;
         }
@@ -334,7 +333,6 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
     uint32_t* ring = ring_in_smem ? ring_s + lane : a.sync_ring + li;
     const long rstride = ring_in_smem ? 32 : ns;
     uint8_t* out_row = active ? a.out + (long)row * a.out_stride : nullptr;
-    A2State dummy;  // reset_state() inside the state machine also clears an A2State: the real one lives in warp 1
     int epoch = 0;
     unsigned spins = 0;
     bool alive = true;
@@ -359,7 +357,7 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
         int k_reset = -1;
         if (lane_busy) {
           const uint32_t bits = sh.bits[t % kPipeDec][lane];
-          k_reset = sm_tile_events<true>(dummy, b, bits, sh.amp[t % kPipeDec] + lane, b_from, nk, pos_t0, len_t0, slot_t0,
+          k_reset = sm_tile_events<true>(b, bits, sh.amp[t % kPipeDec] + lane, b_from, nk, pos_t0, len_t0, slot_t0,
                                          alen_t0, a, li, out_row, ring, rstride);
           if (k_reset < 0 || 2 * (k_reset + 1) >= v_hi) {
             // this lane is done with the tile: end-of-tile ring bookkeeping

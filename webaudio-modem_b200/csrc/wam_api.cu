@@ -326,7 +326,7 @@ static int atan_table_device(int device, const double2** out) {
 // Word-aligned frame-sync templates (see sync_mismatches in fsk_demod.cuh).
 static int build_sync_templates(Group& g) {
   FskDerived& d = g.d;
-  d.tmpl_expect = nullptr; d.tmpl_mask = nullptr; d.tmpl_words = 0; d.max_mismatch = -1;
+  d.tmpl_expect = nullptr; d.tmpl_mask = nullptr; d.tmpl_words = 0; d.max_mismatch = -1; d.tmpl0_words = 0;
   if (d.ring_fractional || d.total_bits <= 0) return WAM_OK;
   const int care = d.total_bits - d.dspb;  // the newest dspb samples (j == 0) never match
   const int W = (31 + care + 31) / 32;
@@ -347,6 +347,15 @@ static int build_sync_templates(Group& g) {
   d.tmpl_expect = g.tmpl;
   d.tmpl_mask = g.tmpl + (size_t)32 * W;
   d.tmpl_words = W;
+  const int W0 = (care + 31) / 32;  // offset 0: bit idx of the window sits at bit idx
+  d.tmpl0_words = 0;
+  if (W0 <= kTmpl0Words) {
+    d.tmpl0_words = W0;
+    for (int i = 0; i < kTmpl0Words; i++) {
+      d.tmpl0_expect[i] = i < W0 ? h[(size_t)i] : 0u;
+      d.tmpl0_mask[i] = i < W0 ? h[(size_t)32 * W + i] : 0u;
+    }
+  }
   d.max_mismatch = (d.min_matched == INT_MAX) ? -1 : care - d.min_matched;
   return WAM_OK;
 }

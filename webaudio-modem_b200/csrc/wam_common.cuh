@@ -7,6 +7,7 @@
 
 namespace wam {
 
+constexpr int kTmpl0Words = 80;     // by-value sync template: up to 2560 compared samples ((nbits - 1) * dspb)
 constexpr int kMaxPatternWords = 8;  // preamble+SFD template: up to 256 line bits
 constexpr int kTile = 32;            // samples per stream per staged tile (one 128-byte row)
 constexpr int kStages = 2;           // cp.async pipeline depth (per warp)
@@ -53,6 +54,12 @@ struct FskDerived {
   const uint32_t* tmpl_mask;
   int tmpl_words;
   int max_mismatch;     // care_bits - min_matched (negative: can never sync)
+  // the offset-0 template again, by value (constant bank): the search shifts the RING words into alignment
+  // (funnel shift by the window's bit offset) and compares against these, so the template reads are the same for
+  // every lane.  tmpl0_words == 0: template too long, use the per-offset tables above.
+  int tmpl0_words;      // ceil(compared samples / 32)
+  uint32_t tmpl0_expect[kTmpl0Words];
+  uint32_t tmpl0_mask[kTmpl0Words];
   const double2* atan_tab;  // device: {k / 64, atan(k / 64)}, k = 0..64
   // modulator (fsk.ts:389-424)
   double mark, space, fs;
