@@ -222,10 +222,25 @@ __device__ __forceinline__ int sync_mismatches0(const uint32_t* __restrict__ rin
   }
   return mism;
 }
+#ifdef WAM_SEARCH_STATS  // debug build (scripts/exp_search_stats.py)
+__device__ unsigned long long g_search_stats[52];
+#endif
 // out-of-line copy for the fused kernel (no registers to spare for an inlined search)
 __device__ __noinline__ int sync_mismatches0_call(const uint32_t* __restrict__ ring, long ns, uint32_t pos,
                                                   const FskDerived& d) {
+#ifdef WAM_SEARCH_STATS
+  // [0] warp-level calls, [1] lane searches, [4 + lanes] calls by number of active lanes, [40 + pos / 2400] calls by time
+  const unsigned am = __activemask();
+  if ((int)(threadIdx.x & 31) == __ffs((int)am) - 1) {
+    atomicAdd(&g_search_stats[0], 1ull);
+    atomicAdd(&g_search_stats[4 + __popc(am)], 1ull);
+    atomicAdd(&g_search_stats[40 + min(pos / 2400u, 11u)], 1ull);
+  }
+  atomicAdd(&g_search_stats[1], 1ull);
   return sync_mismatches0<true>(ring, ns, pos, d);
+#else
+  return sync_mismatches0<true>(ring, ns, pos, d);
+#endif
 }
 
 // ---- literal emulation of RingBuffer with a fractional capacity (utils.ts:14-47) ----

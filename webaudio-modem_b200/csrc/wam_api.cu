@@ -1450,3 +1450,11 @@ extern "C" int wam_host_free(void* p) {
 
 // definitions of the helpers declared in filters.cuh that need fail()/CUDA_TRY
 #include "filters_host.inl"
+
+#ifdef WAM_SEARCH_STATS
+extern "C" int wam_debug_search_stats(unsigned long long* out52, int clear) {
+  if (out52) cudaMemcpyFromSymbol(out52, wam::g_search_stats, sizeof(unsigned long long) * 52);
+  if (clear) { unsigned long long z[52] = {0}; cudaMemcpyToSymbol(wam::g_search_stats, z, sizeof(z)); }
+  return 0;
+}
+#endif
