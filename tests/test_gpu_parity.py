@@ -141,6 +141,26 @@ def test_batch_awgn_sweep_matches_oracle(gpu_wam, oracle, cfg):
     assert sum(len(w) for w in want) > 0
 
 
+@pytest.mark.parametrize("preamble,force_fused", [([0x55] * 4, True), ([0x55] * 4, False), ([0x55, 0x55, 0xAA], True)])
+def test_long_sync_template_falls_back_to_offset_tables(gpu_wam, oracle, preamble, force_fused):
+    """The frame search compares against ONE template passed by value (up to 80 words = 2560 compared samples).
+    A 4-byte preamble at 300 Bd needs (50 - 1) * 80 = 3920 samples: both kernels must take the per-offset tables in
+    global memory instead and still agree with the oracle; a 3-byte preamble (3120 samples = 98 words) likewise."""
+    cfg = dict(baudRate=300, preamblePattern=preamble)
+    n_streams, n = 64, 56000
+    snr = np.repeat(np.array([-6.0, 0.0, 6.0, 30.0]), n_streams // 4)
+    x, _ = siggen.noisy_streams(cfg, n_streams, n, 20, snr, seed=77)
+    want, ost = oracle.batch_demodulate([cfg], None, x.copy(), n_threads=8)
+    b = gpu_wam.FSKBatch(n_streams, cfg)
+    got = b.demodulate_bytes(x, flags=gpu_wam._lib.WAM_BATCH_NO_PIPELINE if force_fused else 0)
+    gst = b.status()
+    bad = [i for i in range(n_streams) if got[i] != want[i]]
+    assert not bad, f"{len(bad)} streams differ, first {bad[:5]}"
+    for i in range(n_streams):
+        assert_status_equal(gst[i], ost[i], f"stream {i}")
+    assert sum(st["syncDetections"] for st in ost) > 0 and sum(len(w) for w in want) > 0
+
+
 def test_batch_two_configs_and_streaming_state(gpu_wam, oracle):
     """V.21 ch1 + ch2 in one batch (config 2 layout), fed in 3 unequal slabs: the device-resident
     state must carry across calls exactly like one FSKCore per stream."""
