@@ -223,8 +223,7 @@ def run_reference(args):
         return 0
     cores = host_cores()
     threads = cores
-    # bounded sample: about 1-2 s of CPU work per step per thread
-    n_streams = max(32, min(4096, threads * 8))
+    n_streams = max(32, min(4096, threads * 32))  # bounded sample: about 1.5 s of CPU work per step
     total, times, bits = cpu_reference_run(n_streams, args.steps, min(args.warmup, 1), threads)
     t = sum(times)
     value = total * len(times) / t / 1e6
