@@ -150,6 +150,22 @@ __device__ __forceinline__ void ring_st(uint32_t* p, uint32_t v) { *p = v; }
 __device__ __forceinline__ void amp_st(float* p, float v) { *p = v; }
 #endif
 
+// Sync rings in global memory: [stream][ring_words], a stream's words contiguous (the frame search reads four
+// at a time); in shared memory (pipelined kernel) [word][lane].  Word w of a ring is ring[w * rstride].
+__device__ __forceinline__ uint32_t* ring_of(const DemodArgs& a, int li) {
+  return a.sync_ring + (size_t)li * (size_t)a.d.ring_words;
+}
+__device__ __forceinline__ uint4 ring_ld4(const uint32_t* p) {  // 16-byte aligned group of four ring words
+#ifndef WAM_AB_NO_L2HINT
+  uint4 v;
+  asm("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(l2_evict_last()) : "memory");
+  return v;
+#else
+  return *reinterpret_cast<const uint4*>(p);
+#endif
+}
+
 // Frame-sync template match, integral-capacity ring — fsk.ts:303-312.
 // The reference compares the newest nbits*dspb ring samples with preambleSfdBits[nbits - j] for
 // window j (j*dspb .. (j+1)*dspb-1 samples back); j == 0 compares against `undefined` and never
@@ -198,27 +214,56 @@ __device__ __forceinline__ int sync_mismatches0(const uint32_t* __restrict__ rin
   const uint32_t lo = pos - (uint32_t)d.total_bits;
   const uint32_t o = lo & 31u;
   const uint32_t wmask = (uint32_t)(d.ring_words - 1);
+  const uint32_t st = (uint32_t)ns;  // ring_words * streams < 2^31 words: 32-bit element indices
   uint32_t w = (lo >> 5) & wmask;
-  uint32_t prev = ring_ld<GLOBAL>(ring + (long)w * ns, keep);
+  uint32_t prev = ring_ld<GLOBAL>(ring + w * st, keep);
   int mism = 0;
   int i = 0;
   for (; i + R <= d.tmpl0_words; i += R) {
     uint32_t r[R];
 #pragma unroll
-    for (int j = 0; j < R; ++j) r[j] = ring_ld<GLOBAL>(ring + (long)((w + 1 + j) & wmask) * ns, keep);
+    for (int j = 0; j < R; ++j) r[j] = ring_ld<GLOBAL>(ring + ((w + 1u + (uint32_t)j) & wmask) * st, keep);
 #pragma unroll
     for (int j = 0; j < R; ++j) {
-      mism += __popc((__funnelshift_r(prev, r[j], o) ^ d.tmpl0_expect[i + j]) & d.tmpl0_mask[i + j]);
+      mism += __popc((__funnelshift_r(prev, r[j], o) ^ d.tmpl0_expect[4 + i + j]) & d.tmpl0_mask[4 + i + j]);
       prev = r[j];
     }
     w += R;
     if (mism > d.max_mismatch) return mism;  // cannot reach the threshold any more
   }
   for (; i < d.tmpl0_words; ++i) {
-    const uint32_t r1 = ring_ld<GLOBAL>(ring + (long)((w + 1) & wmask) * ns, keep);
-    mism += __popc((__funnelshift_r(prev, r1, o) ^ d.tmpl0_expect[i]) & d.tmpl0_mask[i]);
+    const uint32_t r1 = ring_ld<GLOBAL>(ring + ((w + 1u) & wmask) * st, keep);
+    mism += __popc((__funnelshift_r(prev, r1, o) ^ d.tmpl0_expect[4 + i]) & d.tmpl0_mask[4 + i]);
     prev = r1;
     ++w;
+  }
+  return mism;
+}
+// The same for a contiguous ring (global memory): aligned groups of four ring words per 16-byte load.  x_n = ring
+// word (g + n) with g the aligned group holding the window's first word, s = first word's place in its group;
+// window word i is the funnel shift of (x_{s+i}, x_{s+i+1}) and meets template word i, stored at [i + 4] behind four
+// all-zero words so that the pairs in front of the window (i < 0) are masked out without a branch.
+__device__ __forceinline__ int sync_mismatches0v(const uint32_t* __restrict__ ring, uint32_t pos, const FskDerived& d) {
+  const uint32_t lo = pos - (uint32_t)d.total_bits;
+  const uint32_t o = lo & 31u;
+  const uint32_t wmask = (uint32_t)(d.ring_words - 1);
+  const uint32_t w = (lo >> 5) & wmask;
+  const uint32_t s = w & 3u;
+  uint32_t g = w & ~3u;
+  const int n_end = (int)s + d.tmpl0_words;  // pairs n = 0 .. n_end - 1 carry compared samples
+  const uint32_t* __restrict__ ex = d.tmpl0_expect + 4 - (int)s;  // pair n meets template word n - s
+  const uint32_t* __restrict__ mk = d.tmpl0_mask + 4 - (int)s;
+  uint32_t prev = 0u;
+  int mism = 0;
+  for (int n = -1; n < n_end; n += 4) {  // pairs (prev, x_{n+1}) = n, n + 1, n + 2, n + 3
+    const uint4 v = ring_ld4(ring + g);
+    g = (g + 4u) & wmask;
+    mism += __popc((__funnelshift_r(prev, v.x, o) ^ ex[n]) & mk[n]) +
+            __popc((__funnelshift_r(v.x, v.y, o) ^ ex[n + 1]) & mk[n + 1]) +
+            __popc((__funnelshift_r(v.y, v.z, o) ^ ex[n + 2]) & mk[n + 2]) +
+            __popc((__funnelshift_r(v.z, v.w, o) ^ ex[n + 3]) & mk[n + 3]);
+    prev = v.w;
+    if (mism > d.max_mismatch) return mism;  // cannot reach the threshold any more
   }
   return mism;
 }
@@ -226,8 +271,7 @@ __device__ __forceinline__ int sync_mismatches0(const uint32_t* __restrict__ rin
 __device__ unsigned long long g_search_stats[52];
 #endif
 // out-of-line copy for the fused kernel (no registers to spare for an inlined search)
-__device__ __noinline__ int sync_mismatches0_call(const uint32_t* __restrict__ ring, long ns, uint32_t pos,
-                                                  const FskDerived& d) {
+__device__ __noinline__ int sync_mismatches0_call(const uint32_t* __restrict__ ring, uint32_t pos, const FskDerived& d) {
 #ifdef WAM_SEARCH_STATS
   // [0] warp-level calls, [1] lane searches, [4 + lanes] calls by number of active lanes, [40 + pos / 2400] calls by time
   const unsigned am = __activemask();
@@ -237,9 +281,9 @@ __device__ __noinline__ int sync_mismatches0_call(const uint32_t* __restrict__ r
     atomicAdd(&g_search_stats[40 + min(pos / 2400u, 11u)], 1ull);
   }
   atomicAdd(&g_search_stats[1], 1ull);
-  return sync_mismatches0<true>(ring, ns, pos, d);
+  return sync_mismatches0v(ring, pos, d);
 #else
-  return sync_mismatches0<true>(ring, ns, pos, d);
+  return sync_mismatches0v(ring, pos, d);
 #endif
 }
 
@@ -260,7 +304,7 @@ __device__ __noinline__ bool ring_put_fractional(double* __restrict__ f64, long 
   double wi = f64[F_RING_WI * ns], ri = f64[F_RING_RI * ns], flen = f64[F_RING_LEN * ns];
   int ip;
   if (ring_index_valid(wi, d.ring_cap_int, ip)) {
-    uint32_t* w = ring + (long)(ip >> 5) * ns;
+    uint32_t* w = ring + (ip >> 5);
     *w = (*w & ~(1u << (ip & 31))) | ((uint32_t)bit << (ip & 31));
   }
   wi = ring_fmod_cap(wi + 1.0, d.ring_cap);
@@ -285,7 +329,7 @@ __device__ __noinline__ int sync_matched_fractional(const double* __restrict__ f
       if (j == 0) {
         matched += valid ? 0 : 1;  // undefined === undefined (fsk.ts:306-307)
       } else if (valid) {
-        const int bit = (ring[(long)(ip >> 5) * ns] >> (ip & 31)) & 1;
+        const int bit = (ring[ip >> 5] >> (ip & 31)) & 1;
         matched += (bit == expect);
       }
     }
@@ -345,8 +389,8 @@ __device__ __forceinline__ bool sm_step(BState& b, int bit, double amplitude, ui
   const FskDerived& d = a.d;
   const long ns = a.n_local;
   // RING_ARG: the caller keeps this stream's sync ring somewhere else (shared memory); otherwise the state array
-  uint32_t* ring = RING_ARG ? ring_arg : a.sync_ring + li;
-  const long rstride = RING_ARG ? rstride_arg : ns;
+  uint32_t* ring = RING_ARG ? ring_arg : ring_of(a, li);
+  const long rstride = RING_ARG ? rstride_arg : 1;
   // silence / EOD — fsk.ts:285-295
   b.gsc++;
   b.gmod = (b.gmod + 1u == (uint32_t)d.check_period) ? 0u : b.gmod + 1u;
@@ -370,7 +414,12 @@ __device__ __forceinline__ bool sm_step(BState& b, int bit, double amplitude, ui
           ring_st<!RING_ARG>(ring + (long)((b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * rstride, b.cur_word);
         int mism;
         if (d.tmpl0_words > 0) {  // by-value template + funnel shift (templates up to kTmpl0Words words)
-          mism = RING_ARG ? sync_mismatches0<false>(ring, rstride, ring_pos, d) : sync_mismatches0_call(ring, rstride, ring_pos, d);
+                    // RING_ARG (pipelined kernel): the ring may be in shared memory ([word][lane]) -> word-by-word walk
+#ifdef WAM_SYNC_INLINE
+          mism = RING_ARG ? sync_mismatches0<false>(ring, rstride, ring_pos, d) : sync_mismatches0v(ring, ring_pos, d);
+#else
+          mism = RING_ARG ? sync_mismatches0<false>(ring, rstride, ring_pos, d) : sync_mismatches0_call(ring, ring_pos, d);
+#endif
         } else {
           mism = sync_mismatches(ring, rstride, ring_pos, d);
         }
@@ -410,14 +459,14 @@ __device__ __forceinline__ bool sm_sample_generic(BState& b, int bit, double amp
                                                   const DemodArgs& a, int li, uint8_t* out_row) {
   const FskDerived& d = a.d;
   const long ns = a.n_local;
-  uint32_t* ring = a.sync_ring + li;
+  uint32_t* ring = ring_of(a, li);
   bool ready;
   // syncSamplesBuffer.put(bit) — fsk.ts:281
   if (!d.ring_fractional) {
     b.cur_word |= (uint32_t)bit << (b.ring_pos & 31u);
     b.ring_pos++;
     if ((b.ring_pos & 31u) == 0u) {
-      ring[(long)(((b.ring_pos - 1u) >> 5) & (uint32_t)(d.ring_words - 1)) * ns] = b.cur_word;
+      ring[((b.ring_pos - 1u) >> 5) & (uint32_t)(d.ring_words - 1)] = b.cur_word;
       b.cur_word = 0u;
     }
     b.ring_len = min(b.ring_len + 1u, (uint32_t)d.ring_cap_int);
@@ -446,8 +495,8 @@ __device__ __forceinline__ int sm_tile_events(BState& b, uint32_t bits, const do
   // the caller's copy (shared memory in fsk_demod_pipe_kernel)
   const FskDerived& d = a.d;
   const long ns = a.n_local;
-  uint32_t* ring = RING_ARG ? ring_arg : a.sync_ring + li;
-  const long rstride = RING_ARG ? rstride_arg : ns;
+  uint32_t* ring = RING_ARG ? ring_arg : ring_of(a, li);
+  const long rstride = RING_ARG ? rstride_arg : 1;
   float* aring = a.amp_ring + li;
   const uint32_t wmask = (uint32_t)(d.ring_words - 1);
 
@@ -783,7 +832,7 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
     b.out_n = a.append ? a.out_len[row] : 0;
     b.cur_word = 0u;
     if (!d.ring_fractional && (b.ring_pos & 31u) != 0u) {
-      const uint32_t w = a.sync_ring[(long)((b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns + li];
+      const uint32_t w = ring_of(a, li)[(b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)];
       b.cur_word = w & ((1u << (b.ring_pos & 31u)) - 1u);
     }
     b_store(b, park_d, park_u, lane);
@@ -997,7 +1046,7 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
     u[U_RING_POS * ns] = b.ring_pos; u[U_RING_LEN * ns] = b.ring_len;
     u[U_AMP_POS * ns] = b.amp_pos; u[U_AMP_LEN * ns] = b.amp_len;
     if (!d.ring_fractional && (b.ring_pos & 31u) != 0u)
-      a.sync_ring[(long)((b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns + li] = b.cur_word;
+      ring_of(a, li)[(b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)] = b.cur_word;
     a.out_len[row] = b.out_n < a.out_stride ? b.out_n : (int)a.out_stride;
     if (GENERIC && a.n_valid) ragged_account(a, li, n_l);
   }

@@ -323,15 +323,15 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
       b.amp_pos = u[U_AMP_POS * ns]; b.amp_len = u[U_AMP_LEN * ns];
       b.out_n = a.append ? a.out_len[row] : 0;
       if ((b.ring_pos & 31u) != 0u) {
-        const uint32_t w = a.sync_ring[(long)((b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns + li];
+        const uint32_t w = ring_of(a, li)[(b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)];
         b.cur_word = w & ((1u << (b.ring_pos & 31u)) - 1u);
       }
       if (ring_in_smem)
-        for (int w = 0; w < d.ring_words; ++w) ring_s[w * 32 + lane] = a.sync_ring[(long)w * ns + li];
+        for (int w = 0; w < d.ring_words; ++w) ring_s[w * 32 + lane] = ring_of(a, li)[w];
     }
     __syncwarp();
-    uint32_t* ring = ring_in_smem ? ring_s + lane : a.sync_ring + li;
-    const long rstride = ring_in_smem ? 32 : ns;
+    uint32_t* ring = ring_in_smem ? ring_s + lane : ring_of(a, li);
+    const long rstride = ring_in_smem ? 32 : 1;
     uint8_t* out_row = active ? a.out + (long)row * a.out_stride : nullptr;
     int epoch = 0;
     unsigned spins = 0;
@@ -408,9 +408,9 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
       u[U_RING_POS * ns] = b.ring_pos; u[U_RING_LEN * ns] = b.ring_len;
       u[U_AMP_POS * ns] = b.amp_pos; u[U_AMP_LEN * ns] = b.amp_len;
       if (ring_in_smem)
-        for (int w = 0; w < d.ring_words; ++w) a.sync_ring[(long)w * ns + li] = ring_s[w * 32 + lane];
+        for (int w = 0; w < d.ring_words; ++w) ring_of(a, li)[w] = ring_s[w * 32 + lane];
       if ((b.ring_pos & 31u) != 0u)
-        a.sync_ring[(long)((b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)) * ns + li] = b.cur_word;
+        ring_of(a, li)[(b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1)] = b.cur_word;
       a.out_len[row] = b.out_n < a.out_stride ? b.out_n : (int)a.out_stride;
       if (a.n_valid) ragged_account(a, li, n_l);
       if (sh.abort_flag) u[(long)U_ERR * ns] |= WAM_ERR_PIPE_TIMEOUT;

@@ -351,9 +351,10 @@ static int build_sync_templates(Group& g) {
   d.tmpl0_words = 0;
   if (W0 <= kTmpl0Words) {
     d.tmpl0_words = W0;
-    for (int i = 0; i < kTmpl0Words; i++) {
-      d.tmpl0_expect[i] = i < W0 ? h[(size_t)i] : 0u;
-      d.tmpl0_mask[i] = i < W0 ? h[(size_t)32 * W + i] : 0u;
+    for (int i = 0; i < 4 + kTmpl0Words + 4; i++) {
+      const int wi = i - 4;
+      d.tmpl0_expect[i] = (wi >= 0 && wi < W0) ? h[(size_t)wi] : 0u;
+      d.tmpl0_mask[i] = (wi >= 0 && wi < W0) ? h[(size_t)32 * W + wi] : 0u;
     }
   }
   d.max_mismatch = (d.min_matched == INT_MAX) ? -1 : care - d.min_matched;

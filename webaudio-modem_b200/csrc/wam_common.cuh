@@ -58,8 +58,8 @@ struct FskDerived {
   // (funnel shift by the window's bit offset) and compares against these, so the template reads are the same for
   // every lane.  tmpl0_words == 0: template too long, use the per-offset tables above.
   int tmpl0_words;      // ceil(compared samples / 32)
-  uint32_t tmpl0_expect[kTmpl0Words];
-  uint32_t tmpl0_mask[kTmpl0Words];
+  uint32_t tmpl0_expect[4 + kTmpl0Words + 4];  // word i at [4 + i]; the words around it are zero with a zero mask
+  uint32_t tmpl0_mask[4 + kTmpl0Words + 4];
   const double2* atan_tab;  // device: {k / 64, atan(k / 64)}, k = 0..64
   // modulator (fsk.ts:389-424)
   double mark, space, fs;
@@ -93,7 +93,7 @@ struct DemodArgs {
   // state
   double* f64;
   uint32_t* u32;
-  uint32_t* sync_ring;  // [ring_words][n_local]
+  uint32_t* sync_ring;  // [n_local][ring_words] (see ring_of)
   float* amp_ring;      // [amp_phys][n_local]
   // data
   float* samples;       // [rows][stride]
