@@ -253,17 +253,32 @@ __device__ __forceinline__ int sync_mismatches0v(const uint32_t* __restrict__ ri
   const int n_end = (int)s + d.tmpl0_words;  // pairs n = 0 .. n_end - 1 carry compared samples
   const uint32_t* __restrict__ ex = d.tmpl0_expect + 4 - (int)s;  // pair n meets template word n - s
   const uint32_t* __restrict__ mk = d.tmpl0_mask + 4 - (int)s;
-  uint32_t prev = 0u;
-  int mism = 0;
-  for (int n = -1; n < n_end; n += 4) {  // pairs (prev, x_{n+1}) = n, n + 1, n + 2, n + 3
-    const uint4 v = ring_ld4(ring + g);
+  // first group: pairs -1 .. 2, some of them in front of the window (zero mask)
+  uint4 v = ring_ld4(ring + g);
+  g = (g + 4u) & wmask;
+  int mism = __popc((__funnelshift_r(v.x, v.y, o) ^ ex[0]) & mk[0]) + __popc((__funnelshift_r(v.y, v.z, o) ^ ex[1]) & mk[1]) +
+             __popc((__funnelshift_r(v.z, v.w, o) ^ ex[2]) & mk[2]);
+  uint32_t prev = v.w;
+  int n = 3;
+  // interior groups: all four window words are compared in full (mask ~0): no mask words to fetch
+  const int n_full = (int)s + d.tmpl0_full;  // pairs below n_full meet all-ones mask words
+  for (; n + 4 <= n_full; n += 4) {
+    v = ring_ld4(ring + g);
+    g = (g + 4u) & wmask;
+    mism += __popc(__funnelshift_r(prev, v.x, o) ^ ex[n]) + __popc(__funnelshift_r(v.x, v.y, o) ^ ex[n + 1]) +
+            __popc(__funnelshift_r(v.y, v.z, o) ^ ex[n + 2]) + __popc(__funnelshift_r(v.z, v.w, o) ^ ex[n + 3]);
+    prev = v.w;
+    if (mism > d.max_mismatch) return mism;  // cannot reach the threshold any more
+  }
+  // last groups: the partial word at the end of the window and the words behind it (zero mask)
+  for (; n < n_end; n += 4) {
+    v = ring_ld4(ring + g);
     g = (g + 4u) & wmask;
     mism += __popc((__funnelshift_r(prev, v.x, o) ^ ex[n]) & mk[n]) +
             __popc((__funnelshift_r(v.x, v.y, o) ^ ex[n + 1]) & mk[n + 1]) +
             __popc((__funnelshift_r(v.y, v.z, o) ^ ex[n + 2]) & mk[n + 2]) +
             __popc((__funnelshift_r(v.z, v.w, o) ^ ex[n + 3]) & mk[n + 3]);
     prev = v.w;
-    if (mism > d.max_mismatch) return mism;  // cannot reach the threshold any more
   }
   return mism;
 }

@@ -326,7 +326,7 @@ static int atan_table_device(int device, const double2** out) {
 // Word-aligned frame-sync templates (see sync_mismatches in fsk_demod.cuh).
 static int build_sync_templates(Group& g) {
   FskDerived& d = g.d;
-  d.tmpl_expect = nullptr; d.tmpl_mask = nullptr; d.tmpl_words = 0; d.max_mismatch = -1; d.tmpl0_words = 0;
+  d.tmpl_expect = nullptr; d.tmpl_mask = nullptr; d.tmpl_words = 0; d.max_mismatch = -1; d.tmpl0_words = 0; d.tmpl0_full = 0;
   if (d.ring_fractional || d.total_bits <= 0) return WAM_OK;
   const int care = d.total_bits - d.dspb;  // the newest dspb samples (j == 0) never match
   const int W = (31 + care + 31) / 32;
@@ -351,6 +351,7 @@ static int build_sync_templates(Group& g) {
   d.tmpl0_words = 0;
   if (W0 <= kTmpl0Words) {
     d.tmpl0_words = W0;
+    d.tmpl0_full = care / 32;
     for (int i = 0; i < 4 + kTmpl0Words + 4; i++) {
       const int wi = i - 4;
       d.tmpl0_expect[i] = (wi >= 0 && wi < W0) ? h[(size_t)wi] : 0u;

@@ -58,6 +58,7 @@ struct FskDerived {
   // (funnel shift by the window's bit offset) and compares against these, so the template reads are the same for
   // every lane.  tmpl0_words == 0: template too long, use the per-offset tables above.
   int tmpl0_words;      // ceil(compared samples / 32)
+  int tmpl0_full;       // floor(compared samples / 32): template words whose mask is all ones
   uint32_t tmpl0_expect[4 + kTmpl0Words + 4];  // word i at [4 + i]; the words around it are zero with a zero mask
   uint32_t tmpl0_mask[4 + kTmpl0Words + 4];
   const double2* atan_tab;  // device: {k / 64, atan(k / 64)}, k = 0..64
