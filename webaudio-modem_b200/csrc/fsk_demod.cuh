@@ -141,6 +141,7 @@ __device__ __forceinline__ void ring_st(uint32_t* p, uint32_t v) {
   asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(l2_evict_last()) : "memory");
 }
 __device__ __forceinline__ void amp_st(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void amp_st4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
 #else
 __device__ __forceinline__ uint64_t l2_evict_last() { return 0; }
 template <bool GLOBAL>
@@ -148,6 +149,7 @@ __device__ __forceinline__ uint32_t ring_ld(const uint32_t* p, uint64_t) { retur
 template <bool GLOBAL>
 __device__ __forceinline__ void ring_st(uint32_t* p, uint32_t v) { *p = v; }
 __device__ __forceinline__ void amp_st(float* p, float v) { *p = v; }
+__device__ __forceinline__ void amp_st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 #endif
 
 // Sync rings in global memory: [stream][ring_words], a stream's words contiguous (the frame search reads four
@@ -380,16 +382,36 @@ __device__ __forceinline__ bool process_byte(BState& b, int bit, const DemodArgs
   return false;
 }
 
+// Amplitude rings in global memory: [stream][amp_phys] float32, a stream's slots contiguous (amp_phys is a multiple
+// of 8, so rows are 16-byte aligned): a full tile's 16 amplitudes go out as four 16-byte stores, and the mean at a
+// sync detection reads 16 bytes at a time.
+__device__ __forceinline__ float* amp_of(const DemodArgs& a, int li) {
+  return a.amp_ring + (size_t)li * (size_t)a.d.amp_phys;
+}
+
 // silence threshold = mean(amplitude ring) * 0.1, summed oldest -> newest in f64 — fsk.ts:321-326.
 // amp_next = physical slot following the newest entry; the ring has amp_phys physical slots of
-// which the newest amp_len (<= amp_cap) are the reference's ring contents.
-__device__ __noinline__ double amp_ring_threshold(const float* __restrict__ aring, long ns, uint32_t amp_next,
-                                                  uint32_t amp_len, uint32_t amp_phys) {
+// which the newest amp_len (<= amp_cap) are the reference's ring contents.  `row` = this stream's slots.
+__device__ __noinline__ double amp_ring_threshold(const float* __restrict__ row, uint32_t amp_next, uint32_t amp_len,
+                                                  uint32_t amp_phys) {
   double sum = 0.0;
   uint32_t slot = (amp_next + amp_phys - amp_len) % amp_phys;
-  for (uint32_t i = 0; i < amp_len; ++i) {
-    sum += (double)aring[(long)slot * ns];
+  uint32_t left = amp_len;
+  while (left > 0u && (slot & 3u) != 0u) {
+    sum += (double)row[slot];
     slot = (slot + 1u == amp_phys) ? 0u : slot + 1u;
+    --left;
+  }
+  while (left >= 4u) {  // slot is a multiple of 4 and so is amp_phys: a group never straddles the end
+    const float4 v = *reinterpret_cast<const float4*>(row + slot);
+    sum += (double)v.x; sum += (double)v.y; sum += (double)v.z; sum += (double)v.w;  // same order as one by one
+    slot = (slot + 4u == amp_phys) ? 0u : slot + 4u;
+    left -= 4u;
+  }
+  while (left > 0u) {
+    sum += (double)row[slot];
+    slot = (slot + 1u == amp_phys) ? 0u : slot + 1u;
+    --left;
   }
   return (sum / (double)amp_len) * 0.1;
 }
@@ -447,7 +469,7 @@ __device__ __forceinline__ bool sm_step(BState& b, int bit, double amplitude, ui
         b.current = 0; b.bitpos = 0;
         b.bit_acc = 0; b.bit_cnt = 0; b.bsc = 0; b.next_idx = 0;
         a.u32[(long)U_SYNC_DET * ns + li]++;
-        b.sil_thr = amp_ring_threshold(a.amp_ring + li, ns, amp_next, amp_len, (uint32_t)d.amp_phys);
+        b.sil_thr = amp_ring_threshold(amp_of(a, li), amp_next, amp_len, (uint32_t)d.amp_phys);
         thr_changed = true;
       }
     }
@@ -490,7 +512,7 @@ __device__ __forceinline__ bool sm_sample_generic(BState& b, int bit, double amp
     ready = ring_put_fractional(a.f64 + li, ns, ring, bit, d);
   }
   // syncAmplitudeBuffer.put(amplitude) — fsk.ts:282 (Float32Array store)
-  a.amp_ring[(long)b.amp_pos * ns + li] = (float)amplitude;
+  amp_of(a, li)[b.amp_pos] = (float)amplitude;
   b.amp_pos = (b.amp_pos + 1u == (uint32_t)d.amp_phys) ? 0u : b.amp_pos + 1u;
   b.amp_len = min(b.amp_len + 1u, (uint32_t)d.amp_cap);
   bool thr_changed = false;
@@ -512,7 +534,7 @@ __device__ __forceinline__ int sm_tile_events(BState& b, uint32_t bits, const do
   const long ns = a.n_local;
   uint32_t* ring = RING_ARG ? ring_arg : ring_of(a, li);
   const long rstride = RING_ARG ? rstride_arg : 1;
-  float* aring = a.amp_ring + li;
+  float* aring = amp_of(a, li);
   const uint32_t wmask = (uint32_t)(d.ring_words - 1);
 
   uint32_t silent = 0u;
@@ -539,15 +561,25 @@ __device__ __forceinline__ int sm_tile_events(BState& b, uint32_t bits, const do
       // amplitude-ring puts (fsk.ts:282, Float32Array store) and the silence flags for the current threshold
       // (fsk.ts:286) from the same shared-memory reads; the ring wraps at most once inside a tile
       const double thr = b.sil_thr;
-      float* p = aring + (long)slot * ns;
-      int until_wrap = d.amp_phys - (int)slot;
+      if (b_from == 0 && nk == kTile / 2 && (slot & 3u) == 0u && slot + (uint32_t)(kTile / 2) <= (uint32_t)d.amp_phys) {
+        // a whole tile into aligned slots: four 16-byte streaming stores
+#pragma unroll
+        for (int q = 0; q < kTile / 8; ++q) {
+          const double a0 = amp[(4 * q) * 32], a1 = amp[(4 * q + 1) * 32], a2 = amp[(4 * q + 2) * 32], a3 = amp[(4 * q + 3) * 32];
+          amp_st4(aring + slot + 4 * q, make_float4((float)a0, (float)a1, (float)a2, (float)a3));
+          silent |= ((a0 < thr ? 1u : 0u) | (a1 < thr ? 2u : 0u) | (a2 < thr ? 4u : 0u) | (a3 < thr ? 8u : 0u)) << (4 * q);
+        }
+      } else {
+        float* p = aring + slot;
+        int until_wrap = d.amp_phys - (int)slot;
 #pragma unroll 4
-      for (int k = b_from; k < nk; ++k) {
-        const double av = amp[k * 32];
-        amp_st(p, (float)av);
-        p += ns;
-        if (--until_wrap == 0) p = aring;
-        silent |= (av < thr ? 1u : 0u) << k;
+        for (int k = b_from; k < nk; ++k) {
+          const double av = amp[k * 32];
+          amp_st(p, (float)av);
+          ++p;
+          if (--until_wrap == 0) p = aring;
+          silent |= (av < thr ? 1u : 0u) << k;
+        }
       }
     }
   }

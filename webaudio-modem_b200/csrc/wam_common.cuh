@@ -95,7 +95,7 @@ struct DemodArgs {
   double* f64;
   uint32_t* u32;
   uint32_t* sync_ring;  // [n_local][ring_words] (see ring_of)
-  float* amp_ring;      // [amp_phys][n_local]
+  float* amp_ring;      // [n_local][amp_phys] (see amp_of)
   // data
   float* samples;       // [rows][stride]
   long stride;
