@@ -245,6 +245,10 @@ __device__ __forceinline__ int sync_mismatches0(const uint32_t* __restrict__ rin
 // word (g + n) with g the aligned group holding the window's first word, s = first word's place in its group;
 // window word i is the funnel shift of (x_{s+i}, x_{s+i+1}) and meets template word i, stored at [i + 4] behind four
 // all-zero words so that the pairs in front of the window (i < 0) are masked out without a branch.
+// __constant__ copies of the by-value templates, [slot][expect | mask][4 + kTmpl0Words + 4] (host: tmpl_slot_acquire)
+__constant__ uint32_t c_tmpl[kTmplSlots][2][4 + kTmpl0Words + 4];
+
+template <bool CONST_SLOT>
 __device__ __forceinline__ int sync_mismatches0v(const uint32_t* __restrict__ ring, uint32_t pos, const FskDerived& d) {
   const uint32_t lo = pos - (uint32_t)d.total_bits;
   const uint32_t o = lo & 31u;
@@ -253,8 +257,9 @@ __device__ __forceinline__ int sync_mismatches0v(const uint32_t* __restrict__ ri
   const uint32_t s = w & 3u;
   uint32_t g = w & ~3u;
   const int n_end = (int)s + d.tmpl0_words;  // pairs n = 0 .. n_end - 1 carry compared samples
-  const uint32_t* __restrict__ ex = d.tmpl0_expect + 4 - (int)s;  // pair n meets template word n - s
-  const uint32_t* __restrict__ mk = d.tmpl0_mask + 4 - (int)s;
+  // pair n meets template word n - s; CONST_SLOT: read through the constant cache (LDC), otherwise generic loads
+  const uint32_t* __restrict__ ex = (CONST_SLOT ? c_tmpl[d.tmpl_slot][0] : d.tmpl0_expect) + 4 - (int)s;
+  const uint32_t* __restrict__ mk = (CONST_SLOT ? c_tmpl[d.tmpl_slot][1] : d.tmpl0_mask) + 4 - (int)s;
   // first group: pairs -1 .. 2, some of them in front of the window (zero mask)
   uint4 v = ring_ld4(ring + g);
   g = (g + 4u) & wmask;
@@ -298,10 +303,9 @@ __device__ __noinline__ int sync_mismatches0_call(const uint32_t* __restrict__ r
     atomicAdd(&g_search_stats[40 + min(pos / 2400u, 11u)], 1ull);
   }
   atomicAdd(&g_search_stats[1], 1ull);
-  return sync_mismatches0v(ring, pos, d);
-#else
-  return sync_mismatches0v(ring, pos, d);
 #endif
+  if (d.tmpl_slot >= 0) return sync_mismatches0v<true>(ring, pos, d);
+  return sync_mismatches0v<false>(ring, pos, d);
 }
 
 // ---- literal emulation of RingBuffer with a fractional capacity (utils.ts:14-47) ----
@@ -453,7 +457,7 @@ __device__ __forceinline__ bool sm_step(BState& b, int bit, double amplitude, ui
         if (d.tmpl0_words > 0) {  // by-value template + funnel shift (templates up to kTmpl0Words words)
                     // RING_ARG (pipelined kernel): the ring may be in shared memory ([word][lane]) -> word-by-word walk
 #ifdef WAM_SYNC_INLINE
-          mism = RING_ARG ? sync_mismatches0<false>(ring, rstride, ring_pos, d) : sync_mismatches0v(ring, ring_pos, d);
+          mism = RING_ARG ? sync_mismatches0<false>(ring, rstride, ring_pos, d) : sync_mismatches0v<false>(ring, ring_pos, d);
 #else
           mism = RING_ARG ? sync_mismatches0<false>(ring, rstride, ring_pos, d) : sync_mismatches0_call(ring, ring_pos, d);
 #endif

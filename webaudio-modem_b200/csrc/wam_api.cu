@@ -3,6 +3,9 @@
 #include "../../include/wam.h"
 
 #include <algorithm>
+#include <array>
+#include <map>
+#include <mutex>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -156,6 +159,7 @@ extern "C" int wam_design_sinc_bandpass(double f0, double bandwidth, double fs, 
 // ------------------------------------------------------------------------------------------
 static int derive(const wam_fsk_config& c, FskDerived& d) {
   memset(&d, 0, sizeof(d));
+  d.tmpl_slot = -1;
   if (!(c.sampleRate > 0) || !(c.baudRate > 0) || !std::isfinite(c.sampleRate) || !std::isfinite(c.baudRate) ||
       !std::isfinite(c.markFrequency) || !std::isfinite(c.spaceFrequency))
     return fail(WAM_E_UNSUPPORTED, "sampleRate/baudRate/frequencies must be finite and positive");
@@ -323,10 +327,43 @@ static int atan_table_device(int device, const double2** out) {
   return WAM_OK;
 }
 
+// __constant__ template slots (c_tmpl in fsk_demod.cuh): per device, shared by content, reference counted.
+namespace {
+constexpr int kTmplWordsPerSlot = 2 * (4 + wam::kTmpl0Words + 4);
+struct TmplSlot { std::vector<uint32_t> content; int refs = 0; };
+std::mutex g_tmpl_mu;
+std::map<int, std::array<TmplSlot, wam::kTmplSlots>> g_tmpl_slots;  // by device
+}  // namespace
+// Returns a slot holding `content` on the current device (uploading it if needed), or -1 when all slots are taken.
+static int tmpl_slot_acquire(int device, const std::vector<uint32_t>& content) {
+  std::lock_guard<std::mutex> lk(g_tmpl_mu);
+  auto& slots = g_tmpl_slots[device];
+  int free_slot = -1;
+  for (int i = 0; i < wam::kTmplSlots; i++) {
+    if (slots[i].refs > 0 && slots[i].content == content) { slots[i].refs++; return i; }
+    if (slots[i].refs == 0 && free_slot < 0) free_slot = i;
+  }
+  if (free_slot < 0) return -1;
+  if (cudaMemcpyToSymbol(wam::c_tmpl, content.data(), sizeof(uint32_t) * kTmplWordsPerSlot,
+                         sizeof(uint32_t) * kTmplWordsPerSlot * (size_t)free_slot) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  slots[free_slot].content = content;
+  slots[free_slot].refs = 1;
+  return free_slot;
+}
+static void tmpl_slot_release(int device, int slot) {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_tmpl_mu);
+  auto it = g_tmpl_slots.find(device);
+  if (it != g_tmpl_slots.end() && it->second[slot].refs > 0) it->second[slot].refs--;
+}
+
 // Word-aligned frame-sync templates (see sync_mismatches in fsk_demod.cuh).
-static int build_sync_templates(Group& g) {
+static int build_sync_templates(Group& g, int device) {
   FskDerived& d = g.d;
-  d.tmpl_expect = nullptr; d.tmpl_mask = nullptr; d.tmpl_words = 0; d.max_mismatch = -1; d.tmpl0_words = 0; d.tmpl0_full = 0;
+  d.tmpl_expect = nullptr; d.tmpl_mask = nullptr; d.tmpl_words = 0; d.max_mismatch = -1; d.tmpl0_words = 0; d.tmpl0_full = 0; d.tmpl_slot = -1;
   if (d.ring_fractional || d.total_bits <= 0) return WAM_OK;
   const int care = d.total_bits - d.dspb;  // the newest dspb samples (j == 0) never match
   const int W = (31 + care + 31) / 32;
@@ -357,6 +394,9 @@ static int build_sync_templates(Group& g) {
       d.tmpl0_expect[i] = (wi >= 0 && wi < W0) ? h[(size_t)wi] : 0u;
       d.tmpl0_mask[i] = (wi >= 0 && wi < W0) ? h[(size_t)32 * W + wi] : 0u;
     }
+    std::vector<uint32_t> content(d.tmpl0_expect, d.tmpl0_expect + 4 + kTmpl0Words + 4);
+    content.insert(content.end(), d.tmpl0_mask, d.tmpl0_mask + 4 + kTmpl0Words + 4);
+    d.tmpl_slot = tmpl_slot_acquire(device, content);
   }
   d.max_mismatch = (d.min_matched == INT_MAX) ? -1 : care - d.min_matched;
   return WAM_OK;
@@ -388,6 +428,7 @@ static void free_batch(wam_fsk_batch* b) {
   cudaSetDevice(b->device);
   for (auto& g : b->groups) {
     cudaFree(g.d_ids); cudaFree(g.f64); cudaFree(g.u32); cudaFree(g.sync_ring); cudaFree(g.amp_ring); cudaFree(g.tmpl);
+    tmpl_slot_release(b->device, g.d.tmpl_slot);
   }
   for (int i = 0; i < 2; i++) {
     if (b->streams[i]) cudaStreamDestroy(b->streams[i]);
@@ -453,7 +494,7 @@ extern "C" int wam_fsk_batch_create(int device, long n_streams, const wam_fsk_co
       free_batch(b);
       return fail(e == cudaErrorMemoryAllocation ? WAM_E_NOMEM : WAM_E_CUDA, std::string("state allocation: ") + cudaGetErrorString(e));
     }
-    int rc = build_sync_templates(g);
+    int rc = build_sync_templates(g, device);
     if (rc == WAM_OK) rc = atan_table_device(device, &g.d.atan_tab);
     if (rc == WAM_OK) rc = init_group_state(g, nullptr);
     if (rc != WAM_OK) { free_batch(b); return rc; }

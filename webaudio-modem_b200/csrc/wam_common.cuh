@@ -7,6 +7,7 @@
 
 namespace wam {
 
+constexpr int kTmplSlots = 8;        // __constant__ copies of by-value sync templates (per device, shared by content)
 constexpr int kTmpl0Words = 80;     // by-value sync template: up to 2560 compared samples ((nbits - 1) * dspb)
 constexpr int kMaxPatternWords = 8;  // preamble+SFD template: up to 256 line bits
 constexpr int kTile = 32;            // samples per stream per staged tile (one 128-byte row)
@@ -59,6 +60,8 @@ struct FskDerived {
   // every lane.  tmpl0_words == 0: template too long, use the per-offset tables above.
   int tmpl0_words;      // ceil(compared samples / 32)
   int tmpl0_full;       // floor(compared samples / 32): template words whose mask is all ones
+  int tmpl_slot;        // >= 0: the same template also sits in __constant__ slot c_tmpl[tmpl_slot] (functions that are
+                        // not inlined into the kernel cannot address the kernel parameters as constants)
   uint32_t tmpl0_expect[4 + kTmpl0Words + 4];  // word i at [4 + i]; the words around it are zero with a zero mask
   uint32_t tmpl0_mask[4 + kTmpl0Words + 4];
   const double2* atan_tab;  // device: {k / 64, atan(k / 64)}, k = 0..64
