@@ -51,9 +51,11 @@ __device__ __forceinline__ double fast_atan2(double y, double x, const double2* 
   const bool swap = ay > ax;
   double mx = swap ? ay : ax;
   double mn = swap ? ax : ay;
-  if (__double2hiint(mx) < 0x06000000) {
-    // rare: zero / denormal / tiny magnitudes — renormalise (the angle is scale invariant)
-    mx *= 0x1p+900; mn *= 0x1p+900;
+  {
+    // rare: zero / denormal / tiny magnitudes — renormalise (the angle is scale invariant): one select on the scale
+    // factor's high word instead of two on each operand
+    const double sc = __hiloint2double(__double2hiint(mx) < 0x06000000 ? 0x78300000 : 0x3ff00000, 0);  // 2^900 : 1
+    mx *= sc; mn *= sc;
   }
   // coarse ratio from the reciprocal seed picks the table interval
   double r0;
@@ -73,8 +75,15 @@ __device__ __forceinline__ double fast_atan2(double y, double x, const double2* 
   a = (mx > 0.0) ? a : 0.0;
   // quadrant: swap -> pi/2 - a ; x < 0 -> pi - a  (sign bit of x, so that atan2(+-0, -0) = +-pi)
   const bool xneg = hx < 0;
-  const double base = swap ? 1.5707963267948966 : (xneg ? 3.141592653589793 : 0.0);
-  a = (swap != xneg) ? base - a : base + a;
+  {
+    // base = swap ? pi/2 : (xneg ? pi : 0): pi and pi/2 share their low word (0x54442D18), so three integer
+    // selects; "base - a" is "base + (-a)": flip a's sign bit instead of selecting between two sums
+    const int base_hi = swap ? 0x3FF921FB : (xneg ? 0x400921FB : 0);
+    const int base_lo = (swap || xneg) ? 0x54442D18 : 0;
+    const int flip = (swap != xneg) ? (int)0x80000000 : 0;
+    const double as = __hiloint2double(__double2hiint(a) ^ flip, __double2loint(a));
+    a = __hiloint2double(base_hi, base_lo) + as;
+  }
   return copysign(a, y);
 }
 

@@ -456,11 +456,7 @@ __device__ __forceinline__ bool sm_step(BState& b, int bit, double amplitude, ui
         int mism;
         if (d.tmpl0_words > 0) {  // by-value template + funnel shift (templates up to kTmpl0Words words)
                     // RING_ARG (pipelined kernel): the ring may be in shared memory ([word][lane]) -> word-by-word walk
-#ifdef WAM_SYNC_INLINE
-          mism = RING_ARG ? sync_mismatches0<false>(ring, rstride, ring_pos, d) : sync_mismatches0v<false>(ring, ring_pos, d);
-#else
           mism = RING_ARG ? sync_mismatches0<false>(ring, rstride, ring_pos, d) : sync_mismatches0_call(ring, ring_pos, d);
-#endif
         } else {
           mism = sync_mismatches(ring, rstride, ring_pos, d);
         }
@@ -703,10 +699,6 @@ __device__ __forceinline__ int phase_a2_decim(A2State& s, double si, double sq, 
   const double phase = fast_atan2(sq, si, d.atan_tab);  // atan2(avgQ, avgI): scale invariant
   p = __dadd_rn(__dmul_rn(si, si), __dmul_rn(sq, sq));
   double pd = phase - s.last_phase;
-#ifdef WAM_AB_OLD_WRAP
-  if (pd > kPi) pd -= 6.283185307179586;
-  else if (pd < -kPi) pd += 6.283185307179586;
-#else
   {
     // the same wrap (fsk.ts:255-256) with one compare: subtract 2*pi carrying pd's sign when |pd| > pi
     // (x - (-2pi) == x + 2pi exactly); 2*Math.PI = 0x401921FB54442D18
@@ -714,7 +706,6 @@ __device__ __forceinline__ int phase_a2_decim(A2State& s, double si, double sq, 
     const double wrapped = pd - adj;
     pd = fabs(pd) > kPi ? wrapped : pd;
   }
-#endif
   s.last_phase = phase;
   double uo = pd + s.ox2;
   uo = fma(2.0, s.ox1, uo);
