@@ -122,7 +122,9 @@ enum {
   WAM_BATCH_TAP_PREFILTER = 1u << 1, /* (device API) write pre-filtered f32 samples to tap buffer */
   WAM_BATCH_DEBUG_GENERIC_SM = 1u << 2, /* test hook: per-sample state machine instead of the event-driven one */
   WAM_BATCH_NO_PIPELINE = 1u << 3,    /* test hook: never use the warp-specialised few-stream kernel */
-  WAM_BATCH_NO_TMA = 1u << 4          /* test hook: stage input tiles with cp.async instead of TMA */
+  WAM_BATCH_NO_TMA = 1u << 4,         /* test hook: stage input tiles with cp.async instead of TMA */
+  WAM_BATCH_NO_SLABS = 1u << 5,       /* test hook: every warp walks its streams in one pass (no dynamic time slabs) */
+  WAM_BATCH_FORCE_SLABS = 1u << 6     /* test hook: dynamic time slabs even for few streams / short calls */
 };
 
 /* cfg_index[stream] selects cfgs[]; NULL = all streams use cfgs[0]. */

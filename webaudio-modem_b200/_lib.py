@@ -26,6 +26,8 @@ WAM_BATCH_TAP_PREFILTER = 2
 WAM_BATCH_DEBUG_GENERIC_SM = 4
 WAM_BATCH_NO_PIPELINE = 8
 WAM_BATCH_NO_TMA = 16
+WAM_BATCH_NO_SLABS = 32
+WAM_BATCH_FORCE_SLABS = 64
 
 
 class WamError(RuntimeError):

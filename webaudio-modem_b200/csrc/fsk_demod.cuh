@@ -814,6 +814,13 @@ __device__ __forceinline__ void tma_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
+// Time-slab hand-over between launches (see launch_slabbed): the CTA that ran a slab publishes its streams' state.
+__device__ __noinline__ void slab_publish(int* flag, int slab) {
+  __threadfence();  // this lane's state / ring / output stores before the publication
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(slab + 1) : "memory");
+}
+
 // Grid: one warp (32 streams) per CTA, so that 2048 warps spread evenly over 148 SMs.
 // GENERIC = false: the common case (no AGC write-back, no tap, integral sync ring, eod_count > 16) —
 // only the event-driven state machine is compiled in, which keeps the kernel's code footprint small.
@@ -836,6 +843,14 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
   __shared__ int rows[32];
 
   const int lane = threadIdx.x;
+  // Time slabs (host: launch_slabbed): a long call arrives as launches of kSlabTiles tiles that overlap on two
+  // streams; a CTA of slab j waits here until the CTA of slab j - 1 has published the state of the same 32 streams.
+  // Every lane spins with an acquire load (one opaque asm block: a C++ loop here costs the kernel 48 bytes of spills).
+  if (STAGE_TMA && !GENERIC && L.slab_done != nullptr && L.slab > 0) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .s32 v;\n$L_slab_wait:\n\tld.acquire.gpu.global.s32 v, [%0];\n\t"
+                 "setp.lt.s32 p, v, %1;\n\t@p nanosleep.u32 256;\n\t@p bra $L_slab_wait;\n\t}\n"
+                 ::"l"(L.slab_done + blockIdx.x), "r"(L.slab) : "memory");
+  }
   const int li = a.l_begin + ((int)blockIdx.x - L.block_begin[gi]) * 32 + lane;
   bool active = li < a.l_end;
   int row = -1;
@@ -1092,6 +1107,7 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
     a.out_len[row] = b.out_n < a.out_stride ? b.out_n : (int)a.out_stride;
     if (GENERIC && a.n_valid) ragged_account(a, li, n_l);
   }
+  if (STAGE_TMA && !GENERIC && L.slab_done != nullptr) slab_publish(L.slab_done + blockIdx.x, L.slab);
 }
 
 }  // namespace wam

@@ -282,6 +282,7 @@ struct wam_fsk_batch {
   int sm_count = 148;
   int32_t* stage_nvalid = nullptr;
   size_t stage_nvalid_bytes = 0;
+  int fused_per_sm = -1;          // resident CTAs per SM of fsk_demod_exact_kernel<true, false, true>, -1 = not asked yet
   int pipe_per_sm[2] = {-1, -1};  // resident CTAs per SM of fsk_demod_pipe_kernel<unaligned / aligned>, -1 = not asked yet
   size_t pipe_smem = 0;
   int pipe_ring_smem = 0;
@@ -299,6 +300,11 @@ struct wam_fsk_batch {
   int32_t* stage_len[2] = {nullptr, nullptr};
   size_t stage_samples_bytes = 0, stage_out_bytes = 0, stage_len_bytes = 0;
   unsigned long long* phase_cycles = nullptr;  // debug: [max CTAs][4]
+  // time slabs of the fused kernel: two streams whose launches overlap, fork / join events, per-CTA progress flags
+  cudaStream_t slab_streams[2] = {nullptr, nullptr};
+  cudaEvent_t slab_fork = nullptr, slab_join[2] = {nullptr, nullptr};
+  int* slab_done = nullptr;
+  size_t slab_done_bytes = 0;
   long phase_ctas = 0;
   // modulator scratch
   uint32_t* mod_prefix = nullptr;
@@ -437,6 +443,12 @@ static void free_batch(wam_fsk_batch* b) {
     cudaFree(b->stage_samples[i]); cudaFree(b->stage_out[i]); cudaFree(b->stage_len[i]);
   }
   cudaFree(b->phase_cycles);
+  cudaFree(b->slab_done);
+  for (int i = 0; i < 2; i++) {
+    if (b->slab_streams[i]) cudaStreamDestroy(b->slab_streams[i]);
+    if (b->slab_join[i]) cudaEventDestroy(b->slab_join[i]);
+  }
+  if (b->slab_fork) cudaEventDestroy(b->slab_fork);
   cudaFree(b->stage_nvalid);
   cudaFree(b->mod_prefix); cudaFree(b->mod_data); cudaFree(b->mod_out); cudaFree(b->mod_len);
   delete b;
@@ -598,6 +610,60 @@ static bool make_sample_tmap(CUtensorMap* m, float* d_samples, long stride, long
 // launch the demodulator for all streams of `b` whose global id lies in [s0, s1); row 0 of the
 // buffers is stream `row_base`.  All configuration groups go into one launch (up to
 // kMaxGroupsPerLaunch per launch) so their one-warp CTAs share the SMs.
+static int ensure(void** p, size_t* cur, size_t need);
+
+// The fused TMA kernel over a long call of many warps: the call is cut into time slabs of kSlabTiles tiles, one launch
+// per slab, alternating between two streams so that slab j + 1 starts on the SM slots slab j frees; a CTA of slab
+// j + 1 waits (slab_wait) until the CTA of slab j has published the state of the same 32 streams (slab_publish).
+// Why: 2048 one-warp CTAs on 148 SMs x 4 schedulers leave schedulers with 4 and with 3 warps, and a warp on a 4-warp
+// scheduler advances about 25 % slower (profiles/r01_notes.md); with one launch the kernel ends when those finish.
+// With slabs the hardware CTA scheduler hands the next slab's CTAs to whichever slots come free first, so the streams
+// migrate between slow and fast slots and all schedulers stay busy to the end.  At most two launches overlap (the
+// third waits for the first on its stream), and the earlier one is fully resident by then: no CTA waits on a CTA that
+// cannot run.
+static int launch_slabbed(wam_fsk_batch* b, const DemodLaunch& L0, const long* tmap_rows, long n, cudaStream_t st) {
+  const int W = L0.block_begin[L0.n_groups];
+  long slab_len = (long)kSlabTiles * kTile;
+  if (const char* e = getenv("WAM_SLAB_TILES")) slab_len = (long)std::max(4, atoi(e)) * kTile;  // experiments
+  if (!b->slab_streams[0]) {
+    for (int i = 0; i < 2; i++) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&b->slab_streams[i], cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&b->slab_join[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&b->slab_fork, cudaEventDisableTiming));
+  }
+  int rc = ensure((void**)&b->slab_done, &b->slab_done_bytes, sizeof(int) * (size_t)W);
+  if (rc != WAM_OK) return rc;
+  CUDA_TRY(cudaMemsetAsync(b->slab_done, 0, sizeof(int) * (size_t)W, st));
+  CUDA_TRY(cudaEventRecord(b->slab_fork, st));
+  for (int i = 0; i < 2; i++) CUDA_TRY(cudaStreamWaitEvent(b->slab_streams[i], b->slab_fork, 0));
+  int slab = 0;
+  for (long t0 = 0; t0 < n; t0 += slab_len, ++slab) {
+    // every slab is a call of its own on samples [t0, t0 + len): shifted sample pointers and TMA descriptors,
+    // decoded bytes appended behind those of the earlier slabs
+    DemodLaunch L = L0;
+    const long len = std::min(slab_len, n - t0);
+    for (int g = 0; g < L.n_groups; g++) {
+      DemodArgs& a = L.g[g];
+      a.samples = L0.g[g].samples + t0;
+      a.n = len;
+      if (slab > 0) a.append = 1;
+      if (!make_sample_tmap(&L.tmap[g], a.samples, a.stride, len, tmap_rows[g]))
+        return fail(WAM_E_CUDA, "cuTensorMapEncodeTiled failed for a time slab");
+    }
+    L.slab = slab;
+    L.slab_done = b->slab_done;
+    fsk_demod_exact_kernel<true, false, true><<<W, 32, 0, b->slab_streams[slab & 1]>>>(L);
+    b->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  for (int i = 0; i < 2; i++) {
+    CUDA_TRY(cudaEventRecord(b->slab_join[i], b->slab_streams[i]));
+    CUDA_TRY(cudaStreamWaitEvent(st, b->slab_join[i], 0));
+  }
+  return WAM_OK;
+}
+
 static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base, float* d_samples, long stride, long n,
                               uint8_t* d_out, long out_stride, int32_t* d_out_len, float* d_tap, uint32_t flags,
                               cudaStream_t st, bool append = false, const int32_t* d_n_valid = nullptr,
@@ -610,6 +676,7 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
   const bool ragged = d_n_valid != nullptr;
   bool generic = wb || tap || (flags & WAM_BATCH_DEBUG_GENERIC_SM);
   bool tma_ok = aligned;  // every group of the launch has contiguous rows and a TMA descriptor
+  long tmap_rows[kMaxGroupsPerLaunch] = {0, 0, 0, 0};
   auto flush = [&]() -> int {
     if (L.n_groups == 0) return WAM_OK;
     // Few streams (<= 5 three-warp CTAs per SM): the warp-specialised pipeline (fsk_demod_pipe.cuh) advances a
@@ -637,7 +704,25 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
     }
     if (pipe) {
     } else if (aligned && !generic && !ragged && tma_ok && !(flags & WAM_BATCH_NO_TMA)) {
-      fsk_demod_exact_kernel<true, false, true><<<L.block_begin[L.n_groups], 32, 0, st>>>(L);
+      const int W = L.block_begin[L.n_groups];
+      const long n_tiles = (n + kTile - 1) / kTile;
+      const bool force = (flags & WAM_BATCH_FORCE_SLABS) != 0;
+      if (b->fused_per_sm < 0) {  // once per batch: resident CTAs per SM of the fused TMA kernel
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fsk_demod_exact_kernel<true, false, true>, 32, 0));
+        b->fused_per_sm = per_sm;
+      }
+      // slabs only when every CTA of a slab launch is resident at once (see launch_slabbed) and the launch is big
+      // enough for the 4-warp / 3-warp scheduler imbalance to matter
+      const bool one_wave = W <= b->fused_per_sm * b->sm_count;
+      if (!(flags & WAM_BATCH_NO_SLABS) && one_wave &&
+          ((W >= b->sm_count * 8 && n_tiles >= 4 * kSlabTiles) || (force && n_tiles > kSlabTiles))) {
+        int rc = launch_slabbed(b, L, tmap_rows, n, st);
+        if (rc != WAM_OK) return rc;
+        b->launches--;  // counted per slab inside
+      } else {
+        fsk_demod_exact_kernel<true, false, true><<<W, 32, 0, st>>>(L);
+      }
     } else if (aligned) { if (generic || ragged) launch_demod<true, true>(L, st); else launch_demod<true, false>(L, st); }
     else         { if (generic || ragged) launch_demod<false, true>(L, st); else launch_demod<false, false>(L, st); }
     b->launches++;
@@ -670,6 +755,7 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
     a.phase_cycles = b->phase_cycles;
     if (tma_ok && !generic && !ragged)
       tma_ok = g.contiguous && make_sample_tmap(&L.tmap[L.n_groups], d_samples, stride, n, s1 - row_base);
+    tmap_rows[L.n_groups] = s1 - row_base;
     L.block_begin[L.n_groups + 1] = L.block_begin[L.n_groups] + (int)((hi - lo + 31) / 32);
     L.n_groups++;
     if (L.n_groups == kMaxGroupsPerLaunch) {
@@ -743,7 +829,8 @@ static int demodulate_host_impl(wam_fsk_batch* b, float* samples, long stream_st
     b->demodulation_calls += 1;
     b->total_samples += (double)n_samples;
   }
-  flags &= (WAM_BATCH_WRITEBACK_AGC | WAM_BATCH_DEBUG_GENERIC_SM | WAM_BATCH_NO_PIPELINE | WAM_BATCH_NO_TMA);
+  flags &= (WAM_BATCH_WRITEBACK_AGC | WAM_BATCH_DEBUG_GENERIC_SM | WAM_BATCH_NO_PIPELINE | WAM_BATCH_NO_TMA | WAM_BATCH_NO_SLABS |
+            WAM_BATCH_FORCE_SLABS);
 
   // The call is cut into TIME slabs (all streams, samples [t0, t1)): the H2D copy of slab k+1 overlaps
   // the kernel of slab k (copy stream + compute stream, two staging buffers), and every slab launch

@@ -11,6 +11,7 @@ constexpr int kTmplSlots = 8;        // __constant__ copies of by-value sync tem
 constexpr int kTmpl0Words = 80;     // by-value sync template: up to 2560 compared samples ((nbits - 1) * dspb)
 constexpr int kMaxPatternWords = 8;  // preamble+SFD template: up to 256 line bits
 constexpr int kTile = 32;            // samples per stream per staged tile (one 128-byte row)
+constexpr int kSlabTiles = 64;       // tiles per time slab of a long call (2048 samples per stream)
 constexpr int kStages = 2;           // cp.async pipeline depth (per warp)
 
 // Resident one-warp CTAs per SM the demodulator is compiled for.  BASELINE config 2 is 2048 warps
@@ -126,6 +127,10 @@ struct DemodLaunch {
   int n_groups;
   int block_begin[kMaxGroupsPerLaunch + 1];  // first CTA of every group, then the total
   int pipe_ring_smem;                        // fsk_demod_pipe_kernel: the sync rings are copied to shared memory
+  // time slabs (fsk_demod_exact_kernel<.., STAGE_TMA>, host: launch_slabbed): this launch is slab number `slab` of a
+  // call; slab_done[cta] = slabs of that warp-group published so far.  slab_done == nullptr: a call in one launch.
+  int slab;
+  int* slab_done;
   DemodArgs g[kMaxGroupsPerLaunch];
 };
 
