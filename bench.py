@@ -51,19 +51,24 @@ def measured_peak_gbs():
 
 
 def ncu_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the demod kernel (one launch of this workload) from
-    the committed `ncu --set full` summary, or None."""
-    p = os.path.join(ROOT, "profiles", "r01_demod_ncu_full_summary.json")
+    """dram__bytes_read.sum + dram__bytes_write.sum of the demod kernel over ONE step of this workload (a step is a
+    series of time-slab launches), from the committed ncu launch list `profiles/r01_demod_slabs.csv`
+    (`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum -k regex:fsk_demod_exact`
+    of `bench.py --steps 1 --warmup 0`), as (mean bytes per launch, launches), or (None, 0)."""
+    import csv
+    p = os.path.join(ROOT, "profiles", "r01_demod_slabs.csv")
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
     try:
-        rec = json.load(open(p))[0]
-        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
-        tot = 0.0
-        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            v, u = rec[k]
-            tot += float(v.replace(",", "")) * scale[u]
-        return tot
+        tot, ids = 0.0, set()
+        for r in csv.reader(open(p)):
+            if len(r) < 15 or not r[0].isdigit() or "fsk_demod_exact_kernel" not in r[4]:
+                continue
+            if r[12] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(r[14].replace(",", "")) * scale[r[13]]
+                ids.add(r[0])
+        return (tot / len(ids), len(ids)) if ids else (None, 0)
     except Exception:
-        return None
+        return None, 0
 
 
 def host_cores():
@@ -371,6 +376,8 @@ def run_gpu(args):
     peak, peak_src = measured_peak_gbs()
     k_ms = statistics.mean(kernel_ms)
     achieved = S * N_SAMPLES * BYTES_PER_SAMPLE / (k_ms * 1e-3) / 1e9
+    lps = launches / args.steps
+    traffic, traffic_launches = ncu_traffic_bytes() if S == 65536 else (None, 0)
     line = {
         "metric": "fsk_demod_msamples_per_s", "value": value, "unit": "Msamples/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -382,14 +389,18 @@ def run_gpu(args):
         "decoded_bits_per_s": decoded_bytes * 8 * world / (ms_total_max * 1e-3 / args.steps),
         "frame_ok_frac_snr_ge_6dB": frac_ok_hi,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": (ncu_traffic_bytes() if S == 65536 else None), "traffic_unit": "bytes per launch",
+                     "traffic": traffic, "traffic_unit": "bytes per launch (mean over the launches of one step, ncu)",
+                     "traffic_launches": traffic_launches,
                      "peak_source": peak_src, "kernel": "fsk_demod_exact_kernel",
-                     "launches_per_step": launches / args.steps,
-                     "achieved_per_launch_bytes": S * N_SAMPLES * BYTES_PER_SAMPLE, "kernel_ms": k_ms,
-                     "note": "algorithmic 4 B/input sample x samples per launch / CUDA-event time of the launch "
-                             "(both V.21 channels in one launch, input tiles staged by TMA); the kernel is "
-                             "instruction-issue/latency bound (float64, reference-faithful), see profiles/r01_notes.md "
-                             "for issue-slot utilisation"},
+                     "launches_per_step": lps,
+                     "achieved_per_launch_bytes": S * N_SAMPLES * BYTES_PER_SAMPLE / max(lps, 1.0),
+                     "kernel_ms_per_launch": k_ms / max(lps, 1.0), "kernel_ms": k_ms,
+                     "note": "a step is one demodulate call = a series of overlapping time-slab launches of "
+                             "fsk_demod_exact_kernel (2048 samples per stream each, two streams, DESIGN.md 5.1); "
+                             "kernel_ms = CUDA-event time of the whole series, achieved = algorithmic 4 B/input sample "
+                             "x samples of the call / kernel_ms (= per-launch bytes / per-launch share of that time); "
+                             "the kernel is instruction-issue/latency bound (float64, reference-faithful), see "
+                             "profiles/r01_notes.md for issue-slot utilisation"},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
