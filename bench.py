@@ -219,6 +219,7 @@ def cpu_reference_run(n_sample_streams, steps, warmup, threads):
             times.append(dt)
     total = n_sample_streams * N_SAMPLES
     bits = sum(len(r) for r in res) * 8
+    cpu_reference_run.last = (x, cfg_index, res)  # for the GPU-vs-oracle check of bench's cpu_baseline leg
     return total, times, bits
 
 
@@ -324,6 +325,22 @@ def run_gpu(args):
     # results of the last step
     lens = d_len.cpu().numpy()
     outs = d_out.cpu().numpy()
+    # full-size self-check, untimed: the same call as ONE launch per group set (no time slabs) gives the same bytes
+    parity = {}
+    if rank == 0 and not (args.demod_flags & wam._lib.WAM_BATCH_NO_SLABS):
+        d_out2 = torch.zeros_like(d_out)
+        d_len2 = torch.zeros_like(d_len)
+        batch.renew(sp)
+        batch.demodulate_device(x.data_ptr(), N_SAMPLES, N_SAMPLES, d_out2.data_ptr(), cap, d_len2.data_ptr(), stream=sp,
+                                flags=args.demod_flags | wam._lib.WAM_BATCH_NO_SLABS)
+        torch.cuda.synchronize()
+        lens2 = d_len2.cpu().numpy()
+        outs2 = d_out2.cpu().numpy()
+        ok_same = bool((lens2 == lens).all()) and all(
+            bytes(outs2[s, :lens[s]]) == bytes(outs[s, :lens[s]]) for s in range(S))
+        parity["time_slabs_equal_one_pass"] = {"streams": int(S), "identical": ok_same}
+        assert ok_same, "time-slab launches and the one-pass launch decoded different bytes"
+        del d_out2, d_len2
     decoded_bytes = int(lens.sum())
     ok = np.array([lens[s] >= PAYLOAD and bytes(outs[s, :PAYLOAD]) == payloads[s].tobytes() for s in range(S)])
     hi_snr = snr >= 6
@@ -404,6 +421,7 @@ def run_gpu(args):
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
+        "parity": parity,
     }
     if not args.no_cpu and world >= 1:
         cores = host_cores()
@@ -412,6 +430,14 @@ def run_gpu(args):
         line["cpu_baseline"] = {"value": total / times[0] / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
                                 "sample": f"{n_cpu} streams x 1 s of the same workload, C float64 port of the reference "
                                           f"FSKCore (oracle/), one pthread per host core"}
+        # the same sample through the CUDA path (checker use of the oracle, outside every timed region)
+        hx, hcfg, want = cpu_reference_run.last
+        chk = wam.FSKBatch(n_cpu, [CFG_CH1, CFG_CH2], hcfg, device=dev.index)
+        got = chk.demodulate_bytes(hx.copy())
+        chk.close()
+        same = sum(1 for g, w in zip(got, want) if g == w)
+        line["parity"]["oracle_sample"] = {"streams": n_cpu, "identical": same, "decoded_bytes": sum(len(w) for w in want)}
+        assert same == n_cpu, "GPU bytes differ from the oracle on the cpu_baseline sample"
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
