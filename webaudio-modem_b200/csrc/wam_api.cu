@@ -715,8 +715,13 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
       // slabs only when every CTA of a slab launch is resident at once (see launch_slabbed) and the launch is big
       // enough for the 4-warp / 3-warp scheduler imbalance to matter
       const bool one_wave = W <= b->fused_per_sm * b->sm_count;
+      // warps per scheduler (4 per SM): slabs pay when a good part of the schedulers carries one warp more than the
+      // rest (measured on B200: 2.0 and 3.0 per scheduler lose 2-7 % with slabs, 3.46 gains 11 %)
+      const double per_sched = (double)W / (4.0 * b->sm_count);
+      const double frac = per_sched - std::floor(per_sched);
+      const bool uneven = frac > 0.03 && frac < 0.7;
       if (!(flags & WAM_BATCH_NO_SLABS) && one_wave &&
-          ((W >= b->sm_count * 8 && n_tiles >= 4 * kSlabTiles) || (force && n_tiles > kSlabTiles))) {
+          ((W >= b->sm_count * 8 && n_tiles >= 4 * kSlabTiles && uneven) || (force && n_tiles > kSlabTiles))) {
         int rc = launch_slabbed(b, L, tmap_rows, n, st);
         if (rc != WAM_OK) return rc;
         b->launches--;  // counted per slab inside
