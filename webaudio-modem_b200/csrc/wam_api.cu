@@ -301,8 +301,8 @@ struct wam_fsk_batch {
   size_t stage_samples_bytes = 0, stage_out_bytes = 0, stage_len_bytes = 0;
   unsigned long long* phase_cycles = nullptr;  // debug: [max CTAs][4]
   // time slabs of the fused kernel: two streams whose launches overlap, fork / join events, per-CTA progress flags
-  cudaStream_t slab_streams[2] = {nullptr, nullptr};
-  cudaEvent_t slab_fork = nullptr, slab_join[2] = {nullptr, nullptr};
+  cudaStream_t slab_streams[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t slab_fork = nullptr, slab_join[4] = {nullptr, nullptr, nullptr, nullptr};
   int* slab_done = nullptr;
   size_t slab_done_bytes = 0;
   long phase_ctas = 0;
@@ -444,7 +444,7 @@ static void free_batch(wam_fsk_batch* b) {
   }
   cudaFree(b->phase_cycles);
   cudaFree(b->slab_done);
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < 4; i++) {
     if (b->slab_streams[i]) cudaStreamDestroy(b->slab_streams[i]);
     if (b->slab_join[i]) cudaEventDestroy(b->slab_join[i]);
   }
@@ -625,8 +625,10 @@ static int launch_slabbed(wam_fsk_batch* b, const DemodLaunch& L0, const long* t
   const int W = L0.block_begin[L0.n_groups];
   long slab_len = (long)kSlabTiles * kTile;
   if (const char* e = getenv("WAM_SLAB_TILES")) slab_len = (long)std::max(4, atoi(e)) * kTile;  // experiments
+  int n_str = 2;
+  if (const char* e = getenv("WAM_SLAB_STREAMS")) n_str = std::min(4, std::max(1, atoi(e)));  // experiments
   if (!b->slab_streams[0]) {
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 4; i++) {
       CUDA_TRY(cudaStreamCreateWithFlags(&b->slab_streams[i], cudaStreamNonBlocking));
       CUDA_TRY(cudaEventCreateWithFlags(&b->slab_join[i], cudaEventDisableTiming));
     }
@@ -636,7 +638,7 @@ static int launch_slabbed(wam_fsk_batch* b, const DemodLaunch& L0, const long* t
   if (rc != WAM_OK) return rc;
   CUDA_TRY(cudaMemsetAsync(b->slab_done, 0, sizeof(int) * (size_t)W, st));
   CUDA_TRY(cudaEventRecord(b->slab_fork, st));
-  for (int i = 0; i < 2; i++) CUDA_TRY(cudaStreamWaitEvent(b->slab_streams[i], b->slab_fork, 0));
+  for (int i = 0; i < n_str; i++) CUDA_TRY(cudaStreamWaitEvent(b->slab_streams[i], b->slab_fork, 0));
   int slab = 0;
   for (long t0 = 0; t0 < n; t0 += slab_len, ++slab) {
     // every slab is a call of its own on samples [t0, t0 + len): shifted sample pointers and TMA descriptors,
@@ -653,11 +655,11 @@ static int launch_slabbed(wam_fsk_batch* b, const DemodLaunch& L0, const long* t
     }
     L.slab = slab;
     L.slab_done = b->slab_done;
-    fsk_demod_exact_kernel<true, false, true><<<W, 32, 0, b->slab_streams[slab & 1]>>>(L);
+    fsk_demod_exact_kernel<true, false, true><<<W, 32, 0, b->slab_streams[slab % n_str]>>>(L);
     b->launches++;
   }
   CUDA_TRY(cudaGetLastError());
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < n_str; i++) {
     CUDA_TRY(cudaEventRecord(b->slab_join[i], b->slab_streams[i]));
     CUDA_TRY(cudaStreamWaitEvent(st, b->slab_join[i], 0));
   }
