@@ -60,7 +60,9 @@ __device__ __forceinline__ double fast_atan2(double y, double x, const double2* 
   // coarse ratio from the reciprocal seed picks the table interval
   double r0;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(mx));
-  int k = __double2int_rn(mn * r0 * 64.0);
+  // round(64 * mn * r0) from the low word of (x + 1.5 * 2^52): no F2I; 0 <= mn * r0 <= 1 + 2^-22, NaN (mx == 0) gives
+  // a garbage index that is clamped and whose result is discarded below
+  int k = __double2loint(fma(mn * r0, 64.0, 6755399441055744.0));
   k = max(0, min(k, 64));
   const double2 e = __ldg(tab + k);
   // rotate by -atan(c): t = (mn - c*mx) / (mx + c*mn), |t| <= ~1/120
