@@ -263,6 +263,10 @@ __device__ __forceinline__ int sync_mismatches0v(const uint32_t* __restrict__ ri
   // first group: pairs -1 .. 2, some of them in front of the window (zero mask)
   uint4 v = ring_ld4(ring + g);
   g = (g + 4u) & wmask;
+  // the next group is always requested one round ahead (the ring is circular, so the last, unused request stays in
+  // bounds): the early-exit test of a round no longer waits for that round's own memory round trip
+  uint4 nx = ring_ld4(ring + g);
+  g = (g + 4u) & wmask;
   int mism = __popc((__funnelshift_r(v.x, v.y, o) ^ ex[0]) & mk[0]) + __popc((__funnelshift_r(v.y, v.z, o) ^ ex[1]) & mk[1]) +
              __popc((__funnelshift_r(v.z, v.w, o) ^ ex[2]) & mk[2]);
   uint32_t prev = v.w;
@@ -270,7 +274,8 @@ __device__ __forceinline__ int sync_mismatches0v(const uint32_t* __restrict__ ri
   // interior groups: all four window words are compared in full (mask ~0): no mask words to fetch
   const int n_full = (int)s + d.tmpl0_full;  // pairs below n_full meet all-ones mask words
   for (; n + 4 <= n_full; n += 4) {
-    v = ring_ld4(ring + g);
+    v = nx;
+    nx = ring_ld4(ring + g);
     g = (g + 4u) & wmask;
     mism += __popc(__funnelshift_r(prev, v.x, o) ^ ex[n]) + __popc(__funnelshift_r(v.x, v.y, o) ^ ex[n + 1]) +
             __popc(__funnelshift_r(v.y, v.z, o) ^ ex[n + 2]) + __popc(__funnelshift_r(v.z, v.w, o) ^ ex[n + 3]);
@@ -279,7 +284,8 @@ __device__ __forceinline__ int sync_mismatches0v(const uint32_t* __restrict__ ri
   }
   // last groups: the partial word at the end of the window and the words behind it (zero mask)
   for (; n < n_end; n += 4) {
-    v = ring_ld4(ring + g);
+    v = nx;
+    nx = ring_ld4(ring + g);
     g = (g + 4u) & wmask;
     mism += __popc((__funnelshift_r(prev, v.x, o) ^ ex[n]) & mk[n]) +
             __popc((__funnelshift_r(v.x, v.y, o) ^ ex[n + 1]) & mk[n + 1]) +
