@@ -640,29 +640,31 @@ __device__ __forceinline__ int sm_tile_events(BState& b, uint32_t bits, const do
 }
 
 // ---- phase A1: AGC + pre-filter for one sample -------------------------------------------------
-// 1 / (2 * level) to ~1e-14 relative: MUFU.RCP seed + one Newton step in f64.  (The reference
-// divides in f64; the gain recurrence is a contraction, so an error this size is invisible next to
-// the float32 store of fsk.ts:55 — see DESIGN.md "numerics".)
-__device__ __forceinline__ double agc_target(float level) {
-  const float l2 = fmaxf(level + level, 1e-30f);
-  float r0;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(l2));
-  const double r = (double)r0;
-  const double e = fma(-(double)l2, r, 1.0);
-  return fma(r, e, r);
-}
-
+// The AGC target 0.5 / level comes from 1 / level to ~1e-14 relative: MUFU.RCP seed + one Newton step in f64 (the
+// reference divides in f64; the gain recurrence is a contraction, so an error this size is invisible next to the
+// float32 store of fsk.ts:55 — see DESIGN.md "numerics").
 __device__ __forceinline__ float phase_a1_sample(A1State& s, float x, const FskDerived& d, bool agc, double att,
                                                  double rel, float& agc_out) {
   // AGC, fsk.ts:52-76 (evaluated unconditionally, selected by `agc`, so the code stays branch-free)
   const float sg_agc = (float)((double)x * s.gain);
   const float sg = agc ? sg_agc : x;
   const float level = fabsf(sg);
-  const double target = agc_target(level);
+  // 1 / level (MUFU.RCP seed + one Newton step); the 0.5 of "0.5 / level" rides on the update's first FMA instead of
+  // an addition in front of the reciprocal
+  const float lv = fmaxf(level, 5e-31f);
+  float r0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(lv));
+  const double r = (double)r0;
+  const double inv = fma(r, fma(-(double)lv, r, 1.0), r);
   const double rate = level > 0.5f ? att : rel;
-  double g = fma(target - s.gain, rate, s.gain);
-  g = g > 10.0 ? 10.0 : g;
-  g = g < 0.1 ? 0.1 : g;
+  double g = fma(fma(inv, 0.5, -s.gain), rate, s.gain);
+  {
+    // the two clamps exclude each other: both compares look at the unclamped g, so they run side by side and the
+    // recurrence chain ends in compare -> select -> select instead of compare -> select -> compare -> select
+    const bool over = g > 10.0, under = g < 0.1;
+    g = over ? 10.0 : g;
+    g = under ? 0.1 : g;
+  }
   s.gain = (agc && level > 0.0f) ? g : s.gain;
   agc_out = sg;
   // pre-filter: butterworthBandpass has b1 == 0 and b2 == -b0 exactly (filters.ts:230)
