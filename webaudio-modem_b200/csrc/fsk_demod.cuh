@@ -656,7 +656,9 @@ __device__ __forceinline__ float phase_a1_sample(A1State& s, float x, const FskD
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(lv));
   const double r = (double)r0;
   const double inv = fma(r, fma(-(double)lv, r, 1.0), r);
-  const double rate = level > 0.5f ? att : rel;
+  // "gain unchanged" (AGC off, or level == 0: fsk.ts:60-66 has no branch for it) is rate 0: inv is finite
+  // (lv >= 5e-31), so g == gain exactly and the clamps leave it alone — no select at the end of the recurrence chain
+  const double rate = (agc && level > 0.0f) ? (level > 0.5f ? att : rel) : 0.0;
   double g = fma(fma(inv, 0.5, -s.gain), rate, s.gain);
   {
     // the two clamps exclude each other: both compares look at the unclamped g, so they run side by side and the
@@ -665,7 +667,7 @@ __device__ __forceinline__ float phase_a1_sample(A1State& s, float x, const FskD
     g = over ? 10.0 : g;
     g = under ? 0.1 : g;
   }
-  s.gain = (agc && level > 0.0f) ? g : s.gain;
+  s.gain = g;
   agc_out = sg;
   // pre-filter: butterworthBandpass has b1 == 0 and b2 == -b0 exactly (filters.ts:230)
   double y = d.pre_b0 * ((double)sg - (double)s.px2);
