@@ -124,7 +124,10 @@ enum {
   WAM_BATCH_NO_PIPELINE = 1u << 3,    /* test hook: never use the warp-specialised few-stream kernel */
   WAM_BATCH_NO_TMA = 1u << 4,         /* test hook: stage input tiles with cp.async instead of TMA */
   WAM_BATCH_NO_SLABS = 1u << 5,       /* test hook: every warp walks its streams in one pass (no dynamic time slabs) */
-  WAM_BATCH_FORCE_SLABS = 1u << 6     /* test hook: dynamic time slabs even for few streams / short calls */
+  WAM_BATCH_FORCE_SLABS = 1u << 6,    /* test hook: dynamic time slabs even for few streams / short calls */
+  WAM_BATCH_EXACT_ONLY = 1u << 7,     /* never take the mixed-precision fast path: float64 kernels only */
+  WAM_BATCH_FORCE_FAST = 1u << 8,     /* test hook: fast path even for few streams / short calls */
+  WAM_BATCH_FAST_UNGUARDED = 1u << 9  /* test hook: keep the float32 results of flagged streams (no float64 re-run) */
 };
 
 /* cfg_index[stream] selects cfgs[]; NULL = all streams use cfgs[0]. */
@@ -180,6 +183,17 @@ int wam_fsk_batch_status(wam_fsk_batch* b, wam_fsk_status* st);
 int wam_fsk_batch_debug_phase_cycles(wam_fsk_batch* b, int enable, double* out4, double* per_cta, long n_ctas);
 /* kernels launched by this handle so far (bench.py's gpu_launches) */
 long wam_fsk_batch_launch_count(wam_fsk_batch* b);
+/* Mixed-precision fast path (float32 kernel with certified decisions; streams whose decisions the float32 error
+ * could have turned are demodulated again in float64): counters over the batch's life. */
+typedef struct wam_fast_stats {
+  int64_t fast_calls;          /* demodulate calls served by the fast kernel */
+  int64_t flagged_last_call;   /* streams re-run in float64 in the most recent fast call */
+  int64_t flagged_streams;     /* streams flagged at least once */
+  int64_t doubtful_samples;    /* decimated samples whose hard bit was inside the float32 error band */
+  uint32_t flag_causes;        /* OR of the causes seen: 1 start-bit vote, 2 data-bit vote, 4 stop-bit vote, 8 sync, 16 EOD, 32 range */
+  uint32_t error_flags;        /* OR of the streams' error words (1 output overflow, 2 pipeline timeout, 4 slab timeout) */
+} wam_fast_stats;
+int wam_fsk_batch_fast_stats(wam_fsk_batch* b, wam_fast_stats* out);
 
 /* modulateData() for every stream: data uint8 [n_streams][data_stride], data_len[s] bytes each
  * (NULL = nbytes for all).  out float32 [n_streams][out_stride]; out_len[s] samples written.

@@ -469,6 +469,8 @@ struct wamo_fsk {
   double eodEvents, errorEvents, configuredEvents;
   int threw;
   float* tap; long tapcap;
+  /* optional decimated-rate tap (tests / fast-path model): filteredPhaseDiff and amplitude per decimated sample */
+  double* dtapF; double* dtapA; long dtapcap, dtapn;
 };
 
 void wamo_default_config(wamo_fsk_config* c) { /* fsk.ts:19-33 */
@@ -699,6 +701,7 @@ static int process_sample(wamo_fsk* m, double sample) { /* fsk.ts:224-276 */
     m->lastPhase = currentPhase;
     double filteredPhaseDiff = wamo_iir_process(m->postFilter, phaseDiff);
     int bitValue = filteredPhaseDiff > 0 ? 1 : 0;
+    if (m->dtapF && m->dtapn < m->dtapcap) { m->dtapF[m->dtapn] = filteredPhaseDiff; m->dtapA[m->dtapn] = amplitude; m->dtapn++; }
     m->iAcc = 0; m->qAcc = 0; m->dsCounter = 0;
     return process_downsampled_bit(m, bitValue, amplitude);
   }
@@ -794,6 +797,8 @@ void wamo_fsk_params(const wamo_fsk* m, double out[8]) {
   out[7] = m->samplesForEOD;
 }
 void wamo_fsk_set_prefilter_tap(wamo_fsk* m, float* buf, long cap) { m->tap = buf; m->tapcap = cap; }
+void wamo_fsk_set_decim_tap(wamo_fsk* m, double* f, double* amp, long cap) { m->dtapF = f; m->dtapA = amp; m->dtapcap = cap; m->dtapn = 0; }
+long wamo_fsk_decim_tap_count(const wamo_fsk* m) { return m->dtapn; }
 
 /* ------------------------------------------------------------------------------------------
  * Multi-threaded batch driver: one FSKCore instance per stream, streams split over pthreads.

@@ -82,6 +82,9 @@ void wamo_fsk_params(const wamo_fsk* m, double out[8]);
 /* optional tap: record the pre-filtered f32 samples of the last demodulate call (tests compare
  * "filtered samples" within 1e-4).  buffer owned by caller, cap floats. */
 void wamo_fsk_set_prefilter_tap(wamo_fsk* m, float* buf, long cap);
+/* optional tap: filteredPhaseDiff (fsk.ts:261) and amplitude (fsk.ts:252) of every decimated sample since the tap was set */
+void wamo_fsk_set_decim_tap(wamo_fsk* m, double* f, double* amp, long cap);
+long wamo_fsk_decim_tap_count(const wamo_fsk* m);
 
 /* ---- filters.ts ---- */
 typedef struct wamo_iir wamo_iir;

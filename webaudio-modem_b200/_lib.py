@@ -28,6 +28,9 @@ WAM_BATCH_NO_PIPELINE = 8
 WAM_BATCH_NO_TMA = 16
 WAM_BATCH_NO_SLABS = 32
 WAM_BATCH_FORCE_SLABS = 64
+WAM_BATCH_EXACT_ONLY = 128
+WAM_BATCH_FORCE_FAST = 256
+WAM_BATCH_FAST_UNGUARDED = 512
 
 
 class WamError(RuntimeError):
@@ -65,6 +68,12 @@ class PktResult(C.Structure):
         ("payloadOffset", C.c_int32), ("crcReceived", C.c_int32), ("crcComputed", C.c_int32),
         ("bytesConsumed", C.c_int32),
     ]
+
+
+class FastStats(C.Structure):
+    """wam_fast_stats (include/wam.h)"""
+    _fields_ = [("fast_calls", C.c_int64), ("flagged_last_call", C.c_int64), ("flagged_streams", C.c_int64),
+                ("doubtful_samples", C.c_int64), ("flag_causes", C.c_uint32), ("error_flags", C.c_uint32)]
 
 
 class XmodemRxState(C.Structure):
@@ -110,6 +119,7 @@ SYMBOLS = {
     "wam_fsk_mux_batch": (_vp, [_vp]),
     "wam_fsk_batch_status": (C.c_int, [_vp, _stp]),
     "wam_fsk_batch_launch_count": (C.c_long, [_vp]),
+    "wam_fsk_batch_fast_stats": (C.c_int, [_vp, C.POINTER(FastStats)]),
     "wam_fsk_batch_debug_phase_cycles": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_long]),
     "wam_fsk_batch_modulate": (C.c_int, [_vp, _vp, C.c_long, _vp, C.c_long, _vp, C.c_long, _vp]),
     "wam_fsk_batch_modulate_device": (C.c_int, [_vp, _vp, C.c_long, _vp, C.c_long, _vp, C.c_long, _vp, _vp]),

@@ -861,8 +861,16 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
                  "setp.lt.s32 p, v, %1;\n\t@p nanosleep.u32 256;\n\t@p bra $L_slab_wait;\n\t}\n"
                  ::"l"(L.slab_done + blockIdx.x), "r"(L.slab) : "memory");
   }
-  const int li = a.l_begin + ((int)blockIdx.x - L.block_begin[gi]) * 32 + lane;
+  int li = a.l_begin + ((int)blockIdx.x - L.block_begin[gi]) * 32 + lane;
   bool active = li < a.l_end;
+  if (!STAGE_TMA && a.sel != nullptr) {
+    // sub-selection (float64 re-run of the streams the fast kernel flagged): entry j of the list names the stream;
+    // the list length lives in device memory, the grid is sized for the worst case and surplus CTAs leave at once
+    const int cnt = *a.sel_count;
+    if (li - lane >= cnt) return;
+    active = li < cnt;
+    li = active ? a.sel[li] : a.l_begin;
+  }
   int row = -1;
   if (active) row = (a.ids ? a.ids[li] : a.id0 + li) - a.row_base;
   long n_l = a.n;  // this stream's samples in this launch (ragged launches run the GENERIC variant)

@@ -44,7 +44,6 @@ constexpr int kPipeThreads = 96;
 constexpr int kPipeA1Chunks = WAM_PIPE_A1_CHUNKS;  // float4 chunks per iteration of the A1 loop
 constexpr int kPipeA2Unroll = WAM_PIPE_A2_UNROLL;  // pairs per iteration of the A2 loop
 constexpr unsigned kPipeSpinLimit = 1u << 24;
-#define WAM_ERR_PIPE_TIMEOUT 2u
 
 struct PipeShared {
   float tiles[kStages][kTile * kTile];     // input staging (swizzled), A1 only
@@ -84,8 +83,14 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
 
   const int lane = threadIdx.x & 31;
   const int role = threadIdx.x >> 5;
-  const int li = a.l_begin + ((int)blockIdx.x - L.block_begin[gi]) * 32 + lane;
+  int li = a.l_begin + ((int)blockIdx.x - L.block_begin[gi]) * 32 + lane;
   bool active = li < a.l_end;
+  if (a.sel != nullptr) {  // sub-selection, see fsk_demod_exact_kernel; the whole CTA takes the same way out
+    const int cnt = *a.sel_count;
+    if (li - lane >= cnt) return;
+    active = li < cnt;
+    li = active ? a.sel[li] : a.l_begin;
+  }
   int row = -1;
   if (active) row = (a.ids ? a.ids[li] : a.id0 + li) - a.row_base;
   long n_l = a.n;  // this stream's samples in this launch (ragged launches: its own count)

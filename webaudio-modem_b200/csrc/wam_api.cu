@@ -18,6 +18,7 @@
 #include "filters.cuh"
 #include "fsk_demod.cuh"
 #include "fsk_demod_pipe.cuh"
+#include "fsk_demod_fast.cuh"
 #include "fsk_mod.cuh"
 #include "wam_common.cuh"
 
@@ -157,6 +158,39 @@ extern "C" int wam_design_sinc_bandpass(double f0, double bandwidth, double fs, 
 // ------------------------------------------------------------------------------------------
 // FSKCore.configure(): derived parameters (fsk.ts:133-173, :426-462)
 // ------------------------------------------------------------------------------------------
+// Fast path (fsk_demod_fast.cuh): the biquads in normal form — poles sg +- j om, y = b0 x + k1 w1 + k2 w2 with
+// k1 = b1 - b0 a1, k2 = (b2 - b0 a2 + k1 sg) / om — and the constants of the doubt band.  The band's constants were
+// calibrated on the CPU model (oracle/fastmodel.c, scripts/exp_fastmodel.py): over 16,384 noisy streams the float32
+// error of filteredPhaseDiff stayed below 0.23 of the band.
+static bool normal_form(double b0, double b1, double b2, double a1, double a2, double& k1, double& k2, double& sg, double& om) {
+  sg = -a1 / 2;
+  const double om2 = a2 - sg * sg;
+  if (!(om2 > 1e-12) || !(fabs(a2) > 1e-12) || !std::isfinite(om2)) return false;  // real or degenerate poles
+  om = sqrt(om2);
+  k1 = b1 - b0 * a1;
+  k2 = (b2 - b0 * a2 + k1 * sg) / om;
+  return std::isfinite(k1) && std::isfinite(k2);
+}
+static void derive_fast(FskDerived& d) {
+  bool ok = normal_form(d.pre_b0, d.pre_b1, d.pre_b2, d.pre_a1, d.pre_a2, d.pre_nk1, d.pre_nk2, d.pre_nsg, d.pre_nom);
+  ok = normal_form(d.lp_b0, d.lp_b1, d.lp_b2, d.lp_a1, d.lp_a2, d.lp_nk1, d.lp_nk2, d.lp_nsg, d.lp_nom) && ok;
+  if (!ok) { d.fast_ok = 0; return; }
+  d.f_pre_k0 = (float)d.pre_b0; d.f_pre_k1 = (float)d.pre_nk1; d.f_pre_k2 = (float)d.pre_nk2;
+  d.f_pre_sg = (float)d.pre_nsg; d.f_pre_om = (float)d.pre_nom;
+  d.f_lp_k0 = (float)d.lp_b0; d.f_lp_k1 = (float)d.lp_nk1; d.f_lp_k2 = (float)d.lp_nk2;
+  d.f_lp_sg = (float)d.lp_nsg; d.f_lp_om = (float)d.lp_nom;
+  d.f_cw = (float)d.cos_omega; d.f_sw = (float)d.sin_omega;
+  d.f_dphi_bias = (float)(2.0 * (atan2((double)d.f_sw, (double)d.f_cw) - d.omega));
+  const double rho = sqrt(d.lp_a2);
+  d.f_rho_e = (float)rho;
+  d.f_gamma = (float)(sqrt(d.lp_nk1 * d.lp_nk1 + d.lp_nk2 * d.lp_nk2) / rho);
+  d.f_kappa = 3e-7f;
+  d.f_eps0 = 3e-7f;
+  d.f_bc_delta = 2e-6f;
+  d.f_amp_ulps = 16;
+  d.fast_ok = (!d.ring_fractional && d.eod_count > 16 && d.total_bits > 0 && d.check_period > 0 && rho < 1.0) ? 1 : 0;
+}
+
 static int derive(const wam_fsk_config& c, FskDerived& d) {
   memset(&d, 0, sizeof(d));
   d.tmpl_slot = -1;
@@ -258,6 +292,7 @@ static int derive(const wam_fsk_config& c, FskDerived& d) {
   d.amp_cap = d.dspb * 8;
   d.amp_phys = d.amp_cap + 32;
   d.mark = c.markFrequency; d.space = c.spaceFrequency; d.fs = fs;
+  derive_fast(d);
   return WAM_OK;
 }
 
@@ -275,6 +310,16 @@ struct Group {
   uint32_t* sync_ring = nullptr;
   float* amp_ring = nullptr;
   uint32_t* tmpl = nullptr;  // expect[32][W] then mask[32][W]
+  // fast path: doubt ring, list of the streams flagged in the current call, shadow copy of the state at call start
+  uint32_t* dring = nullptr;
+  int32_t* flag_list = nullptr;
+  int32_t* flag_count = nullptr;
+  double* sh_f64 = nullptr;
+  uint32_t* sh_u32 = nullptr;
+  uint32_t* sh_sync_ring = nullptr;
+  uint32_t* sh_dring = nullptr;
+  float* sh_amp_ring = nullptr;
+  int doubt_state = 0;  // 0: clean (fresh streams), 1: maintained by the fast kernel, 2: stale (an exact kernel ran since)
 };
 
 struct wam_fsk_batch {
@@ -283,6 +328,7 @@ struct wam_fsk_batch {
   int32_t* stage_nvalid = nullptr;
   size_t stage_nvalid_bytes = 0;
   int fused_per_sm = -1;          // resident CTAs per SM of fsk_demod_exact_kernel<true, false, true>, -1 = not asked yet
+  int fast_per_sm = -1;           // the same for fsk_demod_fast_kernel
   int pipe_per_sm[2] = {-1, -1};  // resident CTAs per SM of fsk_demod_pipe_kernel<unaligned / aligned>, -1 = not asked yet
   size_t pipe_smem = 0;
   int pipe_ring_smem = 0;
@@ -299,6 +345,9 @@ struct wam_fsk_batch {
   uint8_t* stage_out[2] = {nullptr, nullptr};
   int32_t* stage_len[2] = {nullptr, nullptr};
   size_t stage_samples_bytes = 0, stage_out_bytes = 0, stage_len_bytes = 0;
+  int32_t* sh_out_len = nullptr;  // fast path: out_len at call start (append calls)
+  size_t sh_out_len_bytes = 0;
+  long fast_calls = 0, fast_launches = 0;
   unsigned long long* phase_cycles = nullptr;  // debug: [max CTAs][4]
   // time slabs of the fused kernel: two streams whose launches overlap, fork / join events, per-CTA progress flags
   cudaStream_t slab_streams[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -420,6 +469,8 @@ static int init_group_state(Group& g, cudaStream_t st) {
   CUDA_TRY(cudaMemsetAsync(g.u32, 0, sizeof(uint32_t) * U32_COUNT * n, st));
   CUDA_TRY(cudaMemsetAsync(g.sync_ring, 0, sizeof(uint32_t) * (size_t)g.d.ring_words * n, st));
   CUDA_TRY(cudaMemsetAsync(g.amp_ring, 0, sizeof(float) * (size_t)g.d.amp_phys * n, st));
+  if (g.dring) CUDA_TRY(cudaMemsetAsync(g.dring, 0, sizeof(uint32_t) * (size_t)g.d.ring_words * n, st));
+  g.doubt_state = 0;
   // AGC gain 1.0 (fsk.ts:46), silence threshold 0.01 (fsk.ts:128)
   const unsigned blocks = (unsigned)((n + 255) / 256);
   fill_f64_kernel<<<blocks, 256, 0, st>>>(g.f64 + (size_t)F_GAIN * n, 1.0, (long)n);
@@ -434,6 +485,8 @@ static void free_batch(wam_fsk_batch* b) {
   cudaSetDevice(b->device);
   for (auto& g : b->groups) {
     cudaFree(g.d_ids); cudaFree(g.f64); cudaFree(g.u32); cudaFree(g.sync_ring); cudaFree(g.amp_ring); cudaFree(g.tmpl);
+    cudaFree(g.dring); cudaFree(g.flag_list); cudaFree(g.flag_count);
+    cudaFree(g.sh_f64); cudaFree(g.sh_u32); cudaFree(g.sh_sync_ring); cudaFree(g.sh_dring); cudaFree(g.sh_amp_ring);
     tmpl_slot_release(b->device, g.d.tmpl_slot);
   }
   for (int i = 0; i < 2; i++) {
@@ -443,6 +496,7 @@ static void free_batch(wam_fsk_batch* b) {
     cudaFree(b->stage_samples[i]); cudaFree(b->stage_out[i]); cudaFree(b->stage_len[i]);
   }
   cudaFree(b->phase_cycles);
+  cudaFree(b->sh_out_len);
   cudaFree(b->slab_done);
   for (int i = 0; i < 4; i++) {
     if (b->slab_streams[i]) cudaStreamDestroy(b->slab_streams[i]);
@@ -621,12 +675,12 @@ static int ensure(void** p, size_t* cur, size_t need);
 // migrate between slow and fast slots and all schedulers stay busy to the end.  At most two launches overlap (the
 // third waits for the first on its stream), and the earlier one is fully resident by then: no CTA waits on a CTA that
 // cannot run.
-static int launch_slabbed(wam_fsk_batch* b, const DemodLaunch& L0, const long* tmap_rows, long n, cudaStream_t st) {
+typedef void (*demod_kernel_fn)(const DemodLaunch);
+static int launch_slabbed(wam_fsk_batch* b, const DemodLaunch& L0, const long* tmap_rows, long n, cudaStream_t st,
+                          demod_kernel_fn kern) {
   const int W = L0.block_begin[L0.n_groups];
-  long slab_len = (long)kSlabTiles * kTile;
-  if (const char* e = getenv("WAM_SLAB_TILES")) slab_len = (long)std::max(4, atoi(e)) * kTile;  // experiments
-  int n_str = 2;
-  if (const char* e = getenv("WAM_SLAB_STREAMS")) n_str = std::min(4, std::max(1, atoi(e)));  // experiments
+  const long slab_len = (long)kSlabTiles * kTile;
+  const int n_str = 2;
   if (!b->slab_streams[0]) {
     for (int i = 0; i < 4; i++) {
       CUDA_TRY(cudaStreamCreateWithFlags(&b->slab_streams[i], cudaStreamNonBlocking));
@@ -655,7 +709,7 @@ static int launch_slabbed(wam_fsk_batch* b, const DemodLaunch& L0, const long* t
     }
     L.slab = slab;
     L.slab_done = b->slab_done;
-    fsk_demod_exact_kernel<true, false, true><<<W, 32, 0, b->slab_streams[slab % n_str]>>>(L);
+    kern<<<W, 32, 0, b->slab_streams[slab % n_str]>>>(L);
     b->launches++;
   }
   CUDA_TRY(cudaGetLastError());
@@ -664,6 +718,198 @@ static int launch_slabbed(wam_fsk_batch* b, const DemodLaunch& L0, const long* t
     CUDA_TRY(cudaStreamWaitEvent(st, b->slab_join[i], 0));
   }
   return WAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// fast path: float32 kernel with certified decisions + float64 re-run of the flagged streams
+// ------------------------------------------------------------------------------------------
+struct FastRestoreArgs {
+  double* f64; const double* sh_f64;
+  uint32_t* u32; const uint32_t* sh_u32;
+  uint32_t* ring; const uint32_t* sh_ring;
+  uint32_t* dring;
+  float* amp; const float* sh_amp;
+  const int32_t* list; const int32_t* count;
+  const int32_t* ids; int id0, row_base;
+  int32_t* out_len; const int32_t* sh_out_len;  // sh_out_len == nullptr: the call does not append
+  long n;
+  int ring_words, amp_phys;
+};
+// The streams the fast kernel flagged go back to the state they had at the start of the call (shadow copy); their
+// doubt-tracking state is set to "clean after a float64 run": no doubtful bits, the amplitude scale at a safe maximum.
+__global__ void fast_restore_kernel(const FastRestoreArgs r) {
+  const int cnt = *r.count;
+  for (int j = blockIdx.x; j < cnt; j += gridDim.x) {
+    const long li = r.list[j];
+    for (int t = threadIdx.x; t < F64_COUNT; t += blockDim.x) {
+      double v = r.sh_f64[(long)t * r.n + li];
+      if (t == F_FAST_S) v = 16.0;
+      if (t == F_FAST_E || t == F_FAST_RSP) v = 0.0;
+      r.f64[(long)t * r.n + li] = v;
+    }
+    for (int t = threadIdx.x; t < U32_COUNT; t += blockDim.x) {
+      if (t == U_FLAG || t == U_FLAG_EVER || t == U_DOUBT_SAMPLES || t == U_ERR) continue;
+      uint32_t v = r.sh_u32[(long)t * r.n + li];
+      if (t == U_DVOTE || t == U_SILX || t == U_LAST_DOUBT || t == U_DCNT) v = 0u;
+      r.u32[(long)t * r.n + li] = v;
+    }
+    for (int t = threadIdx.x; t < r.ring_words; t += blockDim.x) {
+      r.ring[li * r.ring_words + t] = r.sh_ring[li * r.ring_words + t];
+      r.dring[li * r.ring_words + t] = 0u;
+    }
+    for (int t = threadIdx.x; t < r.amp_phys; t += blockDim.x) r.amp[li * r.amp_phys + t] = r.sh_amp[li * r.amp_phys + t];
+    if (r.sh_out_len && threadIdx.x == 0) {
+      const long row = (r.ids ? r.ids[li] : r.id0 + li) - r.row_base;
+      r.out_len[row] = r.sh_out_len[row];
+    }
+  }
+}
+
+static int fast_buffers(Group& g, cudaStream_t st) {
+  const size_t n = g.ids.size();
+  if (g.dring) return WAM_OK;
+  const size_t rw = sizeof(uint32_t) * (size_t)g.d.ring_words * n;
+  CUDA_TRY(cudaMalloc(&g.dring, rw));
+  CUDA_TRY(cudaMalloc(&g.flag_list, sizeof(int32_t) * n));
+  CUDA_TRY(cudaMalloc(&g.flag_count, sizeof(int32_t)));
+  CUDA_TRY(cudaMalloc(&g.sh_f64, sizeof(double) * F64_COUNT * n));
+  CUDA_TRY(cudaMalloc(&g.sh_u32, sizeof(uint32_t) * U32_COUNT * n));
+  CUDA_TRY(cudaMalloc(&g.sh_sync_ring, rw));
+  CUDA_TRY(cudaMalloc(&g.sh_dring, rw));
+  CUDA_TRY(cudaMalloc(&g.sh_amp_ring, sizeof(float) * (size_t)g.d.amp_phys * n));
+  CUDA_TRY(cudaMemsetAsync(g.dring, 0, rw, st));
+  return WAM_OK;
+}
+
+// After a float64 kernel ran on a group the doubt-tracking state is stale: its bits are certain (no doubtful samples),
+// the error envelope restarts, and the amplitude scale — which the float64 kernels do not track — is set to a safe
+// maximum (it decays to the true scale within a few hundred decimated samples).
+static int fast_clean_doubt(Group& g, cudaStream_t st) {
+  const size_t n = g.ids.size();
+  CUDA_TRY(cudaMemsetAsync(g.dring, 0, sizeof(uint32_t) * (size_t)g.d.ring_words * n, st));
+  for (int u : {(int)U_DVOTE, (int)U_SILX, (int)U_LAST_DOUBT, (int)U_DCNT})
+    CUDA_TRY(cudaMemsetAsync(g.u32 + (size_t)u * n, 0, sizeof(uint32_t) * n, st));
+  for (int f : {(int)F_FAST_E, (int)F_FAST_RSP}) CUDA_TRY(cudaMemsetAsync(g.f64 + (size_t)f * n, 0, sizeof(double) * n, st));
+  fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g.f64 + (size_t)F_FAST_S * n, 16.0, (long)n);
+  CUDA_TRY(cudaGetLastError());
+  return WAM_OK;
+}
+
+// The float64 kernels over the streams named by each group's flag list (sub-selection launches: the list length is
+// read on the device, the grids are sized for the worst case and surplus CTAs leave at once).
+static int launch_exact_flagged(wam_fsk_batch* b, const DemodLaunch& L0, Group* const* lg, bool aligned, long n,
+                                cudaStream_t st) {
+  DemodLaunch L = L0;
+  L.slab = 0; L.slab_done = nullptr;
+  for (int g = 0; g < L.n_groups; g++) {
+    DemodArgs& a = L.g[g];
+    a.sel = lg[g]->flag_list; a.sel_count = lg[g]->flag_count;
+    a.flag_list = nullptr; a.flag_count = nullptr;
+    const int cnt = a.l_end - a.l_begin;
+    a.l_begin = 0; a.l_end = a.n_local;
+    L.block_begin[g + 1] = L.block_begin[g] + (cnt + 31) / 32;
+  }
+  const int W = L.block_begin[L.n_groups];
+  bool pipe = n >= 8 * kTile;
+  if (pipe) {
+    const int v = aligned ? 1 : 0;
+    auto kern = aligned ? fsk_demod_pipe_kernel<true> : fsk_demod_pipe_kernel<false>;
+    if (b->pipe_per_sm[v] < 0) {
+      int ring_words = 0;
+      for (auto& g : b->groups) ring_words = std::max(ring_words, g.d.ring_words);
+      b->pipe_smem = sizeof(PipeShared) + (size_t)ring_words * 32 * sizeof(uint32_t);
+      b->pipe_ring_smem = 1;
+      if (b->pipe_smem > 72 * 1024) { b->pipe_smem = sizeof(PipeShared); b->pipe_ring_smem = 0; }
+      int per_sm = 0;
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->pipe_smem));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPipeThreads, b->pipe_smem));
+      b->pipe_per_sm[v] = per_sm;
+    }
+    L.pipe_ring_smem = b->pipe_ring_smem;
+    pipe = b->pipe_per_sm[v] > 0;
+    if (pipe) kern<<<W, kPipeThreads, b->pipe_smem, st>>>(L);
+  }
+  if (!pipe) {
+    if (aligned) fsk_demod_exact_kernel<true, false><<<W, 32, 0, st>>>(L);
+    else fsk_demod_exact_kernel<false, false><<<W, 32, 0, st>>>(L);
+  }
+  b->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return WAM_OK;
+}
+
+static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, const long* tmap_rows, long n, uint32_t flags,
+                           cudaStream_t st) {
+  const int W = L.block_begin[L.n_groups];
+  long n_rows = 0;
+  for (int g = 0; g < L.n_groups; g++) n_rows = std::max(n_rows, tmap_rows[g]);
+  const bool append = L.g[0].append != 0;
+  const bool guarded = !(flags & WAM_BATCH_FAST_UNGUARDED);
+  for (int gi = 0; gi < L.n_groups; gi++) {
+    Group& g = *lg[gi];
+    const size_t ns = g.ids.size();
+    int rc = fast_buffers(g, st);
+    if (rc != WAM_OK) return rc;
+    if (g.doubt_state == 2) { rc = fast_clean_doubt(g, st); if (rc != WAM_OK) return rc; }
+    g.doubt_state = 1;
+    CUDA_TRY(cudaMemsetAsync(g.u32 + (size_t)U_FLAG * ns, 0, sizeof(uint32_t) * ns, st));
+    CUDA_TRY(cudaMemsetAsync(g.flag_count, 0, sizeof(int32_t), st));
+    if (guarded) {  // shadow copy of the state at the start of the call
+      const size_t rw = sizeof(uint32_t) * (size_t)g.d.ring_words * ns;
+      CUDA_TRY(cudaMemcpyAsync(g.sh_f64, g.f64, sizeof(double) * F64_COUNT * ns, cudaMemcpyDeviceToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(g.sh_u32, g.u32, sizeof(uint32_t) * U32_COUNT * ns, cudaMemcpyDeviceToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(g.sh_sync_ring, g.sync_ring, rw, cudaMemcpyDeviceToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(g.sh_amp_ring, g.amp_ring, sizeof(float) * (size_t)g.d.amp_phys * ns, cudaMemcpyDeviceToDevice, st));
+    }
+    DemodArgs& a = L.g[gi];
+    a.doubt_ring = g.dring; a.flag_list = g.flag_list; a.flag_count = g.flag_count;
+  }
+  if (guarded && append) {
+    int rc = ensure((void**)&b->sh_out_len, &b->sh_out_len_bytes, sizeof(int32_t) * (size_t)n_rows);
+    if (rc != WAM_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(b->sh_out_len, L.g[0].out_len, sizeof(int32_t) * (size_t)n_rows, cudaMemcpyDeviceToDevice, st));
+  }
+  // the fast kernel, in time slabs when the grid is one even wave (same rule as the float64 kernel)
+  const long n_tiles = (n + kTile - 1) / kTile;
+  if (b->fast_per_sm < 0) {
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fsk_demod_fast_kernel, 32, 0));
+    b->fast_per_sm = per_sm;
+  }
+  const bool one_wave = W <= b->fast_per_sm * b->sm_count;
+  const double per_sched = (double)W / (4.0 * b->sm_count);
+  const double frac = per_sched - std::floor(per_sched);
+  const bool uneven = frac > 0.03 && frac < 0.7;
+  const bool force = (flags & WAM_BATCH_FORCE_SLABS) != 0;
+  if (!(flags & WAM_BATCH_NO_SLABS) && one_wave &&
+      ((W >= b->sm_count * 8 && n_tiles >= 4 * kSlabTiles && uneven) || (force && n_tiles > kSlabTiles))) {
+    int rc = launch_slabbed(b, L, tmap_rows, n, st, fsk_demod_fast_kernel);
+    if (rc != WAM_OK) return rc;
+  } else {
+    L.slab = 0; L.slab_done = nullptr;
+    fsk_demod_fast_kernel<<<W, 32, 0, st>>>(L);
+    b->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  b->fast_calls++;
+  if (!guarded) return WAM_OK;
+  // float64 re-run of the flagged streams from the state at the start of the call
+  for (int gi = 0; gi < L.n_groups; gi++) {
+    Group& g = *lg[gi];
+    const DemodArgs& a = L.g[gi];
+    FastRestoreArgs r;
+    r.f64 = g.f64; r.sh_f64 = g.sh_f64; r.u32 = g.u32; r.sh_u32 = g.sh_u32;
+    r.ring = g.sync_ring; r.sh_ring = g.sh_sync_ring; r.dring = g.dring;
+    r.amp = g.amp_ring; r.sh_amp = g.sh_amp_ring;
+    r.list = g.flag_list; r.count = g.flag_count;
+    r.ids = a.ids; r.id0 = a.id0; r.row_base = a.row_base;
+    r.out_len = a.out_len; r.sh_out_len = append ? b->sh_out_len : nullptr;
+    r.n = (long)g.ids.size(); r.ring_words = g.d.ring_words; r.amp_phys = g.d.amp_phys;
+    fast_restore_kernel<<<64, 128, 0, st>>>(r);
+  }
+  CUDA_TRY(cudaGetLastError());
+  const bool aligned = true;
+  return launch_exact_flagged(b, L, lg, aligned, n, st);
 }
 
 static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base, float* d_samples, long stride, long n,
@@ -679,8 +925,25 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
   bool generic = wb || tap || (flags & WAM_BATCH_DEBUG_GENERIC_SM);
   bool tma_ok = aligned;  // every group of the launch has contiguous rows and a TMA descriptor
   long tmap_rows[kMaxGroupsPerLaunch] = {0, 0, 0, 0};
+  Group* lg[kMaxGroupsPerLaunch] = {nullptr, nullptr, nullptr, nullptr};
   auto flush = [&]() -> int {
     if (L.n_groups == 0) return WAM_OK;
+    // Fast path: float32 kernel with certified decisions, float64 re-run of the streams it flags.  Many streams and
+    // long calls only (or WAM_BATCH_FORCE_FAST): short calls are latency-sized and stay with the float64 kernels.
+    {
+      bool fast = aligned && !generic && !ragged && tma_ok && !(flags & (WAM_BATCH_NO_TMA | WAM_BATCH_EXACT_ONLY));
+      for (int g = 0; g < L.n_groups && fast; g++) fast = L.g[g].d.fast_ok != 0 && L.g[g].d.tmpl0_words > 0;
+      if (fast && !(flags & WAM_BATCH_FORCE_FAST))
+        fast = L.block_begin[L.n_groups] >= 4 * b->sm_count && n >= 4 * (long)kSlabTiles * kTile;
+      if (fast) {
+        int rc = fast_demodulate(b, L, lg, tmap_rows, n, flags, st);
+        memset(&L, 0, sizeof(L));
+        generic = wb || tap || (flags & WAM_BATCH_DEBUG_GENERIC_SM);
+        tma_ok = aligned;
+        return rc;
+      }
+      for (int g = 0; g < L.n_groups; g++) lg[g]->doubt_state = 2;  // a float64 kernel is about to run on these groups
+    }
     // Few streams (<= 5 three-warp CTAs per SM): the warp-specialised pipeline (fsk_demod_pipe.cuh) advances a
     // stream at the longest of the three phase chains instead of their sum.  Many streams: the fused kernel,
     // whose one-warp CTAs already hide the chains across warps.
@@ -724,7 +987,7 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
       const bool uneven = frac > 0.03 && frac < 0.7;
       if (!(flags & WAM_BATCH_NO_SLABS) && one_wave &&
           ((W >= b->sm_count * 8 && n_tiles >= 4 * kSlabTiles && uneven) || (force && n_tiles > kSlabTiles))) {
-        int rc = launch_slabbed(b, L, tmap_rows, n, st);
+        int rc = launch_slabbed(b, L, tmap_rows, n, st, fsk_demod_exact_kernel<true, false, true>);
         if (rc != WAM_OK) return rc;
         b->launches--;  // counted per slab inside
       } else {
@@ -745,6 +1008,7 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
     const auto hi = std::lower_bound(g.ids.begin(), g.ids.end(), (int32_t)s1) - g.ids.begin();
     if (hi <= lo) continue;
     DemodArgs& a = L.g[L.n_groups];
+    lg[L.n_groups] = &g;
     a.d = g.d;
     a.ids = g.contiguous ? nullptr : g.d_ids;
     a.id0 = g.ids.front();
@@ -952,6 +1216,34 @@ extern "C" int wam_fsk_batch_status(wam_fsk_batch* b, wam_fsk_status* st) {
 }
 
 extern "C" long wam_fsk_batch_launch_count(wam_fsk_batch* b) { return b ? b->launches : 0; }
+
+extern "C" int wam_fsk_batch_fast_stats(wam_fsk_batch* b, wam_fast_stats* out) {
+  if (!b || !out) return fail(WAM_E_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  memset(out, 0, sizeof(*out));
+  out->fast_calls = b->fast_calls;
+  for (auto& g : b->groups) {
+    const size_t n = g.ids.size();
+    if (n == 0) continue;
+    std::vector<uint32_t> ev(n), ds(n), er(n);
+    CUDA_TRY(cudaMemcpy(ev.data(), g.u32 + (size_t)U_FLAG_EVER * n, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(ds.data(), g.u32 + (size_t)U_DOUBT_SAMPLES * n, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(er.data(), g.u32 + (size_t)U_ERR * n, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; i++) {
+      if (ev[i]) out->flagged_streams++;
+      out->flag_causes |= ev[i];
+      out->doubtful_samples += ds[i];
+      out->error_flags |= er[i];
+    }
+    if (g.flag_count) {
+      int32_t c = 0;
+      CUDA_TRY(cudaMemcpy(&c, g.flag_count, sizeof(c), cudaMemcpyDeviceToHost));
+      out->flagged_last_call += c;
+    }
+  }
+  return WAM_OK;
+}
 
 // Debug: enable (enable != 0) / read-and-clear per-phase SM cycle counters of the demodulator kernel.
 // out4 (nullable) receives the sums over CTAs of cycles spent in A1, A2, B and staging/other;

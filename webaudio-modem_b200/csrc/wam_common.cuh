@@ -66,6 +66,23 @@ struct FskDerived {
   uint32_t tmpl0_expect[4 + kTmpl0Words + 4];  // word i at [4 + i]; the words around it are zero with a zero mask
   uint32_t tmpl0_mask[4 + kTmpl0Words + 4];
   const double2* atan_tab;  // device: {k / 64, atan(k / 64)}, k = 0..64
+  // ---- fast path (fsk_demod_fast.cuh): float32 DSP behind a float64 AGC, decisions certified by a doubt band ----
+  // The three biquads in NORMAL (coupled) form: w' = [[sg, -om], [om, sg]] w + (x, 0), y = k0 x + k1 w1 + k2 w2 (w before
+  // the update).  Same transfer function as the reference's direct form I; in float32 its round-off is ~50x smaller
+  // (measured against the oracle: 1e-8 rms on filteredPhaseDiff instead of 5e-7, oracle/fastmodel.c).
+  double pre_nk1, pre_nk2, pre_nsg, pre_nom;  // float64 copies for the state conversion direct form <-> normal form
+  double lp_nk1, lp_nk2, lp_nsg, lp_nom;
+  float f_pre_k0, f_pre_k1, f_pre_k2, f_pre_sg, f_pre_om;
+  float f_lp_k0, f_lp_k1, f_lp_k2, f_lp_sg, f_lp_om;
+  float f_cw, f_sw;       // float32 LO rotation
+  float f_dphi_bias;      // 2 * (atan2(f_sw, f_cw) - omega): the float32 LO's constant offset on the phase difference
+  float f_rho_e;          // envelope of the post filter's impulse response: |h(j)| <= f_gamma * f_rho_e^j
+  float f_gamma;
+  float f_kappa;          // relative float32 error of an I/Q output against the recent amplitude scale
+  float f_eps0;           // floor of the doubt band on |filteredPhaseDiff|
+  float f_bc_delta;       // a raw phase difference this close to +-pi may have wrapped the other way
+  int f_amp_ulps;         // doubt band of the silence compare, in float32 ulps of the threshold
+  int fast_ok;            // the configuration qualifies for the fast kernel (complex poles, integral ring, by-value template)
   // modulator (fsk.ts:389-424)
   double mark, space, fs;
   int n_preamble, n_sfd;
@@ -79,11 +96,16 @@ enum F64Field {
   F_OX1, F_OX2, F_OY1, F_OY2, F_LAST_PHASE, F_IACC, F_QACC, F_SIL_THR,
   F_RING_WI, F_RING_RI, F_RING_LEN,
   F_RAGGED_CALLS, F_RAGGED_TOTAL,  // demodulateData() calls / samples received through ragged launches (per stream)
+  F_FAST_S, F_FAST_E, F_FAST_RSP,  // fast path: amplitude scale, error envelope, 1 / (4 amplitude) of the last phasor
   F64_COUNT
 };
 enum U32Field {
   U_DSC = 0, U_GSC, U_GMOD, U_BSC, U_NEXT_IDX, U_BIT_ACC, U_BIT_CNT, U_STARTED, U_BITPOS, U_CURRENT,
   U_SIL_CNT, U_RING_POS, U_RING_LEN, U_AMP_POS, U_AMP_LEN, U_SYNC_DET, U_EOD_EV, U_ERR,
+  // fast path (doubt tracking): doubtful samples of the running vote (ones | zeros << 16); pending doubtful silence
+  // compare (bit 31) + the silent run it would add; ring position behind the newest doubtful hard bit (0: none);
+  // causes flagged in the current call (bit = WAM_FLAG_*), and over the batch's life (statistics)
+  U_DVOTE, U_SILX, U_LAST_DOUBT, U_DCNT, U_FLAG, U_FLAG_EVER, U_DOUBT_SAMPLES,
   U32_COUNT
 };
 
@@ -115,6 +137,14 @@ struct DemodArgs {
   int writeback;        // write the AGC-scaled samples back into `samples` (fsk.ts:55)
   int append;           // out_len[row] holds the bytes already written for this stream: append after them
   unsigned long long* phase_cycles;  // debug (nullable): [CTA][4] SM cycles spent in A1, A2, B, staging/other
+  // sub-selection (exact re-run of the streams the fast kernel flagged): local index j -> sel[j], and the number of
+  // entries read from device memory (the host launches a grid for the worst case; surplus CTAs leave at once)
+  const int32_t* sel;
+  const int32_t* sel_count;
+  // fast path
+  uint32_t* doubt_ring;  // [n_local][ring_words]: 1 = that hard bit of the sync ring is doubtful
+  int32_t* flag_list;    // local indices of the streams flagged in this call, appended at *flag_count
+  int32_t* flag_count;
 };
 
 // All configuration groups of a batch run in ONE launch (one-warp CTAs; blockIdx selects the group)
@@ -135,5 +165,15 @@ struct DemodLaunch {
 };
 
 #define WAM_ERR_OUT_OVERFLOW 1u
+#define WAM_ERR_PIPE_TIMEOUT 2u
+#define WAM_ERR_SLAB_TIMEOUT 4u
+
+// causes of a flagged (doubtful) decision in the fast kernel
+#define WAM_FLAG_VOTE_START 1u
+#define WAM_FLAG_VOTE_DATA 2u
+#define WAM_FLAG_VOTE_STOP 4u
+#define WAM_FLAG_SYNC 8u
+#define WAM_FLAG_EOD 16u
+#define WAM_FLAG_RANGE 32u
 
 }  // namespace wam

@@ -254,6 +254,12 @@ class FSKBatch:
     def launch_count(self) -> int:
         return int(self._lib.wam_fsk_batch_launch_count(self._h))
 
+    def fast_stats(self) -> dict:
+        """Counters of the mixed-precision fast path (wam_fsk_batch_fast_stats)."""
+        st = L.FastStats()
+        L.check(self._lib.wam_fsk_batch_fast_stats(self._h, C.byref(st)))
+        return {k: int(getattr(st, k)) for k, _ in L.FastStats._fields_}
+
     # -- host buffers --------------------------------------------------------------------------
     def demodulate(self, samples: np.ndarray, writeback_agc: bool = False, flags: int = 0):
         """samples float32 [n_streams, n]; returns (out uint8 [n_streams, cap], out_len int32 [n_streams])."""
