@@ -127,7 +127,9 @@ enum {
   WAM_BATCH_FORCE_SLABS = 1u << 6,    /* test hook: dynamic time slabs even for few streams / short calls */
   WAM_BATCH_EXACT_ONLY = 1u << 7,     /* never take the mixed-precision fast path: float64 kernels only */
   WAM_BATCH_FORCE_FAST = 1u << 8,     /* test hook: fast path even for few streams / short calls */
-  WAM_BATCH_FAST_UNGUARDED = 1u << 9  /* test hook: keep the float32 results of flagged streams (no float64 re-run) */
+  WAM_BATCH_FAST_UNGUARDED = 1u << 9, /* test hook: keep the float32 results of flagged streams (no float64 re-run) */
+  WAM_BATCH_TAP_FAST_DECISION = 1u << 10 /* test hook (device API, fast path): tap[stream][2k, 2k+1] = filtered phase
+                                            difference and doubt band of decimated sample k */
 };
 
 /* cfg_index[stream] selects cfgs[]; NULL = all streams use cfgs[0]. */

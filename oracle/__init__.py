@@ -138,6 +138,9 @@ def lib():
     L.wamo_fsk_status_get.argtypes = [vp, C.POINTER(StatusStruct)]
     L.wamo_fsk_params.argtypes = [vp, dp]
     L.wamo_fsk_set_prefilter_tap.argtypes = [vp, fp, C.c_long]
+    L.wamo_fsk_set_decim_tap.argtypes = [vp, dp, dp, C.c_long]
+    L.wamo_fsk_decim_tap_count.restype = C.c_long
+    L.wamo_fsk_decim_tap_count.argtypes = [vp]
     L.wamo_iir_new.restype = vp
     L.wamo_iir_new.argtypes = [dp, C.c_int, dp, C.c_int, C.POINTER(C.c_int)]
     L.wamo_iir_free.argtypes = [vp]
@@ -247,6 +250,17 @@ class FSKCore:
         if n < 0:
             raise NotConfigured("FSK demodulator not configured")
         return bytes(out[:n])
+
+    def demodulateTapped(self, samples: np.ndarray):
+        """demodulateData plus the decimated-rate internals: (bytes, filteredPhaseDiff[k], amplitude[k]) — fsk.ts:246-264."""
+        assert samples.dtype == np.float32 and samples.flags.c_contiguous
+        nd = len(samples) // 2 + 2
+        f, a = np.zeros(nd), np.zeros(nd)
+        lib().wamo_fsk_set_decim_tap(self._h, _f64(f), _f64(a), nd)
+        out = self.demodulateData(samples)
+        n = lib().wamo_fsk_decim_tap_count(self._h)
+        lib().wamo_fsk_set_decim_tap(self._h, None, None, 0)
+        return out, f[:n], a[:n]
 
     def reset(self):
         lib().wamo_fsk_reset(self._h)

@@ -31,6 +31,7 @@ WAM_BATCH_FORCE_SLABS = 64
 WAM_BATCH_EXACT_ONLY = 128
 WAM_BATCH_FORCE_FAST = 256
 WAM_BATCH_FAST_UNGUARDED = 512
+WAM_BATCH_TAP_FAST_DECISION = 1024
 
 
 class WamError(RuntimeError):

@@ -1,22 +1,28 @@
-// fsk_demod_fast.cuh — fused FSK demodulator, mixed-precision fast path with certified decisions.
+// fsk_demod_fast.cuh — fused FSK demodulator, mixed-precision fast path with certified decisions (second version).
 //
-// Same job and same tile structure as fsk_demod_exact_kernel (fsk_demod.cuh): one thread walks one stream
+// Same job and the same tile structure as fsk_demod_exact_kernel (fsk_demod.cuh): one thread walks one stream
 // (FSKCore.demodulateData, src/modems/fsk.ts:190-375), a warp owns 32 streams and is its own CTA, samples arrive as
-// 32 x 32 TMA tiles.  What changes is the arithmetic:
+// 32 x 32 TMA tiles.  What changes is the arithmetic and its cost (warp instructions per input sample: 128 -> ~60):
 //   A1  the AGC gain recurrence (fsk.ts:52-76) stays in float64 — its branch `level > 0.5` is a discontinuity, and an
-//       exact gain keeps the float32 store of fsk.ts:55 exact — but the band-pass pre-filter runs in float32;
-//   A2  LO rotation, I/Q low-pass (packed f32x2: I and Q share their coefficients), /2 decimation, phase difference as
-//       atan2(cross, dot) of consecutive phasors, post low-pass and slicer all run in float32.  The three biquads use
-//       the NORMAL (coupled) form instead of the reference's direct form I: same transfer function, but in float32 its
-//       round-off on filteredPhaseDiff is 1e-8 rms against 5e-7 (measured against the oracle, oracle/fastmodel.c);
+//       exact gain keeps the float32 store of fsk.ts:55 exact.  Its float32 <-> float64 traffic is cut to the two
+//       conversions of the product (|x| -> f64, x * gain -> f32): the reciprocal seed and the level re-enter float64
+//       by integer exponent arithmetic (one IMAD.WIDE each, both are positive normal floats), the attack / release
+//       choice is two predicated DFMAs instead of 64-bit selects.
+//   A2  every filter runs in float32 NORMAL (coupled) form, two input samples per step (the decimator only wants the
+//       sum of a pair, fsk.ts:241-249): state' = A^2 state + A B x0 + B x1, pair sum = c . state + d0 x0 + d1 x1.
+//       The LO is two rotation recurrences (even / odd samples) turning by 2 omega; the wrapped phase difference is
+//       atan2(cross, dot) of consecutive phasors; post low-pass and slicer in float32.
 //   B   the decimated-rate state machine (fsk.ts:278-375) is the exact kernel's event-driven one plus DOUBT TRACKING:
-//       a hard bit whose |filteredPhaseDiff| is inside the float32 error band is doubtful (second bit ring), an
-//       amplitude within a few ulps of the silence threshold is doubtful, and a DECISION — majority vote, sync
-//       threshold, EOD — that the doubtful samples could turn FLAGS the stream.
-// A flagged stream is demodulated again by the float64 kernels from the state it had at the start of the call (host:
-// fast_demodulate in wam_api.cu), so the bytes and counters that leave the library are the float64 ones wherever the
-// float32 arithmetic could have mattered.  Measured on the CPU model of this kernel (oracle/fastmodel.c, 16,384 noisy
-// V.21 streams, -15..+30 dB): 0 streams differ from the oracle among the unflagged ones, 0.06 % are flagged.
+//       a hard bit whose |filteredPhaseDiff| is inside the float32 error band is doubtful, an amplitude within a few
+//       ulps of the silence threshold is doubtful, and a DECISION — majority vote, sync threshold, EOD — that the
+//       doubtful samples could turn FLAGS the stream.  The four per-tile masks (hard bits, doubt, silent, silence
+//       doubt) are shifted together from SIGN bits (one FADD + one SHF per entry instead of compare + select + shift).
+// A flagged stream is demodulated again by the float64 kernels (host: fast_demodulate in wam_api.cu), so the bytes and
+// counters that leave the library are the float64 ones wherever the float32 arithmetic could have mattered.
+//
+// Fast-path calls are ALIGNED: every call since the last reset() had a multiple of 32 samples, so a tile is 16 whole
+// decimated samples, its 16 hard bits are one aligned half word of the bit-packed sync ring and its 16 amplitudes four
+// aligned 16-byte stores (the host keeps track and falls back to the float64 kernels otherwise).
 //
 // The per-stream state lives in the same arrays and the same (direct form) representation as the exact kernel's, so
 // both kernels can run on a batch in any order: this kernel converts on the way in and out (float64, once per launch).
@@ -30,58 +36,30 @@
 
 namespace wam {
 
-struct FastA2 {    // everything resetState() zeroes on the DSP side, float32
-  float lc, ls;    // LO rotation
+struct FastDsp {
+  float2 e0, e1;   // LO phasors of the next even / odd input sample
   float2 w1, w2;   // I/Q low-pass, normal form, packed (I, Q)
   float ow1, ow2;  // post low-pass
   float psi, psq;  // previous decimated phasor (lastPhase as a vector)
-  float2 acc;      // decimator
   float S, E, rsp; // doubt envelope: amplitude scale, error envelope of the post filter, 1 / (4 amp) of the last phasor
-  uint32_t dsc;
 };
-struct FastB {     // BState + doubt tracking
-  float sil_thr;
+struct FastB {     // state machine + doubt tracking, in registers for the whole launch
+  float sil_thr, thr_lo, thr_hi;
   uint32_t gsc, gmod, bsc, next_idx, bit_acc, bit_cnt, started, current, sil_cnt;
   int bitpos;
-  uint32_t ring_pos, ring_len, amp_pos, amp_len, cur_word, dcur_word;
   int out_n;
   uint32_t dvote, silx, flag;
   uint32_t dlast, dcnt;  // ring position behind the newest doubtful hard bit (0: none yet); doubtful bits put since the
                          // last gap of total_bits + 32 positions without any (saturating)
+  uint32_t sync_det, eod_ev;
 };
 
-constexpr int kFParkU = 23;  // pre-filter state (2 float words) + 21 state-machine words
-
-__device__ __forceinline__ void fb_load(FastB& b, const uint32_t (*pu)[32], int lane) {
-  b.sil_thr = __uint_as_float(pu[2][lane]);
-  b.gsc = pu[3][lane]; b.gmod = pu[4][lane]; b.bsc = pu[5][lane]; b.next_idx = pu[6][lane];
-  b.bit_acc = pu[7][lane]; b.bit_cnt = pu[8][lane];
-  const uint32_t f = pu[9][lane];
-  b.started = f & 1u; b.bitpos = (int)((f >> 8) & 0xffu) - 1; b.current = (f >> 16) & 0xffu;
-  b.sil_cnt = pu[10][lane]; b.ring_pos = pu[11][lane]; b.ring_len = pu[12][lane];
-  b.amp_pos = pu[13][lane]; b.amp_len = pu[14][lane]; b.cur_word = pu[15][lane]; b.out_n = (int)pu[16][lane];
-  b.dcur_word = pu[17][lane]; b.dvote = pu[18][lane]; b.silx = pu[19][lane]; b.dlast = pu[20][lane];
-  b.flag = pu[21][lane]; b.dcnt = pu[22][lane];
-}
-__device__ __forceinline__ void fb_store(const FastB& b, uint32_t (*pu)[32], int lane) {
-  pu[2][lane] = __float_as_uint(b.sil_thr);
-  pu[3][lane] = b.gsc; pu[4][lane] = b.gmod; pu[5][lane] = b.bsc; pu[6][lane] = b.next_idx;
-  pu[7][lane] = b.bit_acc; pu[8][lane] = b.bit_cnt;
-  pu[9][lane] = (b.started & 1u) | ((uint32_t)(b.bitpos + 1) << 8) | ((b.current & 0xffu) << 16);
-  pu[10][lane] = b.sil_cnt; pu[11][lane] = b.ring_pos; pu[12][lane] = b.ring_len;
-  pu[13][lane] = b.amp_pos; pu[14][lane] = b.amp_len; pu[15][lane] = b.cur_word; pu[16][lane] = (uint32_t)b.out_n;
-  pu[17][lane] = b.dcur_word; pu[18][lane] = b.dvote; pu[19][lane] = b.silx; pu[20][lane] = b.dlast;
-  pu[21][lane] = b.flag; pu[22][lane] = b.dcnt;
-}
-
-__device__ __forceinline__ void reset_state_fa2(FastA2& s) {
-  s.lc = 1.0f; s.ls = 0.0f;
+__device__ __forceinline__ void reset_state_fdsp(FastDsp& s, const FskDerived& d) {
+  s.e0 = make_float2(1.0f, 0.0f); s.e1 = make_float2(d.f_cw, d.f_sw);  // localOscPhase = 0 at the next sample
   s.w1 = make_float2(0.0f, 0.0f); s.w2 = make_float2(0.0f, 0.0f);
   s.ow1 = s.ow2 = 0.0f;
   s.psi = 1.0f; s.psq = 0.0f;  // lastPhase = 0
-  s.acc = make_float2(0.0f, 0.0f);
   s.E = 0.0f; s.rsp = 0.0f;    // the error envelope belongs to the post filter's state
-  s.dsc = 0;
 }
 __device__ __forceinline__ void reset_state_fb(FastB& b) {
   b.gsc = 0; b.gmod = 0; b.bsc = 0; b.bit_acc = 0; b.bit_cnt = 0; b.next_idx = 0;
@@ -89,6 +67,10 @@ __device__ __forceinline__ void reset_state_fb(FastB& b) {
   b.started = 0;
   b.sil_cnt = 0;
   b.dvote = 0; b.silx = 0;
+}
+__device__ __forceinline__ void set_thresholds(FastB& b, const FskDerived& d) {
+  b.thr_lo = b.sil_thr * (1.0f - d.f_amp_eps);
+  b.thr_hi = b.sil_thr * (1.0f + d.f_amp_eps);
 }
 
 // ---- state conversion: direct form I history <-> normal-form state (float64, once per launch and stream) ----
@@ -124,11 +106,18 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+// a positive normal float as a double scaled by 2^k, by exponent arithmetic: one 32 x 32 -> 64-bit multiply-add
+__device__ __forceinline__ double pos_f32_as_f64(float v, int k) {
+  const unsigned long long q =
+      (unsigned long long)__float_as_uint(v) * 0x20000000ull + ((unsigned long long)(uint32_t)(896 + k) << 52);
+  return __longlong_as_double((long long)q);
+}
 // atan2(y, x), absolute error <= 1.5e-7 (degree-15 odd minimax on [0, 1] + float32 rounding); atan2(0, 0) = 0.
+// Octant fix-ups as |b - a| with b = 0 or pi/2 (pi): two compare + select pairs, no third select.
 __device__ __forceinline__ float fast_atan2f(float y, float x) {
   const float ax = fabsf(x), ay = fabsf(y);
-  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-  const float r = mx > 1e-37f ? mn * rcp_approx(mx) : 0.0f;  // (the reciprocal flushes denormals)
+  const float mx = fmaxf(fmaxf(ax, ay), 1e-37f), mn = fminf(ax, ay);
+  const float r = mn * rcp_approx(mx);
   const float z = r * r;
   float p = -0.004054499790072441f;
   p = fmaf(p, z, 0.021862739697098732f);
@@ -138,85 +127,96 @@ __device__ __forceinline__ float fast_atan2f(float y, float x) {
   p = fmaf(p, z, 0.19946566224098206f);
   p = fmaf(p, z, -0.33329862356185913f);
   p = fmaf(p, z, 0.9999993443489075f);
-  float a = p * r;
-  a = ay > ax ? 1.5707963267948966f - a : a;
-  a = x < 0.0f ? 3.141592653589793f - a : a;
-  return copysignf(a, y);
+  const float a = p * r;
+  const float b1 = ay > ax ? 1.5707963267948966f : 0.0f;
+  const float t1 = b1 - a;          // |t1| = the angle in the first quadrant
+  const float b2 = x < 0.0f ? 3.141592653589793f : 0.0f;
+  const float t2 = b2 - fabsf(t1);  // |t2| = the angle in the upper half plane
+  return copysignf(t2, y);
 }
 
-// ---- phase A1: float64 AGC (the exact kernel's arithmetic) + float32 normal-form pre-filter ----
-__device__ __forceinline__ float fast_a1_sample(double& gain, float& w1, float& w2, float x, const FskDerived& d, bool agc,
-                                                double att, double rel) {
-  const float sg_agc = (float)((double)x * gain);
-  const float sg = agc ? sg_agc : x;
-  const float level = fabsf(sg);
-  const float lv = fmaxf(level, 5e-31f);
-  const double r = (double)rcp_approx(lv);
-  const double inv = fma(r, fma(-(double)lv, r, 1.0), r);
-  const double rate = (agc && level > 0.0f) ? (level > 0.5f ? att : rel) : 0.0;
-  double g = fma(fma(inv, 0.5, -gain), rate, gain);
-  {
-    const bool over = g > 10.0, under = g < 0.1;
-    g = over ? 10.0 : g;
-    g = under ? 0.1 : g;
-  }
+// ---- phase A1: float64 AGC (fsk.ts:52-76).  Returns the scaled sample, exactly the reference's float32 store. ----
+__device__ __forceinline__ float fast_agc(double& gain, float x, double att, double rel) {
+  const float sa = (float)((double)fabsf(x) * gain);  // |samples[i] * gain| as stored in the Float32Array
+  const float lv = fmaxf(sa, 5e-31f);
+  const float r0 = rcp_approx(lv);
+  // 0.5 / level to 1e-14: Newton step on the seed; seed and level enter float64 by exponent arithmetic
+  const double r = pos_f32_as_f64(r0, 0), l = pos_f32_as_f64(lv, 0);
+  const double e = fma(-l, r, 1.0);
+  const double h = fma(e, 0.5, 0.5);
+  const double u = fma(r, h, -gain);  // 0.5 / level - gain
+  // gain += u * (level > 0.5 ? attack : level > 0 ? release : nothing), then the clamp to [0.1, 10]
+  const double rate = sa > 0.5f ? att : (sa > 0.0f ? rel : 0.0);
+  double g = fma(u, rate, gain);
+  if (g > 10.0) g = 10.0;
+  if (g < 0.1) g = 0.1;
   gain = g;
-  const float y = fmaf(d.f_pre_k2, w2, fmaf(d.f_pre_k1, w1, d.f_pre_k0 * sg));
-  const float n1 = fmaf(d.f_pre_sg, w1, fmaf(-d.f_pre_om, w2, sg));
-  const float n2 = fmaf(d.f_pre_om, w1, d.f_pre_sg * w2);
+  return copysignf(sa, x);
+}
+
+// ---- one PAIR of input samples through the pre-filter (normal form, two samples per step) ----
+__device__ __forceinline__ void fast_pre_pair(float& w1, float& w2, float s0, float s1, const FskDerived& d, float& p0,
+                                              float& p1) {
+  p0 = fmaf(d.f_pre_k2, w2, fmaf(d.f_pre_k1, w1, d.f_pre_k0 * s0));
+  p1 = fmaf(d.f_pre_c2, w2, fmaf(d.f_pre_c1, w1, fmaf(d.f_pre_k1, s0, d.f_pre_k0 * s1)));
+  const float n1 = fmaf(d.f_pre_A, w1, fmaf(-d.f_pre_B, w2, fmaf(d.f_pre_sg, s0, s1)));
+  const float n2 = fmaf(d.f_pre_B, w1, fmaf(d.f_pre_A, w2, d.f_pre_om * s0));
   w1 = n1; w2 = n2;
-  return y;
 }
 
-// ---- phase A2: one input sample through the LO and the packed I/Q low-pass ----
-__device__ __forceinline__ float2 fast_a2_half(FastA2& s, float pf, const FskDerived& d) {
-  const float2 x = __fmul2_rn(make_float2(pf, pf), make_float2(s.lc, s.ls));
-  const float nc = fmaf(s.lc, d.f_cw, -(s.ls * d.f_sw));
-  const float nsn = fmaf(s.ls, d.f_cw, s.lc * d.f_sw);
-  s.lc = nc; s.ls = nsn;
-  const float2 k0 = make_float2(d.f_lp_k0, d.f_lp_k0), k1 = make_float2(d.f_lp_k1, d.f_lp_k1);
-  const float2 k2 = make_float2(d.f_lp_k2, d.f_lp_k2), sg = make_float2(d.f_lp_sg, d.f_lp_sg);
-  const float2 om = make_float2(d.f_lp_om, d.f_lp_om), nom = make_float2(-d.f_lp_om, -d.f_lp_om);
-  const float2 y = __ffma2_rn(k2, s.w2, __ffma2_rn(k1, s.w1, __fmul2_rn(k0, x)));
-  const float2 n1 = __ffma2_rn(sg, s.w1, __ffma2_rn(nom, s.w2, x));
-  const float2 n2 = __ffma2_rn(om, s.w1, __fmul2_rn(sg, s.w2));
+// ---- one pair through the LO and the packed I/Q low-pass: returns the sum of the two outputs (2 avgI, 2 avgQ) ----
+__device__ __forceinline__ float2 fast_iq_pair(FastDsp& s, float p0, float p1, const FskDerived& d) {
+  const float2 x0 = __fmul2_rn(make_float2(p0, p0), s.e0);
+  const float2 x1 = __fmul2_rn(make_float2(p1, p1), s.e1);
+  // both phasors turn by 2 omega
+  const float c = d.f_c2w, sn = d.f_s2w;
+  s.e0 = make_float2(fmaf(s.e0.x, c, -(s.e0.y * sn)), fmaf(s.e0.y, c, s.e0.x * sn));
+  s.e1 = make_float2(fmaf(s.e1.x, c, -(s.e1.y * sn)), fmaf(s.e1.y, c, s.e1.x * sn));
+  const float2 k0 = make_float2(d.f_lp_k0, d.f_lp_k0), kx0 = make_float2(d.f_lp_kx0, d.f_lp_kx0);
+  const float2 kw1 = make_float2(d.f_lp_kw1, d.f_lp_kw1), kw2 = make_float2(d.f_lp_kw2, d.f_lp_kw2);
+  const float2 A = make_float2(d.f_lp_A, d.f_lp_A), B = make_float2(d.f_lp_B, d.f_lp_B), nB = make_float2(-d.f_lp_B, -d.f_lp_B);
+  const float2 sg = make_float2(d.f_lp_sg, d.f_lp_sg), om = make_float2(d.f_lp_om, d.f_lp_om);
+  const float2 sum = __ffma2_rn(kw2, s.w2, __ffma2_rn(kw1, s.w1, __ffma2_rn(kx0, x0, __fmul2_rn(k0, x1))));
+  const float2 n1 = __ffma2_rn(A, s.w1, __ffma2_rn(nB, s.w2, __ffma2_rn(sg, x0, x1)));
+  const float2 n2 = __ffma2_rn(B, s.w1, __ffma2_rn(A, s.w2, __fmul2_rn(om, x0)));
   s.w1 = n1; s.w2 = n2;
-  return y;
+  return sum;
 }
 
-// decimated-rate discriminator on the summed pair (2 avgI, 2 avgQ): hard bit, doubt flag, amplitude (fsk.ts:246-264)
-__device__ __forceinline__ void fast_a2_decim(FastA2& s, float2 sum, const FskDerived& d, uint32_t& bit, uint32_t& dbit,
-                                              float& amp) {
+// Decimated-rate discriminator on the summed pair (fsk.ts:246-264).  Returns the amplitude; `nf` receives MINUS the
+// filtered phase difference (sign bit set <=> hard bit 1), `dv` a value whose sign bit is set <=> the bit is doubtful.
+template <bool TAP>
+__device__ __forceinline__ float fast_decim(FastDsp& s, float2 sum, const FskDerived& d, float& nf, float& dv, float* tap) {
   const float si = sum.x, sq = sum.y;
   // wrapped (phase - lastPhase) straight from the two phasors; the LO's float32 frequency offset is a known constant
   const float cross = fmaf(sq, s.psi, -(si * s.psq));
   const float dot = fmaf(si, s.psi, sq * s.psq);
   const float pd = fast_atan2f(cross, dot) - d.f_dphi_bias;
   const float pw = fmaf(si, si, sq * sq);
-  const bool tiny = !(pw > 1e-30f);  // also catches NaN
-  const float rs = tiny ? 0.0f : rsqrt_approx(pw);
-  amp = 0.5f * pw * rs;              // fsk.ts:252 (amplitude of the averaged pair)
+  const float rs = rsqrt_approx(fmaxf(pw, 1e-30f));  // a vanishing phasor: rs ~ 1e15 makes the band below huge
+  const float amp = (0.5f * pw) * rs;                // fsk.ts:252 (amplitude of the averaged pair)
   s.psi = si; s.psq = sq;
-  const float fpd = fmaf(d.f_lp_k2, s.ow2, fmaf(d.f_lp_k1, s.ow1, d.f_lp_k0 * pd));
+  nf = -fmaf(d.f_lp_k2, s.ow2, fmaf(d.f_lp_k1, s.ow1, d.f_lp_k0 * pd));
   const float n1 = fmaf(d.f_lp_sg, s.ow1, fmaf(-d.f_lp_om, s.ow2, pd));
   const float n2 = fmaf(d.f_lp_om, s.ow1, d.f_lp_sg * s.ow2);
   s.ow1 = n1; s.ow2 = n2;
-  bit = fpd > 0.0f ? 1u : 0u;
   // doubt band: the float32 error of a phasor's angle grows as (recent amplitude scale) / (its own length); the post
   // filter spreads it with |h(j)| <= gamma rho^j; a raw difference next to +-pi may have wrapped the other way (2 pi)
   s.S = fmaxf(amp, s.S * 0.9921875f);
   const float hrs = 0.5f * rs;
-  const float e1 = d.f_kappa * s.S * (hrs + s.rsp);
+  const float e1 = (d.f_kappa * s.S) * (hrs + s.rsp);
   s.rsp = hrs;
-  float et = tiny ? 10.0f : e1;  // a vanishing phasor has no usable angle
-  if (fabsf(fabsf(pd) - 3.14159265f) < fmaf(4.0f, e1, d.f_bc_delta)) et += 6.3f;
+  const float et = (3.14159265f - fabsf(pd) < fmaf(4.0f, e1, d.f_bc_delta)) ? e1 + 6.3f : e1;
   s.E = fmaf(d.f_rho_e, s.E, d.f_gamma * et);
-  dbit = fabsf(fpd) < s.E + d.f_eps0 ? 1u : 0u;
+  const float band = s.E + d.f_eps0;
+  dv = fabsf(nf) - band;
+  if (TAP) { tap[0] = -nf; tap[1] = band; }
+  return amp;
 }
 
-// Upper bound of the doubtful hard bits among the newest total_bits ring samples, without touching the doubt ring:
-// dcnt counts the doubtful bits put since the last gap of total_bits + 32 positions without any; dlast is the position
-// behind the newest one.  Once ring_pos - dlast exceeds that gap the window is clean.
+// Upper bound of the doubtful hard bits among the newest total_bits ring samples: dcnt counts the doubtful bits put
+// since the last gap of total_bits + 32 positions without any; dlast is the position behind the newest one.  Once
+// ring_pos - dlast exceeds that gap the window is clean.
 __device__ __forceinline__ void doubt_note(FastB& b, uint32_t p, uint32_t dchunk, const FskDerived& d) {
   if (b.dlast != 0u && p - b.dlast >= (uint32_t)d.total_bits + 32u) b.dcnt = 0u;
   b.dcnt = min(b.dcnt + (uint32_t)__popc(dchunk), 0xffffu);
@@ -225,26 +225,6 @@ __device__ __forceinline__ void doubt_note(FastB& b, uint32_t p, uint32_t dchunk
 __device__ __forceinline__ int doubt_bound(FastB& b, uint32_t pos, const FskDerived& d) {
   if (pos - b.dlast >= (uint32_t)d.total_bits + 32u) b.dcnt = 0u;
   return (int)b.dcnt;
-}
-// exact number of doubtful hard bits among the newest total_bits ring samples (rare: only when the bound matters)
-__device__ __noinline__ int doubt_count(const uint32_t* __restrict__ dring, uint32_t pos, const FskDerived& d) {
-  const uint32_t lo = pos - (uint32_t)d.total_bits;
-  const uint32_t o = lo & 31u;
-  const uint32_t wmask = (uint32_t)(d.ring_words - 1);
-  uint32_t w = (lo >> 5) & wmask;
-  uint32_t prev = dring[w];
-  int n = 0;
-  int left = d.total_bits;
-  while (left > 0) {
-    w = (w + 1u) & wmask;
-    const uint32_t cur = dring[w];
-    uint32_t v = __funnelshift_r(prev, cur, o);
-    if (left < 32) v &= (1u << left) - 1u;
-    n += __popc(v);
-    prev = cur;
-    left -= 32;
-  }
-  return n;
 }
 
 // sync_mismatches0v (fsk_demod.cuh) with a caller-supplied cut-off: with D doubtful bits in the window the search may
@@ -350,15 +330,13 @@ __device__ __forceinline__ bool process_byte_fast(FastB& b, int bit, const Demod
   return false;
 }
 
-// One decimated sample of processDownsampledBit (fsk.ts:278-344) AFTER the ring puts, with doubt tracking
-// (oracle/fastmodel.c: fm_decim is the same logic sample by sample).  sil / adoubt: this sample's amplitude is below
-// the silence threshold / within the doubt band of it.  Returns true when resetState() ran.
+// One decimated sample of processDownsampledBit (fsk.ts:278-344) AFTER the ring puts, with doubt tracking.
+// sil / adoubt: this sample's amplitude is taken for silent / is within the doubt band of the threshold.
+// ring_pos: the sync ring's write position behind this sample.  Returns true when resetState() ran.
 __device__ __forceinline__ bool sm_step_fast(FastB& b, int bit, bool sil, bool adoubt, uint32_t ring_pos, bool ring_ready,
-                                             uint32_t amp_next, uint32_t amp_len, const DemodArgs& a, int li,
-                                             uint8_t* out_row, bool& thr_changed) {
+                                          uint32_t amp_next, uint32_t amp_len, const DemodArgs& a, int li,
+                                          uint8_t* out_row, bool& thr_changed) {
   const FskDerived& d = a.d;
-  const long ns = a.n_local;
-  uint32_t* ring = ring_of(a, li);
   b.gsc++;
   b.gmod = (b.gmod + 1u == (uint32_t)d.check_period) ? 0u : b.gmod + 1u;
   // silence / EOD — fsk.ts:285-295.  silx: bit 31 = a doubtful compare is pending, low bits = the silent run the
@@ -372,33 +350,25 @@ __device__ __forceinline__ bool sm_step_fast(FastB& b, int bit, bool sil, bool a
     b.silx = 0u;
   }
   if (sil && b.sil_cnt >= (uint32_t)d.eod_count) {
-    a.u32[(long)U_EOD_EV * ns + li]++;  // emit('eod')
+    b.eod_ev++;  // emit('eod')
     reset_state_fb(b);
     return true;
   }
   if (!b.started) {
     // fsk.ts:297-328
-    const bool due = d.check_period > 0 && b.gmod == 0u;
-    if (due && ring_ready && d.total_bits > 0) {
-      const uint32_t wmask = (uint32_t)(d.ring_words - 1);
-      uint32_t* dring = a.doubt_ring + (size_t)li * (size_t)d.ring_words;
-      if ((b.ring_pos & 31u) != 0u) {  // flush the register copies of the newest (partial) words
-        ring_st<true>(ring + ((b.ring_pos >> 5) & wmask), b.cur_word);
-        dring[(b.ring_pos >> 5) & wmask] = b.dcur_word;
-      }
-      // doubtful bits in the window: a cheap upper bound first, the exact count only when the bound could matter
-      int D = b.dcnt != 0u ? doubt_bound(b, ring_pos, d) : 0;
-      const int mism = sync_mismatches_fast_call(ring, ring_pos, d, d.max_mismatch + D);
-      if (D > 0 && ((mism + D <= d.max_mismatch) != (mism - D <= d.max_mismatch))) {
-        D = doubt_count(dring, ring_pos, d);
-        if (D > 0 && ((mism + D <= d.max_mismatch) != (mism - D <= d.max_mismatch))) b.flag |= WAM_FLAG_SYNC;
-      }
+    const bool due = b.gmod == 0u;
+    if (due && ring_ready) {
+      // doubtful bits in the window: an upper bound; a decision the bound could turn flags the stream
+      const int D = b.dcnt != 0u ? doubt_bound(b, ring_pos, d) : 0;
+      const int mism = sync_mismatches_fast_call(ring_of(a, li), ring_pos, d, d.max_mismatch + D);
+      if (D > 0 && ((mism + D <= d.max_mismatch) != (mism - D <= d.max_mismatch))) b.flag |= WAM_FLAG_SYNC;
       if (mism <= d.max_mismatch) {
         b.started = 1;
         b.current = 0; b.bitpos = 0;
         b.bit_acc = 0; b.bit_cnt = 0; b.bsc = 0; b.next_idx = 0; b.dvote = 0;
-        a.u32[(long)U_SYNC_DET * ns + li]++;
+        b.sync_det++;
         b.sil_thr = (float)amp_ring_threshold(amp_of(a, li), amp_next, amp_len, (uint32_t)d.amp_phys);
+        set_thresholds(b, d);
         thr_changed = true;
       }
     }
@@ -423,89 +393,20 @@ __device__ __forceinline__ bool sm_step_fast(FastB& b, int bit, bool sil, bool a
     b.bit_acc = 0; b.bit_cnt = 0; b.dvote = 0;
     b.next_idx += (uint32_t)d.dspb;
     const bool rst = process_byte_fast(b, decided, a, li, out_row);
-    if (!rst && !b.started && d.check_period > 0) b.gmod = b.gsc % (uint32_t)d.check_period;
+    if (!rst && !b.started) b.gmod = b.gsc % (uint32_t)d.check_period;
     return rst;
   }
   return false;
 }
 
-// bulk put of `cnt` bits (chunk) at ring position p into a bit-packed ring with a register copy of the newest word
-__device__ __forceinline__ void ring_put_bulk(uint32_t* ring, uint32_t wmask, uint32_t& cur, uint32_t p, uint32_t cnt,
-                                              uint32_t chunk, bool hinted) {
-  const uint32_t o = p & 31u;
-  cur = (cur & ((1u << o) - 1u)) | (chunk << o);
-  if (o + cnt >= 32u) {
-    if (hinted) ring_st<true>(ring + ((p >> 5) & wmask), cur);
-    else ring[(p >> 5) & wmask] = cur;
-    cur = (o + cnt > 32u) ? (chunk >> (32u - o)) : 0u;
-  }
-}
-
-// Event-driven state machine for one tile with doubt tracking.  bits / dmask: hard decisions and doubt flags of the
-// decimated samples 0..nk-1, amp[k * 32]: their amplitudes (f32, smem).  Returns the decimated index at which
-// resetState() ran, or -1.
-__device__ __forceinline__ int sm_tile_events_fast(FastB& b, uint32_t bits, uint32_t dmask, const float* __restrict__ amp,
-                                                   int b_from, int nk, uint32_t pos_t0, uint32_t len_t0, uint32_t slot_t0,
+// Event-driven state machine for one aligned tile with doubt tracking.  bits / dmask / silent / adoubt: hard
+// decisions, doubt flags, silence flags and silence-doubt flags of the decimated samples 0..15 (bit k = sample k);
+// the ring puts of the tile are done by the caller.  Returns the decimated index at which resetState() ran, or -1.
+__device__ __forceinline__ int sm_tile_events_fast(FastB& b, uint32_t bits, uint32_t dmask, uint32_t silent, uint32_t adoubt,
+                                                   int b_from, uint32_t pos_t0, uint32_t len_t0, uint32_t slot_t0,
                                                    uint32_t alen_t0, const DemodArgs& a, int li, uint8_t* out_row) {
   const FskDerived& d = a.d;
-  uint32_t* ring = ring_of(a, li);
-  uint32_t* dring = a.doubt_ring + (size_t)li * (size_t)d.ring_words;
-  float* aring = amp_of(a, li);
-  const uint32_t wmask = (uint32_t)(d.ring_words - 1);
-
-  uint32_t silent = 0u, adoubt = 0u;
-  // ---- bulk ring puts for samples [b_from, nk) — fsk.ts:281-282
-  {
-    const uint32_t p = pos_t0 + (uint32_t)b_from;
-    if (b_from > 0) {
-      // replay pass: the words holding position p may already have been flushed
-      ring_st<true>(ring + ((b.ring_pos >> 5) & wmask), b.cur_word);
-      dring[(b.ring_pos >> 5) & wmask] = b.dcur_word;
-      b.cur_word = ring[(p >> 5) & wmask];
-      b.dcur_word = dring[(p >> 5) & wmask];
-    }
-    const uint32_t cnt = (uint32_t)(nk - b_from);
-    const uint32_t keep = (1u << cnt) - 1u;
-    ring_put_bulk(ring, wmask, b.cur_word, p, cnt, (bits >> b_from) & keep, true);
-    const uint32_t dchunk = (dmask >> b_from) & keep;
-    ring_put_bulk(dring, wmask, b.dcur_word, p, cnt, dchunk, false);
-    if (dchunk) doubt_note(b, p, dchunk, d);
-    b.ring_pos = pos_t0 + (uint32_t)nk;
-    uint32_t slot = slot_t0 + (uint32_t)b_from;
-    if (slot >= (uint32_t)d.amp_phys) slot -= (uint32_t)d.amp_phys;
-    {
-      // amplitude-ring puts (fsk.ts:282) and, from the same reads, the silence flags (fsk.ts:286) and their doubt
-      // flags: positive floats order like their bit patterns, so both come from one integer difference
-      const int it = __float_as_int(b.sil_thr);
-      const uint32_t K = (uint32_t)d.f_amp_ulps;
-      if (b_from == 0 && nk == kTile / 2 && (slot & 3u) == 0u && slot + (uint32_t)(kTile / 2) <= (uint32_t)d.amp_phys) {
-#pragma unroll
-        for (int q = 0; q < kTile / 8; ++q) {
-          const float a0 = amp[(4 * q) * 32], a1 = amp[(4 * q + 1) * 32], a2 = amp[(4 * q + 2) * 32], a3 = amp[(4 * q + 3) * 32];
-          amp_st4(aring + slot + 4 * q, make_float4(a0, a1, a2, a3));
-          const int d0 = __float_as_int(a0) - it, d1 = __float_as_int(a1) - it, d2 = __float_as_int(a2) - it,
-                    d3 = __float_as_int(a3) - it;
-          silent |= ((d0 < 0 ? 1u : 0u) | (d1 < 0 ? 2u : 0u) | (d2 < 0 ? 4u : 0u) | (d3 < 0 ? 8u : 0u)) << (4 * q);
-          adoubt |= (((uint32_t)d0 + K <= 2u * K ? 1u : 0u) | ((uint32_t)d1 + K <= 2u * K ? 2u : 0u) |
-                     ((uint32_t)d2 + K <= 2u * K ? 4u : 0u) | ((uint32_t)d3 + K <= 2u * K ? 8u : 0u)) << (4 * q);
-        }
-      } else {
-        float* p2 = aring + slot;
-        int until_wrap = d.amp_phys - (int)slot;
-#pragma unroll 4
-        for (int k = b_from; k < nk; ++k) {
-          const float av = amp[k * 32];
-          amp_st(p2, av);
-          ++p2;
-          if (--until_wrap == 0) p2 = aring;
-          const int dd = __float_as_int(av) - it;
-          silent |= (dd < 0 ? 1u : 0u) << k;
-          adoubt |= ((uint32_t)dd + K <= 2u * K ? 1u : 0u) << k;
-        }
-      }
-    }
-  }
-
+  constexpr int nk = kTile / 2;
   int k = b_from;
   while (k < nk) {
     // next sample at which an event can happen
@@ -518,7 +419,7 @@ __device__ __forceinline__ int sm_tile_events_fast(FastB& b, uint32_t bits, uint
       if (adoubt >> k) k_evt = min(k_evt, k + __ffs((int)(adoubt >> k)) - 1);  // a doubtful compare is an event
     }
     if (!b.started) {
-      if (d.check_period > 0) k_evt = min(k_evt, k + (int)((uint32_t)d.check_period - 1u - b.gmod));
+      k_evt = min(k_evt, k + (int)((uint32_t)d.check_period - 1u - b.gmod));
     } else {
       const uint32_t nb = b.bsc + 1u;
       k_evt = min(k_evt, k + (int)(b.next_idx > nb ? b.next_idx - nb : 0u));
@@ -540,7 +441,7 @@ __device__ __forceinline__ int sm_tile_events_fast(FastB& b, uint32_t bits, uint
     }
     if (b.started && (dmask >> k)) {
       // doubtful samples of the running vote in [k, k_evt] (the event sample included)
-      const uint32_t m2 = (k_evt >= 31 ? 0xffffffffu : ((2u << k_evt) - 1u)) & ~((1u << k) - 1u) & dmask;
+      const uint32_t m2 = ((2u << min(k_evt, nk - 1)) - 1u) & ~((1u << k) - 1u) & dmask;
       b.dvote += (uint32_t)__popc(bits & m2) + ((uint32_t)__popc(~bits & m2) << 16);
     }
     if (k_evt >= nk) break;
@@ -555,14 +456,17 @@ __device__ __forceinline__ int sm_tile_events_fast(FastB& b, uint32_t bits, uint
                      ready, slot_next, alen, a, li, out_row, thr_changed))
       return k_evt;
     if (thr_changed) {
-      silent = 0u; adoubt = 0u;
-      const int it = __float_as_int(b.sil_thr);
-      const uint32_t K = (uint32_t)d.f_amp_ulps;
+      // new silence threshold: the flags of the rest of the tile from the amplitudes just stored (no wrap inside a tile)
+      const float* ar = amp_of(a, li) + slot_t0;
+      uint32_t lo = 0u, hi = 0u;
       for (int kk = k_evt + 1; kk < nk; ++kk) {
-        const int dd = __float_as_int(amp[kk * 32]) - it;
-        silent |= (dd < 0 ? 1u : 0u) << kk;
-        adoubt |= ((uint32_t)dd + K <= 2u * K ? 1u : 0u) << kk;
+        const float av = ar[kk];
+        lo |= (av < b.thr_lo ? 1u : 0u) << kk;
+        hi |= (av < b.thr_hi ? 1u : 0u) << kk;
       }
+      const uint32_t keep = (2u << k_evt) - 1u;
+      silent = (silent & keep) | hi;
+      adoubt = (adoubt & keep) | (lo ^ hi);
     }
     k = k_evt + 1;
   }
@@ -570,8 +474,10 @@ __device__ __forceinline__ int sm_tile_events_fast(FastB& b, uint32_t bits, uint
 }
 
 // Grid: one warp (32 streams) per CTA, TMA-staged tiles, time slabs as in fsk_demod_exact_kernel<.., STAGE_TMA>.
-// Common case only (host: fast_eligible): rows contiguous and 16-byte aligned, integral sync ring, eod_count > 16,
-// by-value sync template, no write-back / tap / ragged counts.
+// Common case only (host: fast path eligibility): rows contiguous and 16-byte aligned, aligned calls (n a multiple of
+// 32 ever since reset), integral sync ring, eod_count > 16, by-value sync template, no write-back / ragged counts.
+// TAP: debug variant writing (filteredPhaseDiff, doubt band) per decimated sample into a.tap[row][2k, 2k + 1].
+template <bool TAP>
 __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_fast_kernel(const __grid_constant__ DemodLaunch L) {
   int gi = 0;
 #pragma unroll
@@ -580,16 +486,13 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_fast_kerne
   const DemodArgs& a = L.g[gi];
   __shared__ __align__(1024) float tiles[kStages][kTile * kTile];
   __shared__ __align__(8) uint64_t tma_bar[kStages];
-  __shared__ __align__(128) float pfbuf[kTile * 32];  // pre-filtered samples [i][lane]
-  __shared__ double park_g[32];                       // AGC gain
-  __shared__ uint32_t park_u[kFParkU][32];
+  __shared__ __align__(128) float pfbuf[kTile * 32];  // pre-filtered samples [i][lane] (replay after resetState())
 
   const int lane = threadIdx.x;
   const int li = a.l_begin + ((int)blockIdx.x - L.block_begin[gi]) * 32 + lane;
   const bool active = li < a.l_end;
   const FskDerived& d = a.d;
   const long ns = a.n_local;
-  bool slab_timeout = false;
   if (L.slab_done != nullptr && L.slab > 0) {
     // time-slab hand-over (launch_slabbed): bounded spin; on expiry the streams are flagged and left untouched
     const int* flag = L.slab_done + blockIdx.x;
@@ -600,23 +503,27 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_fast_kerne
       if (v >= L.slab) break;
       __nanosleep(256);
     } while (++spins < (1u << 22));
-    slab_timeout = v < L.slab;
-    if (slab_timeout) {
+    if (v < L.slab) {
       if (active) a.u32[(long)U_ERR * ns + li] |= WAM_ERR_SLAB_TIMEOUT;
       return;
     }
   }
-  int row = -1;
-  if (active) row = a.id0 + li - a.row_base;
+  const int row = active ? a.id0 + li - a.row_base : 0;
+  const int lq = active ? li : a.l_begin;  // inactive lanes shadow the group's first stream and store nothing
 
-  FastA2 s;
-  reset_state_fa2(s);
-  s.S = 0.0f;
-  if (active) {
-    const double* f = a.f64 + li;
-    const uint32_t* u = a.u32 + li;
-    // ---- direct form (the arrays) -> normal form
-    s.lc = (float)f[F_LO_C * ns]; s.ls = (float)f[F_LO_S * ns];
+  // ---- state in: direct form (the arrays) -> normal form
+  FastDsp s;
+  FastB b;
+  double gain;
+  float pw1, pw2;
+  uint32_t ring_pos0, ring_len0, amp_pos0, amp_len0, flag_in;
+  {
+    const double* f = a.f64 + lq;
+    const uint32_t* u = a.u32 + lq;
+    reset_state_fdsp(s, d);
+    s.e0 = make_float2((float)f[F_LO_C * ns], (float)f[F_LO_S * ns]);
+    s.e1 = make_float2((float)(f[F_LO_C * ns] * d.cos_omega - f[F_LO_S * ns] * d.sin_omega),
+                       (float)(f[F_LO_S * ns] * d.cos_omega + f[F_LO_C * ns] * d.sin_omega));
     float iw1, iw2, qw1, qw2;
     df_to_normal(d.lp_b1, d.lp_b2, d.lp_a1, d.lp_a2, d.lp_nk1, d.lp_nk2, d.lp_nsg, d.lp_nom, f[F_IX1 * ns], f[F_IX2 * ns],
                  f[F_IY1 * ns], f[F_IY2 * ns], iw1, iw2);
@@ -630,39 +537,33 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_fast_kerne
       sincos(f[F_LAST_PHASE * ns], &sn, &cs);
       s.psi = (float)cs; s.psq = (float)sn;
     }
-    s.acc = make_float2((float)f[F_IACC * ns], (float)f[F_QACC * ns]);
     s.S = (float)f[F_FAST_S * ns]; s.E = (float)f[F_FAST_E * ns]; s.rsp = (float)f[F_FAST_RSP * ns];
-    s.dsc = u[U_DSC * ns];
-    float pw1, pw2;
     df_to_normal(d.pre_b1, d.pre_b2, d.pre_a1, d.pre_a2, d.pre_nk1, d.pre_nk2, d.pre_nsg, d.pre_nom, f[F_PX1 * ns],
                  f[F_PX2 * ns], f[F_PY1 * ns], f[F_PY2 * ns], pw1, pw2);
-    park_g[lane] = f[F_GAIN * ns];
-    park_u[0][lane] = __float_as_uint(pw1); park_u[1][lane] = __float_as_uint(pw2);
-    FastB b;
+    gain = f[F_GAIN * ns];
     b.sil_thr = (float)f[F_SIL_THR * ns];
+    set_thresholds(b, d);
     b.gsc = u[U_GSC * ns]; b.gmod = u[U_GMOD * ns]; b.bsc = u[U_BSC * ns]; b.next_idx = u[U_NEXT_IDX * ns];
     b.bit_acc = u[U_BIT_ACC * ns]; b.bit_cnt = u[U_BIT_CNT * ns]; b.started = u[U_STARTED * ns];
     b.bitpos = (int)u[U_BITPOS * ns]; b.current = u[U_CURRENT * ns]; b.sil_cnt = u[U_SIL_CNT * ns];
-    b.ring_pos = u[U_RING_POS * ns]; b.ring_len = u[U_RING_LEN * ns];
-    b.amp_pos = u[U_AMP_POS * ns]; b.amp_len = u[U_AMP_LEN * ns];
+    ring_pos0 = u[U_RING_POS * ns]; ring_len0 = u[U_RING_LEN * ns];
+    amp_pos0 = u[U_AMP_POS * ns]; amp_len0 = u[U_AMP_LEN * ns];
     b.out_n = a.append ? a.out_len[row] : 0;
     b.dvote = u[U_DVOTE * ns]; b.silx = u[U_SILX * ns]; b.dlast = u[U_LAST_DOUBT * ns]; b.flag = u[U_FLAG * ns];
     b.dcnt = u[U_DCNT * ns];
-    b.cur_word = 0u; b.dcur_word = 0u;
-    if ((b.ring_pos & 31u) != 0u) {
-      const uint32_t wi = (b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1);
-      const uint32_t keep = (1u << (b.ring_pos & 31u)) - 1u;
-      b.cur_word = ring_of(a, li)[wi] & keep;
-      b.dcur_word = a.doubt_ring[(size_t)li * (size_t)d.ring_words + wi] & keep;
-    }
-    fb_store(b, park_u, lane);
+    b.sync_det = u[U_SYNC_DET * ns]; b.eod_ev = u[U_EOD_EV * ns];
+    flag_in = b.flag;
   }
-  __syncwarp();
-  uint8_t* out_row = active ? a.out + (long)row * a.out_stride : nullptr;
-  const uint32_t flag_in = active ? park_u[21][lane] : 0u;
+  uint8_t* out_row = a.out + (long)row * a.out_stride;
+  uint16_t* ring16 = reinterpret_cast<uint16_t*>(ring_of(a, lq));
+  const uint32_t hmask = (uint32_t)(2 * d.ring_words - 1);
+  float* aring = amp_of(a, lq);
+  float* tap_row = TAP ? a.tap + (long)row * a.stride : nullptr;
   uint32_t n_doubt = 0u;
+  const bool agc = d.agc_enabled != 0;
+  const double att = d.agc_attack, rel = d.agc_release;
 
-  const long n_tiles = (a.n + kTile - 1) / kTile;
+  const long n_tiles = a.n / kTile;  // aligned calls: whole tiles only
   const int tma_row0 = a.id0 + a.l_begin + ((int)blockIdx.x - L.block_begin[gi]) * 32 - a.row_base;
   if (lane == 0) {
 #pragma unroll
@@ -672,115 +573,99 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_fast_kerne
   __syncwarp();
   for (int p = 0; p < kStages - 1; ++p)
     if (p < n_tiles && lane == 0) tma_load_tile(tiles[p], &L.tmap[gi], &tma_bar[p], p * kTile, tma_row0);
+  uint32_t slot_t0 = amp_pos0;
   for (long t = 0; t < n_tiles; ++t) {
     const long tn = t + kStages - 1;
     if (tn < n_tiles && lane == 0)
       tma_load_tile(tiles[tn % kStages], &L.tmap[gi], &tma_bar[tn % kStages], (int)(tn * kTile), tma_row0);
     tma_wait(&tma_bar[t % kStages], (uint32_t)((t / kStages) & 1));
     __syncwarp();
-    float* tile = tiles[t % kStages];
-    float* pbuf = tile;  // amplitudes [k][lane] after A1
-    const long t0 = t * kTile;
-    const int len = (int)min((long)kTile, a.n - t0);
+    const float* tile = tiles[t % kStages];
+    const uint32_t pos_t0 = ring_pos0 + (uint32_t)t * (kTile / 2);
+    const uint32_t len_t0 = min(ring_len0 + (uint32_t)t * (kTile / 2), (uint32_t)d.ring_cap_int);
+    const uint32_t alen_t0 = min(amp_len0 + (uint32_t)t * (kTile / 2), (uint32_t)d.amp_cap);
 
-    // ---------------- A1: AGC + pre-filter ----------------
-    if (active) {
-      double gain = park_g[lane];
-      float pw1 = __uint_as_float(park_u[0][lane]), pw2 = __uint_as_float(park_u[1][lane]);
-      const bool agc = d.agc_enabled != 0;
-      const double att = d.agc_attack, rel = d.agc_release;
-      if (len == kTile) {
+    // ---------------- A1 + A2, fused: four pairs (8 input samples) per iteration ----------------
+    if ((t & 1) == 0) {
+      // renormalise the LO rotations (one Newton step towards |e| = 1) every other tile
+      const float m0 = fmaf(s.e0.x, s.e0.x, s.e0.y * s.e0.y), m1 = fmaf(s.e1.x, s.e1.x, s.e1.y * s.e1.y);
+      const float f0 = fmaf(-0.5f, m0, 1.5f), f1 = fmaf(-0.5f, m1, 1.5f);
+      s.e0.x *= f0; s.e0.y *= f0; s.e1.x *= f1; s.e1.y *= f1;
+    }
+    uint32_t bits = 0u, dmask = 0u, slo = 0u, shi = 0u;
 #pragma unroll 1
-        for (int ch = 0; ch < 8; ch += kA1Chunks) {
+    for (int q = 0; q < 4; ++q) {
+      const float4 v0 = *reinterpret_cast<const float4*>(tile + tile_index(lane, 8 * q));
+      const float4 v1 = *reinterpret_cast<const float4*>(tile + tile_index(lane, 8 * q + 4));
+      const float xs[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      float am[4];
 #pragma unroll
-          for (int c = 0; c < kA1Chunks; ++c) {
-            const float4 v = *reinterpret_cast<const float4*>(tile + tile_index(lane, (ch + c) * 4));
-            const float p0 = fast_a1_sample(gain, pw1, pw2, v.x, d, agc, att, rel);
-            const float p1 = fast_a1_sample(gain, pw1, pw2, v.y, d, agc, att, rel);
-            const float p2 = fast_a1_sample(gain, pw1, pw2, v.z, d, agc, att, rel);
-            const float p3 = fast_a1_sample(gain, pw1, pw2, v.w, d, agc, att, rel);
-            float* pfp = pfbuf + ((ch + c) * 4) * 32 + lane;
-            pfp[0] = p0; pfp[32] = p1; pfp[64] = p2; pfp[96] = p3;
-          }
+      for (int j = 0; j < 4; ++j) {
+        float s0 = xs[2 * j], s1 = xs[2 * j + 1];
+        if (agc) {
+          s0 = fast_agc(gain, s0, att, rel);
+          s1 = fast_agc(gain, s1, att, rel);
         }
-      } else {
-#pragma unroll 1
-        for (int i = 0; i < len; ++i) pfbuf[i * 32 + lane] = fast_a1_sample(gain, pw1, pw2, tile[tile_index(lane, i)], d, agc, att, rel);
+        float p0, p1;
+        fast_pre_pair(pw1, pw2, s0, s1, d, p0, p1);
+        float* pfp = pfbuf + (8 * q + 2 * j) * 32 + lane;
+        pfp[0] = p0; pfp[32] = p1;
+        const float2 sum = fast_iq_pair(s, p0, p1, d);
+        float nf, dv;
+        am[j] = fast_decim<TAP>(s, sum, d, nf, dv, TAP ? tap_row + t * kTile + 8 * q + 2 * j : nullptr);
+        bits = __funnelshift_l(__float_as_uint(nf), bits, 1);
+        dmask = __funnelshift_l(__float_as_uint(dv), dmask, 1);
+        slo = __funnelshift_l(__float_as_uint(am[j] - b.thr_lo), slo, 1);
+        shi = __funnelshift_l(__float_as_uint(am[j] - b.thr_hi), shi, 1);
       }
-      park_g[lane] = gain;
-      park_u[0][lane] = __float_as_uint(pw1); park_u[1][lane] = __float_as_uint(pw2);
+      if (active) amp_st4(aring + slot_t0 + 4 * q, make_float4(am[0], am[1], am[2], am[3]));
     }
-    __syncwarp();  // every lane is done with the input tile; its storage becomes pbuf
+    // sample 0 of the tile sits in bit 15 of each mask: turn them round
+    bits = __brev(bits) >> 16; dmask = __brev(dmask) >> 16; slo = __brev(slo) >> 16; shi = __brev(shi) >> 16;
+    uint32_t silent = shi, adoubt = slo ^ shi;
+    __syncwarp();  // every lane is done with the input tile
 
-    // ---------------- A2 + B with replay on resetState() ----------------
-    const int dsc0 = active ? (int)s.dsc : 0;
-    const int v_hi = dsc0 + len;
-    const int nk = v_hi >> 1;
-    int k_from = 0, b_from = 0, v_lo = dsc0;
-    uint32_t bits = 0u, dmask = 0u;
+    // ---------------- B, with replay of A2 on resetState() ----------------
+    int b_from = 0;
     bool redo = active;
-    const uint32_t pos_t0 = park_u[11][lane], len_t0 = park_u[12][lane];
-    const uint32_t slot_t0 = park_u[13][lane], alen_t0 = park_u[14][lane];
-    if (active) {
-      // renormalise the LO rotation (one Newton step towards |(c, s)| = 1)
-      const float m = fmaf(s.lc, s.lc, s.ls * s.ls);
-      const float f = fmaf(-0.5f, m, 1.5f);
-      s.lc *= f; s.ls *= f;
-    }
     while (__any_sync(0xffffffffu, redo)) {
       if (redo) {
-        const uint32_t keepm = (1u << k_from) - 1u;
-        bits &= keepm; dmask &= keepm;
-        if (dsc0 == 0 && (v_hi & 1) == 0) {
-#pragma unroll 2
-          for (int k = k_from; k < nk; ++k) {
-            const float* pfp = pfbuf + (2 * k) * 32 + lane;
-            const float2 y0 = fast_a2_half(s, pfp[0], d);
-            const float2 y1 = fast_a2_half(s, pfp[32], d);
-            uint32_t bit, dbit;
-            float amp;
-            fast_a2_decim(s, __fadd2_rn(y0, y1), d, bit, dbit, amp);
-            bits |= bit << k; dmask |= dbit << k;
-            pbuf[k * 32 + lane] = amp;
-          }
-        } else {
-#pragma unroll 1
-          for (int k = k_from; 2 * k < v_hi; ++k) {
-            const int v0 = 2 * k, v1 = 2 * k + 1;
-            if (v0 >= v_lo) s.acc = fast_a2_half(s, pfbuf[(v0 - dsc0) * 32 + lane], d);  // 0 + y
-            if (v1 < v_hi) {
-              const float2 y = fast_a2_half(s, pfbuf[(v1 - dsc0) * 32 + lane], d);
-              uint32_t bit, dbit;
-              float amp;
-              fast_a2_decim(s, __fadd2_rn(s.acc, y), d, bit, dbit, amp);
-              s.acc = make_float2(0.0f, 0.0f);
-              bits |= bit << k; dmask |= dbit << k;
-              pbuf[k * 32 + lane] = amp;
-            }
-          }
-        }
-        s.dsc = (uint32_t)(v_hi & 1);
-        // ---------------- B ----------------
-        FastB b;
-        fb_load(b, park_u, lane);
+        ring16[(pos_t0 >> 4) & hmask] = (uint16_t)bits;  // syncSamplesBuffer.put x 16 — fsk.ts:281
+        const uint32_t dchunk = dmask >> b_from;
+        if (dchunk) doubt_note(b, pos_t0 + (uint32_t)b_from, dchunk, d);
+        n_doubt += (uint32_t)__popc(dchunk);
         redo = false;
-        const int k_reset = sm_tile_events_fast(b, bits, dmask, pbuf + lane, b_from, nk, pos_t0, len_t0, slot_t0, alen_t0,
+        const int k_reset = sm_tile_events_fast(b, bits, dmask, silent, adoubt, b_from, pos_t0, len_t0, slot_t0, alen_t0,
                                                 a, li, out_row);
-        if (k_reset < 0 || 2 * (k_reset + 1) >= v_hi) {
-          b.ring_len = min(len_t0 + (uint32_t)nk, (uint32_t)d.ring_cap_int);
-          const uint32_t sl = slot_t0 + (uint32_t)nk;
-          b.amp_pos = sl >= (uint32_t)d.amp_phys ? sl - (uint32_t)d.amp_phys : sl;
-          b.amp_len = min(alen_t0 + (uint32_t)nk, (uint32_t)d.amp_cap);
+        if (k_reset >= 0 && k_reset + 1 < kTile / 2) {
+          // resetState(): A2 restarts from the zeroed state at the next pair (S is kept) and the rest of the tile is
+          // decided again from the pre-filtered samples
+          n_doubt -= (uint32_t)__popc(dmask >> (k_reset + 1));
+          reset_state_fdsp(s, d);
+          b_from = k_reset + 1;
+          const uint32_t keep = (1u << b_from) - 1u;
+          bits &= keep; dmask &= keep; silent &= keep; adoubt &= keep;
+#pragma unroll 1
+          for (int k = b_from; k < kTile / 2; ++k) {
+            const float* pfp = pfbuf + (2 * k) * 32 + lane;
+            const float2 sum = fast_iq_pair(s, pfp[0], pfp[32], d);
+            float nf, dv;
+            const float am = fast_decim<TAP>(s, sum, d, nf, dv, TAP ? tap_row + t * kTile + 2 * k : nullptr);
+            amp_st(aring + slot_t0 + k, am);
+            bits |= (__float_as_uint(nf) >> 31) << k;
+            dmask |= (__float_as_uint(dv) >> 31) << k;
+            const uint32_t lo = __float_as_uint(am - b.thr_lo) >> 31, hi = __float_as_uint(am - b.thr_hi) >> 31;
+            silent |= hi << k;
+            adoubt |= (lo ^ hi) << k;
+          }
+          redo = true;
+        } else if (k_reset >= 0) {
+          reset_state_fdsp(s, d);  // reset behind the tile's last pair: nothing to decide again
         }
-        n_doubt += (uint32_t)__popc((dmask >> b_from) & (k_reset >= 0 ? (2u << (k_reset - b_from)) - 1u : 0xffffffffu));
-        if (k_reset >= 0) {
-          reset_state_fa2(s);  // resetState(): A2 restarts from the zeroed state at the next pair (S is kept)
-          k_from = k_reset + 1; b_from = k_reset + 1; v_lo = 2 * (k_reset + 1);
-          redo = (v_lo < v_hi);
-        }
-        fb_store(b, park_u, lane);
       }
     }
+    slot_t0 += kTile / 2;
+    if (slot_t0 >= (uint32_t)d.amp_phys) slot_t0 -= (uint32_t)d.amp_phys;
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncwarp();
   }
@@ -788,8 +673,8 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_fast_kerne
   if (active) {
     double* f = a.f64 + li;
     uint32_t* u = a.u32 + li;
-    // ---- normal form -> direct form (x history zero, y history carrying the state)
-    f[F_LO_C * ns] = (double)s.lc; f[F_LO_S * ns] = (double)s.ls;
+    // ---- state out: normal form -> direct form (x history zero, y history carrying the state)
+    f[F_LO_C * ns] = (double)s.e0.x; f[F_LO_S * ns] = (double)s.e0.y;
     double y1, y2;
     normal_to_df(d.lp_a1, d.lp_a2, d.lp_nk1, d.lp_nk2, d.lp_nsg, d.lp_nom, (double)s.w1.x, (double)s.w2.x, y1, y2);
     f[F_IX1 * ns] = 0.0; f[F_IX2 * ns] = 0.0; f[F_IY1 * ns] = y1; f[F_IY2 * ns] = y2;
@@ -798,29 +683,24 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_fast_kerne
     normal_to_df(d.lp_a1, d.lp_a2, d.lp_nk1, d.lp_nk2, d.lp_nsg, d.lp_nom, (double)s.ow1, (double)s.ow2, y1, y2);
     f[F_OX1 * ns] = 0.0; f[F_OX2 * ns] = 0.0; f[F_OY1 * ns] = y1; f[F_OY2 * ns] = y2;
     f[F_LAST_PHASE * ns] = atan2((double)s.psq, (double)s.psi);
-    f[F_IACC * ns] = (double)s.acc.x; f[F_QACC * ns] = (double)s.acc.y;
+    f[F_IACC * ns] = 0.0; f[F_QACC * ns] = 0.0;
     f[F_FAST_S * ns] = (double)s.S; f[F_FAST_E * ns] = (double)s.E; f[F_FAST_RSP * ns] = (double)s.rsp;
-    u[U_DSC * ns] = s.dsc;
-    normal_to_df(d.pre_a1, d.pre_a2, d.pre_nk1, d.pre_nk2, d.pre_nsg, d.pre_nom, (double)__uint_as_float(park_u[0][lane]),
-                 (double)__uint_as_float(park_u[1][lane]), y1, y2);
-    f[F_GAIN * ns] = park_g[lane];
+    u[U_DSC * ns] = 0u;
+    normal_to_df(d.pre_a1, d.pre_a2, d.pre_nk1, d.pre_nk2, d.pre_nsg, d.pre_nom, (double)pw1, (double)pw2, y1, y2);
+    f[F_GAIN * ns] = gain;
     f[F_PX1 * ns] = 0.0; f[F_PX2 * ns] = 0.0; f[F_PY1 * ns] = y1; f[F_PY2 * ns] = y2;
-    FastB b;
-    fb_load(b, park_u, lane);
     f[F_SIL_THR * ns] = (double)b.sil_thr;
     u[U_GSC * ns] = b.gsc; u[U_GMOD * ns] = b.gmod; u[U_BSC * ns] = b.bsc; u[U_NEXT_IDX * ns] = b.next_idx;
     u[U_BIT_ACC * ns] = b.bit_acc; u[U_BIT_CNT * ns] = b.bit_cnt; u[U_STARTED * ns] = b.started;
     u[U_BITPOS * ns] = (uint32_t)b.bitpos; u[U_CURRENT * ns] = b.current; u[U_SIL_CNT * ns] = b.sil_cnt;
-    u[U_RING_POS * ns] = b.ring_pos; u[U_RING_LEN * ns] = b.ring_len;
-    u[U_AMP_POS * ns] = b.amp_pos; u[U_AMP_LEN * ns] = b.amp_len;
+    u[U_RING_POS * ns] = ring_pos0 + (uint32_t)n_tiles * (kTile / 2);
+    u[U_RING_LEN * ns] = min(ring_len0 + (uint32_t)n_tiles * (kTile / 2), (uint32_t)d.ring_cap_int);
+    u[U_AMP_POS * ns] = slot_t0;
+    u[U_AMP_LEN * ns] = min(amp_len0 + (uint32_t)n_tiles * (kTile / 2), (uint32_t)d.amp_cap);
     u[U_DVOTE * ns] = b.dvote; u[U_SILX * ns] = b.silx; u[U_LAST_DOUBT * ns] = b.dlast; u[U_FLAG * ns] = b.flag;
     u[U_DCNT * ns] = b.dcnt;
+    u[U_SYNC_DET * ns] = b.sync_det; u[U_EOD_EV * ns] = b.eod_ev;
     u[U_DOUBT_SAMPLES * ns] += n_doubt;
-    if ((b.ring_pos & 31u) != 0u) {
-      const uint32_t wi = (b.ring_pos >> 5) & (uint32_t)(d.ring_words - 1);
-      ring_of(a, li)[wi] = b.cur_word;
-      a.doubt_ring[(size_t)li * (size_t)d.ring_words + wi] = b.dcur_word;
-    }
     a.out_len[row] = b.out_n < a.out_stride ? b.out_n : (int)a.out_stride;
     if (b.flag != 0u && flag_in == 0u) {  // first flag of this stream in this call: queue it for the float64 re-run
       u[U_FLAG_EVER * ns] |= b.flag;

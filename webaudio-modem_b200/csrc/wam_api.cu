@@ -160,8 +160,8 @@ extern "C" int wam_design_sinc_bandpass(double f0, double bandwidth, double fs, 
 // ------------------------------------------------------------------------------------------
 // Fast path (fsk_demod_fast.cuh): the biquads in normal form — poles sg +- j om, y = b0 x + k1 w1 + k2 w2 with
 // k1 = b1 - b0 a1, k2 = (b2 - b0 a2 + k1 sg) / om — and the constants of the doubt band.  The band's constants were
-// calibrated on the CPU model (oracle/fastmodel.c, scripts/exp_fastmodel.py): over 16,384 noisy streams the float32
-// error of filteredPhaseDiff stayed below 0.23 of the band.
+// calibrated on the CPU model of the kernel (scripts/exp_fastmodel.py): over 16,384 noisy streams the float32 error of
+// filteredPhaseDiff stayed below 0.23 of the band.
 static bool normal_form(double b0, double b1, double b2, double a1, double a2, double& k1, double& k2, double& sg, double& om) {
   sg = -a1 / 2;
   const double om2 = a2 - sg * sg;
@@ -179,16 +179,29 @@ static void derive_fast(FskDerived& d) {
   d.f_pre_sg = (float)d.pre_nsg; d.f_pre_om = (float)d.pre_nom;
   d.f_lp_k0 = (float)d.lp_b0; d.f_lp_k1 = (float)d.lp_nk1; d.f_lp_k2 = (float)d.lp_nk2;
   d.f_lp_sg = (float)d.lp_nsg; d.f_lp_om = (float)d.lp_nom;
+  {  // two samples per step
+    const double sg = d.pre_nsg, om = d.pre_nom, k1 = d.pre_nk1, k2 = d.pre_nk2;
+    d.f_pre_A = (float)(sg * sg - om * om); d.f_pre_B = (float)(2 * sg * om);
+    d.f_pre_c1 = (float)(k1 * sg + k2 * om); d.f_pre_c2 = (float)(k2 * sg - k1 * om);
+  }
+  {
+    const double sg = d.lp_nsg, om = d.lp_nom, k0 = d.lp_b0, k1 = d.lp_nk1, k2 = d.lp_nk2;
+    d.f_lp_A = (float)(sg * sg - om * om); d.f_lp_B = (float)(2 * sg * om);
+    d.f_lp_kx0 = (float)(k0 + k1);
+    d.f_lp_kw1 = (float)(k1 * (1 + sg) + k2 * om); d.f_lp_kw2 = (float)(k2 * (1 + sg) - k1 * om);
+  }
   d.f_cw = (float)d.cos_omega; d.f_sw = (float)d.sin_omega;
-  d.f_dphi_bias = (float)(2.0 * (atan2((double)d.f_sw, (double)d.f_cw) - d.omega));
+  d.f_c2w = (float)cos(2 * d.omega); d.f_s2w = (float)sin(2 * d.omega);
+  d.f_dphi_bias = (float)remainder(atan2((double)d.f_s2w, (double)d.f_c2w) - 2 * d.omega, 2 * M_PI);
   const double rho = sqrt(d.lp_a2);
   d.f_rho_e = (float)rho;
   d.f_gamma = (float)(sqrt(d.lp_nk1 * d.lp_nk1 + d.lp_nk2 * d.lp_nk2) / rho);
   d.f_kappa = 3e-7f;
   d.f_eps0 = 3e-7f;
   d.f_bc_delta = 2e-6f;
-  d.f_amp_ulps = 16;
-  d.fast_ok = (!d.ring_fractional && d.eod_count > 16 && d.total_bits > 0 && d.check_period > 0 && rho < 1.0) ? 1 : 0;
+  d.f_amp_eps = 2e-6f;
+  d.fast_ok = (!d.ring_fractional && d.eod_count > 16 && d.total_bits > 0 && d.check_period > 0 && rho < 1.0 &&
+               d.amp_phys % 16 == 0) ? 1 : 0;
 }
 
 static int derive(const wam_fsk_config& c, FskDerived& d) {
@@ -320,6 +333,7 @@ struct Group {
   uint32_t* sh_dring = nullptr;
   float* sh_amp_ring = nullptr;
   int doubt_state = 0;  // 0: clean (fresh streams), 1: maintained by the fast kernel, 2: stale (an exact kernel ran since)
+  bool unaligned = false;  // some call since reset() was not a whole number of 32-sample tiles: fast path closed
 };
 
 struct wam_fsk_batch {
@@ -471,6 +485,7 @@ static int init_group_state(Group& g, cudaStream_t st) {
   CUDA_TRY(cudaMemsetAsync(g.amp_ring, 0, sizeof(float) * (size_t)g.d.amp_phys * n, st));
   if (g.dring) CUDA_TRY(cudaMemsetAsync(g.dring, 0, sizeof(uint32_t) * (size_t)g.d.ring_words * n, st));
   g.doubt_state = 0;
+  g.unaligned = false;
   // AGC gain 1.0 (fsk.ts:46), silence threshold 0.01 (fsk.ts:128)
   const unsigned blocks = (unsigned)((n + 255) / 256);
   fill_f64_kernel<<<blocks, 256, 0, st>>>(g.f64 + (size_t)F_GAIN * n, 1.0, (long)n);
@@ -845,6 +860,7 @@ static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, c
   for (int g = 0; g < L.n_groups; g++) n_rows = std::max(n_rows, tmap_rows[g]);
   const bool append = L.g[0].append != 0;
   const bool guarded = !(flags & WAM_BATCH_FAST_UNGUARDED);
+  const bool tap = (flags & WAM_BATCH_TAP_FAST_DECISION) != 0 && L.g[0].tap != nullptr;
   for (int gi = 0; gi < L.n_groups; gi++) {
     Group& g = *lg[gi];
     const size_t ns = g.ids.size();
@@ -873,7 +889,7 @@ static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, c
   const long n_tiles = (n + kTile - 1) / kTile;
   if (b->fast_per_sm < 0) {
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fsk_demod_fast_kernel, 32, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fsk_demod_fast_kernel<false>, 32, 0));
     b->fast_per_sm = per_sm;
   }
   const bool one_wave = W <= b->fast_per_sm * b->sm_count;
@@ -883,11 +899,12 @@ static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, c
   const bool force = (flags & WAM_BATCH_FORCE_SLABS) != 0;
   if (!(flags & WAM_BATCH_NO_SLABS) && one_wave &&
       ((W >= b->sm_count * 8 && n_tiles >= 4 * kSlabTiles && uneven) || (force && n_tiles > kSlabTiles))) {
-    int rc = launch_slabbed(b, L, tmap_rows, n, st, fsk_demod_fast_kernel);
+    int rc = launch_slabbed(b, L, tmap_rows, n, st, tap ? fsk_demod_fast_kernel<true> : fsk_demod_fast_kernel<false>);
     if (rc != WAM_OK) return rc;
   } else {
     L.slab = 0; L.slab_done = nullptr;
-    fsk_demod_fast_kernel<<<W, 32, 0, st>>>(L);
+    if (tap) fsk_demod_fast_kernel<true><<<W, 32, 0, st>>>(L);
+    else fsk_demod_fast_kernel<false><<<W, 32, 0, st>>>(L);
     b->launches++;
     CUDA_TRY(cudaGetLastError());
   }
@@ -931,8 +948,10 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
     // Fast path: float32 kernel with certified decisions, float64 re-run of the streams it flags.  Many streams and
     // long calls only (or WAM_BATCH_FORCE_FAST): short calls are latency-sized and stay with the float64 kernels.
     {
-      bool fast = aligned && !generic && !ragged && tma_ok && !(flags & (WAM_BATCH_NO_TMA | WAM_BATCH_EXACT_ONLY));
-      for (int g = 0; g < L.n_groups && fast; g++) fast = L.g[g].d.fast_ok != 0 && L.g[g].d.tmpl0_words > 0;
+      bool fast = aligned && !generic && !ragged && tma_ok && n % kTile == 0 &&
+                  !(flags & (WAM_BATCH_NO_TMA | WAM_BATCH_EXACT_ONLY));
+      for (int g = 0; g < L.n_groups && fast; g++)
+        fast = L.g[g].d.fast_ok != 0 && L.g[g].d.tmpl0_words > 0 && !lg[g]->unaligned;
       if (fast && !(flags & WAM_BATCH_FORCE_FAST))
         fast = L.block_begin[L.n_groups] >= 4 * b->sm_count && n >= 4 * (long)kSlabTiles * kTile;
       if (fast) {
@@ -1017,7 +1036,9 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
     a.row_base = (int)row_base;
     a.f64 = g.f64; a.u32 = g.u32; a.sync_ring = g.sync_ring; a.amp_ring = g.amp_ring;
     a.samples = d_samples; a.stride = stride; a.n = n;
-    a.out = d_out; a.out_stride = out_stride; a.out_len = d_out_len; a.tap = tap ? d_tap : nullptr;
+    a.out = d_out; a.out_stride = out_stride; a.out_len = d_out_len;
+    a.tap = (tap || (flags & WAM_BATCH_TAP_FAST_DECISION)) ? d_tap : nullptr;
+    if (n % kTile != 0 || ragged) g.unaligned = true;
     a.writeback = wb ? 1 : 0;
     if (g.d.ring_fractional || g.d.eod_count <= 16) generic = true;  // needs the per-sample state machine
     a.force_generic = (flags & WAM_BATCH_DEBUG_GENERIC_SM) ? 1 : 0;

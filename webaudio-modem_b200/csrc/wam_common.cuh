@@ -69,19 +69,24 @@ struct FskDerived {
   // ---- fast path (fsk_demod_fast.cuh): float32 DSP behind a float64 AGC, decisions certified by a doubt band ----
   // The three biquads in NORMAL (coupled) form: w' = [[sg, -om], [om, sg]] w + (x, 0), y = k0 x + k1 w1 + k2 w2 (w before
   // the update).  Same transfer function as the reference's direct form I; in float32 its round-off is ~50x smaller
-  // (measured against the oracle: 1e-8 rms on filteredPhaseDiff instead of 5e-7, oracle/fastmodel.c).
+  // (measured on the CPU model of the kernel: 1e-8 rms on filteredPhaseDiff instead of 5e-7).
   double pre_nk1, pre_nk2, pre_nsg, pre_nom;  // float64 copies for the state conversion direct form <-> normal form
   double lp_nk1, lp_nk2, lp_nsg, lp_nom;
   float f_pre_k0, f_pre_k1, f_pre_k2, f_pre_sg, f_pre_om;
   float f_lp_k0, f_lp_k1, f_lp_k2, f_lp_sg, f_lp_om;
-  float f_cw, f_sw;       // float32 LO rotation
-  float f_dphi_bias;      // 2 * (atan2(f_sw, f_cw) - omega): the float32 LO's constant offset on the phase difference
+  // the same filters two input samples per step: state' = [[A, -B], [B, A]] state + (sg x0 + x1, om x0);
+  // pre-filter second output y1 = k0 x1 + k1 x0 + c1 w1 + c2 w2; low-pass pair sum y0 + y1 = k0 x1 + kx0 x0 + kw1 w1 + kw2 w2
+  float f_pre_A, f_pre_B, f_pre_c1, f_pre_c2;
+  float f_lp_A, f_lp_B, f_lp_kx0, f_lp_kw1, f_lp_kw2;
+  float f_cw, f_sw;       // float32 LO: phasor of sample 1 after a reset
+  float f_c2w, f_s2w;     // rotation by 2 omega (the even and the odd phasor both turn once per pair)
+  float f_dphi_bias;      // atan2(f_s2w, f_c2w) - 2 omega: the float32 LO's constant offset on the phase difference
   float f_rho_e;          // envelope of the post filter's impulse response: |h(j)| <= f_gamma * f_rho_e^j
   float f_gamma;
   float f_kappa;          // relative float32 error of an I/Q output against the recent amplitude scale
   float f_eps0;           // floor of the doubt band on |filteredPhaseDiff|
   float f_bc_delta;       // a raw phase difference this close to +-pi may have wrapped the other way
-  int f_amp_ulps;         // doubt band of the silence compare, in float32 ulps of the threshold
+  float f_amp_eps;        // relative doubt band of the silence compare
   int fast_ok;            // the configuration qualifies for the fast kernel (complex poles, integral ring, by-value template)
   // modulator (fsk.ts:389-424)
   double mark, space, fs;
