@@ -189,11 +189,14 @@ long wam_fsk_batch_launch_count(wam_fsk_batch* b);
  * could have turned are demodulated again in float64): counters over the batch's life. */
 typedef struct wam_fast_stats {
   int64_t fast_calls;          /* demodulate calls served by the fast kernel */
-  int64_t flagged_last_call;   /* streams re-run in float64 in the most recent fast call */
+  int64_t flagged_last_call;   /* streams re-run in float64 over the whole of the most recent fast call */
   int64_t flagged_streams;     /* streams flagged at least once */
   int64_t doubtful_samples;    /* decimated samples whose hard bit was inside the float32 error band */
   uint32_t flag_causes;        /* OR of the causes seen: 1 start-bit vote, 2 data-bit vote, 4 stop-bit vote, 8 sync, 16 EOD, 32 range */
   uint32_t error_flags;        /* OR of the streams' error words (1 output overflow, 2 pipeline timeout, 4 slab timeout) */
+  /* most recent fast call: doubtful decisions checked by a float64 run of a short window around them, by outcome
+   * (confirmed: the fast results stand; refuted or dropped for lack of room: the stream is re-run over the whole call) */
+  int64_t windows_confirmed, windows_refuted, windows_dropped;
 } wam_fast_stats;
 int wam_fsk_batch_fast_stats(wam_fsk_batch* b, wam_fast_stats* out);
 

@@ -1,0 +1,515 @@
+// fast_host.inl — host side of the mixed-precision fast path (included by wam_api.cu).
+//
+// One fast call over a configuration group:
+//   1. prologue   the rings' newest contents become the prefix of the call's linear histories (hard bits, amplitudes);
+//   2. fast pass  fsk_demod_fast_kernel, one launch per time slab: reads checkpoint j of the per-stream state, writes
+//                 checkpoint j + 1, appends bytes, writes the histories, and lists the streams in which a decision of
+//                 the slab was doubtful (float32 error band, see fsk_demod_fast.cuh);
+//   3. check      every listed (stream, slab) becomes a WINDOW of 2 slabs (more when the doubtful decision is a frame
+//                 sync, whose template looks further back): state of the checkpoint at the window's start, rings
+//                 rebuilt from the histories, the window's samples — demodulated by the float64 kernel in a scratch
+//                 batch.  The first slab of a window re-converges the filters (the float32 state it starts from is
+//                 1e-7 off; the filters forget that within a few hundred samples), the last one decides the doubtful
+//                 decision in float64.  State machine and bytes at the window's end equal to the fast pass'
+//                 checkpoint: the fast results stand (the usual outcome: a doubtful sample is wrong 1 time in 300).
+//                 Otherwise, or when a window cannot be formed, the stream joins the hard list;
+//   4. hard list  those streams run through the float64 kernel over the whole call from the live state (checkpoint
+//                 0, untouched so far) and the rings (untouched too);
+//   5. epilogue   every other stream's last checkpoint becomes its live state, the histories' tails its rings.
+// So a doubtful decision costs the float64 kernel a few thousand samples instead of the whole call, and what leaves the
+// library is what the float64 kernels alone would have produced.
+
+struct FastGeom {
+  int ns;            // streams of the group
+  long n;            // samples per stream in this call
+  long slab_len;     // samples per time slab (a multiple of kTile); only the last slab may be shorter
+  int n_slabs;
+  int ph;            // prefix of the bit history, half words (= 2 ring_words)
+  int pa;            // prefix of the amplitude history, entries (amp_cap rounded up to 16)
+  long bh_stride, ah_stride;
+  int sync_slabs;    // window length, in slabs, that checks a doubtful sync decision
+  long out_stride;
+  long sv_stride;    // samples per row of the verification scratch (kVerifyClasses slabs)
+};
+
+struct FastCtx {  // what the small kernels below need, by value
+  FastGeom q;
+  int ring_words, amp_phys, amp_cap;
+  double* f64; uint32_t* u32;              // live state (= checkpoint 0)
+  double* ck_f64; uint32_t* ck_u32;        // checkpoints 1..S
+  uint32_t* sync_ring; float* amp_ring;    // live rings
+  uint16_t* bit_hist; float* amp_hist;
+  int32_t* slab_list; int32_t* slab_count;
+  int32_t* hard_list; int32_t* hard_count; uint32_t* hard_mark;
+  int32_t* item_li; int32_t* item_slab; int32_t* item_count;
+  double* sv_f64; uint32_t* sv_u32; uint32_t* sv_ring; float* sv_amp; float* sv_samples; uint8_t* sv_out; int32_t* sv_out_len;
+  const float* samples; long stride;       // the call's sample buffer
+  const int32_t* ids; int id0, row_base;
+  uint8_t* out; int32_t* out_len;
+  int append;
+};
+
+__device__ __forceinline__ long fc_row(const FastCtx& c, int li) { return (long)(c.ids ? c.ids[li] : c.id0 + li) - c.row_base; }
+__device__ __forceinline__ const double* fc_ck_f64(const FastCtx& c, int k) {  // checkpoint k (0 = live)
+  return k == 0 ? c.f64 : c.ck_f64 + (size_t)(k - 1) * F64_COUNT * c.q.ns;
+}
+__device__ __forceinline__ const uint32_t* fc_ck_u32(const FastCtx& c, int k) {
+  return k == 0 ? c.u32 : c.ck_u32 + (size_t)(k - 1) * U32_COUNT * c.q.ns;
+}
+__device__ __forceinline__ void fc_hard(const FastCtx& c, int li) {  // onto the hard list, once
+  if (atomicExch(c.hard_mark + li, 1u) == 0u) c.hard_list[atomicAdd(c.hard_count, 1)] = li;
+}
+
+// (1) prologue: a block per stream
+__global__ void fast_prologue_kernel(const FastCtx c) {
+  const int li = blockIdx.x;
+  const int ns = c.q.ns;
+  const uint32_t ring_pos = c.u32[(size_t)U_RING_POS * ns + li];
+  const uint32_t amp_pos = c.u32[(size_t)U_AMP_POS * ns + li];
+  const uint16_t* ring16 = reinterpret_cast<const uint16_t*>(c.sync_ring + (size_t)li * c.ring_words);
+  uint16_t* bh = c.bit_hist + (size_t)li * c.q.bh_stride;
+  const uint32_t hmask = (uint32_t)(2 * c.ring_words - 1);
+  const uint32_t p16 = ring_pos >> 4;  // aligned calls: ring_pos is a multiple of 16
+  for (int m = threadIdx.x; m < c.q.ph; m += blockDim.x) bh[c.q.ph - 1 - m] = ring16[(p16 - 1u - (uint32_t)m) & hmask];
+  const float* ar = c.amp_ring + (size_t)li * c.amp_phys;
+  float* ah = c.amp_hist + (size_t)li * c.q.ah_stride;
+  for (int k = threadIdx.x; k < c.q.pa; k += blockDim.x) {
+    float v = 0.0f;
+    if (k < c.amp_cap) {
+      int slot = (int)amp_pos - 1 - k;
+      if (slot < 0) slot += c.amp_phys;
+      v = ar[slot];
+    }
+    ah[c.q.pa - 1 - k] = v;
+  }
+  if (threadIdx.x == 0) {
+    c.u32[(size_t)U_OUT_N * ns + li] = c.append ? (uint32_t)c.out_len[fc_row(c, li)] : 0u;
+    c.u32[(size_t)U_FLAG * ns + li] = 0u;
+    c.hard_mark[li] = 0u;
+  }
+}
+
+// (3a) collect: the slab lists become windows, sorted into classes by their length in slabs
+__global__ void fast_collect_kernel(const FastCtx c) {
+  const int ns = c.q.ns;
+  for (int j = blockIdx.y; j < c.q.n_slabs; j += gridDim.y) {
+    const int cnt = min(c.slab_count[j], ns);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += gridDim.x * blockDim.x) {
+      const int v = c.slab_list[(size_t)j * ns + e];
+      const int li = v & 0xffffff;
+      const uint32_t cause = (uint32_t)v >> 24;
+      bool hard = (cause & (WAM_FLAG_EOD | WAM_FLAG_RANGE)) != 0;
+      // a short last slab has no window class of its own
+      if (j == c.q.n_slabs - 1 && c.q.n != (long)c.q.n_slabs * c.q.slab_len) hard = true;
+      const int want = (cause & WAM_FLAG_SYNC) ? c.q.sync_slabs : 2;
+      if (want > kVerifyClasses) hard = true;
+      if (!hard) {
+        const int len = min(want, j + 1);  // windows are cut at the start of the call (checkpoint 0 is the exact state)
+        const int slot = atomicAdd(c.item_count + (len - 1), 1);
+        if (slot < kVerifyCap) {
+          c.item_li[(len - 1) * kVerifyCap + slot] = li;
+          c.item_slab[(len - 1) * kVerifyCap + slot] = j;
+        } else {
+          hard = true;
+          atomicAdd(c.hard_count + 3, 1);
+        }
+      }
+      if (hard) fc_hard(c, li);
+    }
+  }
+}
+
+// (3b) gather: a block per window of class `cls` (cls + 1 slabs).  Scratch index of window i of class cls:
+// cls * kVerifyCap + i.
+__global__ void fast_gather_kernel(const FastCtx c, int cls) {
+  const int i = blockIdx.x;
+  if (i >= min(c.item_count[cls], kVerifyCap)) return;
+  const int ns = c.q.ns;
+  const int li = c.item_li[cls * kVerifyCap + i];
+  const int j = c.item_slab[cls * kVerifyCap + i];
+  const int j0 = j - cls;  // first slab of the window = the checkpoint it starts from
+  const size_t si = (size_t)cls * kVerifyCap + i;
+  const size_t nv = (size_t)kVerifyClasses * kVerifyCap;  // streams of the scratch batch
+  const double* f = fc_ck_f64(c, j0);
+  const uint32_t* u = fc_ck_u32(c, j0);
+  for (int k = threadIdx.x; k < F64_COUNT; k += blockDim.x) {
+    double v = f[(size_t)k * ns + li];
+    if (k == F_FAST_E || k == F_FAST_RSP) v = 0.0;
+    c.sv_f64[(size_t)k * nv + si] = v;
+  }
+  for (int k = threadIdx.x; k < U32_COUNT; k += blockDim.x) {
+    uint32_t v = u[(size_t)k * ns + li];
+    if (k == U_DVOTE || k == U_SILX || k == U_LAST_DOUBT || k == U_DCNT || k == U_FLAG || k == U_ERR) v = 0u;
+    c.sv_u32[(size_t)k * nv + si] = v;
+  }
+  // rings as of the window's start, from the histories
+  const uint32_t ring_pos = u[(size_t)U_RING_POS * ns + li];
+  const uint32_t amp_pos = u[(size_t)U_AMP_POS * ns + li];
+  const long tiles_per_slab = c.q.slab_len / kTile;
+  const uint16_t* bh = c.bit_hist + (size_t)li * c.q.bh_stride + c.q.ph + (long)j0 * tiles_per_slab;  // behind the newest tile
+  uint16_t* ring16 = reinterpret_cast<uint16_t*>(c.sv_ring + si * c.ring_words);
+  const uint32_t hmask = (uint32_t)(2 * c.ring_words - 1);
+  const uint32_t p16 = ring_pos >> 4;
+  for (int m = threadIdx.x; m < 2 * c.ring_words; m += blockDim.x) ring16[(p16 - 1u - (uint32_t)m) & hmask] = bh[-1 - m];
+  const float* ah = c.amp_hist + (size_t)li * c.q.ah_stride + c.q.pa + (long)j0 * (c.q.slab_len / 2);
+  float* ar = c.sv_amp + si * c.amp_phys;
+  for (int k = threadIdx.x; k < c.amp_cap; k += blockDim.x) {
+    int slot = (int)amp_pos - 1 - k;
+    if (slot < 0) slot += c.amp_phys;
+    ar[slot] = ah[-1 - k];
+  }
+  // the window's samples
+  const long wlen = (long)(cls + 1) * c.q.slab_len;
+  const float4* src = reinterpret_cast<const float4*>(c.samples + fc_row(c, li) * c.stride + (long)j0 * c.q.slab_len);
+  float4* dst = reinterpret_cast<float4*>(c.sv_samples + si * c.q.sv_stride);
+  for (long k = threadIdx.x; k < wlen / 4; k += blockDim.x) dst[k] = src[k];
+  if (threadIdx.x == 0) c.sv_out_len[si] = 0;
+}
+
+// (3c) compare: a warp per window.  The float64 run of the window must end in the state machine state of the fast
+// pass' checkpoint behind the window's last slab, having produced the same bytes.
+__global__ void fast_compare_kernel(const FastCtx c, int cls) {
+  const int i = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
+  if (i >= min(c.item_count[cls], kVerifyCap)) return;
+  const int ns = c.q.ns;
+  const int li = c.item_li[cls * kVerifyCap + i];
+  const int j = c.item_slab[cls * kVerifyCap + i];
+  const size_t si = (size_t)cls * kVerifyCap + i;
+  const size_t nv = (size_t)kVerifyClasses * kVerifyCap;
+  const uint32_t* ue = fc_ck_u32(c, j + 1);   // fast pass, behind the window
+  const uint32_t* us = fc_ck_u32(c, j - cls); // fast pass, at the window's start
+  const double* fe = fc_ck_f64(c, j + 1);
+  bool same = true;
+  if (lane == 0) {
+    const int fields[] = {U_GSC, U_BSC, U_NEXT_IDX, U_BIT_ACC, U_BIT_CNT, U_STARTED, U_BITPOS, U_CURRENT, U_SIL_CNT,
+                          U_SYNC_DET, U_EOD_EV, U_RING_POS, U_RING_LEN, U_AMP_POS, U_AMP_LEN, U_DSC};
+    for (int k : fields) same = same && c.sv_u32[(size_t)k * nv + si] == ue[(size_t)k * ns + li];
+    if (!ue[(size_t)U_STARTED * ns + li]) same = same && c.sv_u32[(size_t)U_GMOD * nv + si] == ue[(size_t)U_GMOD * ns + li];
+    // the silence threshold is a float32 mean in one run and a float64 mean in the other
+    const double ta = c.sv_f64[(size_t)F_SIL_THR * nv + si], tb = fe[(size_t)F_SIL_THR * ns + li];
+    same = same && fabs(ta - tb) <= 1e-5 * fabs(tb);
+    same = same && (c.sv_u32[(size_t)U_ERR * nv + si] == 0u);
+  }
+  const int o0 = (int)us[(size_t)U_OUT_N * ns + li], o1 = (int)ue[(size_t)U_OUT_N * ns + li];
+  const int nb = c.sv_out_len[si];
+  if (lane == 0) same = same && nb == o1 - o0;
+  same = __shfl_sync(0xffffffffu, same ? 1 : 0, 0) != 0;
+  if (same) {
+    const uint8_t* pa = c.sv_out + si * c.q.out_stride;
+    const uint8_t* pb = c.out + fc_row(c, li) * c.q.out_stride + o0;
+    bool eq = true;
+    for (int k = lane; k < nb && o0 + k < c.q.out_stride; k += 32) eq = eq && pa[k] == pb[k];
+    same = __all_sync(0xffffffffu, eq);
+  }
+  if (lane == 0) {
+    atomicAdd(c.hard_count + (same ? 1 : 2), 1);
+    if (!same) fc_hard(c, li);
+  }
+}
+
+// (4) hard list: the doubt tracking of these streams restarts clean behind the float64 run, and their byte count goes
+// back to the start of the call.
+__global__ void fast_hard_prepare_kernel(const FastCtx c) {
+  const int ns = c.q.ns;
+  const int cnt = min(c.hard_count[0], ns);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += gridDim.x * blockDim.x) {
+    const int li = c.hard_list[e];
+    c.f64[(size_t)F_FAST_S * ns + li] = 16.0;
+    c.f64[(size_t)F_FAST_E * ns + li] = 0.0;
+    c.f64[(size_t)F_FAST_RSP * ns + li] = 0.0;
+    for (int k : {(int)U_DVOTE, (int)U_SILX, (int)U_LAST_DOUBT, (int)U_DCNT}) c.u32[(size_t)k * ns + li] = 0u;
+    c.out_len[fc_row(c, li)] = (int)c.u32[(size_t)U_OUT_N * ns + li];
+  }
+}
+
+// (5) epilogue: a block per stream that is not on the hard list
+__global__ void fast_epilogue_kernel(const FastCtx c) {
+  const int li = blockIdx.x;
+  const int ns = c.q.ns;
+  if (c.hard_mark[li]) return;
+  const double* f = fc_ck_f64(c, c.q.n_slabs);
+  const uint32_t* u = fc_ck_u32(c, c.q.n_slabs);
+  for (int k = threadIdx.x; k < F64_COUNT; k += blockDim.x) c.f64[(size_t)k * ns + li] = f[(size_t)k * ns + li];
+  for (int k = threadIdx.x; k < U32_COUNT; k += blockDim.x) c.u32[(size_t)k * ns + li] = u[(size_t)k * ns + li];
+  const uint32_t ring_pos = u[(size_t)U_RING_POS * ns + li];
+  const uint32_t amp_pos = u[(size_t)U_AMP_POS * ns + li];
+  const long n_tiles = c.q.n / kTile;
+  const uint16_t* bh = c.bit_hist + (size_t)li * c.q.bh_stride + c.q.ph + n_tiles;
+  uint16_t* ring16 = reinterpret_cast<uint16_t*>(c.sync_ring + (size_t)li * c.ring_words);
+  const uint32_t hmask = (uint32_t)(2 * c.ring_words - 1);
+  const uint32_t p16 = ring_pos >> 4;
+  for (int m = threadIdx.x; m < 2 * c.ring_words; m += blockDim.x) ring16[(p16 - 1u - (uint32_t)m) & hmask] = bh[-1 - m];
+  const float* ah = c.amp_hist + (size_t)li * c.q.ah_stride + c.q.pa + c.q.n / 2;
+  float* ar = c.amp_ring + (size_t)li * c.amp_phys;
+  for (int k = threadIdx.x; k < c.amp_cap; k += blockDim.x) {
+    int slot = (int)amp_pos - 1 - k;
+    if (slot < 0) slot += c.amp_phys;
+    ar[slot] = ah[-1 - k];
+  }
+}
+
+// After a float64 kernel ran on a group the doubt-tracking state is stale: its bits are certain (no doubtful samples),
+// the error envelope restarts, and the amplitude scale — which the float64 kernels do not track — is set to a safe
+// maximum (it decays to the true scale within a few hundred decimated samples).
+static int fast_clean_doubt(Group& g, cudaStream_t st) {
+  const size_t n = g.ids.size();
+  for (int u : {(int)U_DVOTE, (int)U_SILX, (int)U_LAST_DOUBT, (int)U_DCNT})
+    CUDA_TRY(cudaMemsetAsync(g.u32 + (size_t)u * n, 0, sizeof(uint32_t) * n, st));
+  for (int f : {(int)F_FAST_E, (int)F_FAST_RSP}) CUDA_TRY(cudaMemsetAsync(g.f64 + (size_t)f * n, 0, sizeof(double) * n, st));
+  fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g.f64 + (size_t)F_FAST_S * n, 16.0, (long)n);
+  CUDA_TRY(cudaGetLastError());
+  return WAM_OK;
+}
+
+// The float64 kernels over the streams named by a list in device memory (sub-selection launches: the list length is
+// read on the device, the grid is sized for `max_streams` and surplus CTAs leave at once).
+static int launch_exact_selected(wam_fsk_batch* b, DemodLaunch& L, const int32_t* sel, const int32_t* sel_count,
+                                 int max_streams, long n, cudaStream_t st) {
+  L.slab = 0; L.slab_done = nullptr;
+  L.n_groups = 1;
+  DemodArgs& a = L.g[0];
+  a.sel = sel; a.sel_count = sel_count;
+  a.flag_list = nullptr; a.flag_count = nullptr;
+  a.l_begin = 0; a.l_end = a.n_local;
+  L.block_begin[0] = 0;
+  L.block_begin[1] = (max_streams + 31) / 32;
+  const int W = L.block_begin[1];
+  bool pipe = n >= 8 * kTile;
+  if (pipe) {
+    auto kern = fsk_demod_pipe_kernel<true>;
+    if (b->pipe_per_sm[1] < 0) {
+      int ring_words = 0;
+      for (auto& g : b->groups) ring_words = std::max(ring_words, g.d.ring_words);
+      b->pipe_smem = sizeof(PipeShared) + (size_t)ring_words * 32 * sizeof(uint32_t);
+      b->pipe_ring_smem = 1;
+      if (b->pipe_smem > 72 * 1024) { b->pipe_smem = sizeof(PipeShared); b->pipe_ring_smem = 0; }
+      int per_sm = 0;
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->pipe_smem));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPipeThreads, b->pipe_smem));
+      b->pipe_per_sm[1] = per_sm;
+    }
+    L.pipe_ring_smem = b->pipe_ring_smem;
+    pipe = b->pipe_per_sm[1] > 0;
+    if (pipe) kern<<<W, kPipeThreads, b->pipe_smem, st>>>(L);
+  }
+  if (!pipe) fsk_demod_exact_kernel<true, false><<<W, 32, 0, st>>>(L);
+  b->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return WAM_OK;
+}
+
+static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+// time slab length for a call of n samples (n a multiple of kTile): kSlabTiles tiles, or the divisor of the call's
+// tile count nearest to it (so that no slab is short and every doubtful decision has a window)
+static long fast_slab_len(long n) {
+  const long tiles = n / kTile;
+  if (tiles <= kSlabTiles) return tiles * kTile;
+  for (int delta = 0; delta <= kSlabTiles / 2; delta++)
+    for (int sgn : {-1, 1}) {
+      const long t = kSlabTiles + sgn * delta;
+      if (t > 0 && tiles % t == 0) return t * kTile;
+    }
+  return (long)kSlabTiles * kTile;
+}
+
+static int fast_prepare_buffers(wam_fsk_batch* b, Group& g, const FastGeom& q, cudaStream_t st) {
+  FastBuffers& fb = g.fb;
+  const size_t ns = (size_t)q.ns;
+  int rc = WAM_OK;
+  if ((rc = ensure((void**)&fb.ck_f64, &fb.ck_f64_bytes, sizeof(double) * F64_COUNT * ns * q.n_slabs)) != WAM_OK) return rc;
+  if ((rc = ensure((void**)&fb.ck_u32, &fb.ck_u32_bytes, sizeof(uint32_t) * U32_COUNT * ns * q.n_slabs)) != WAM_OK) return rc;
+  if ((rc = ensure((void**)&fb.bit_hist, &fb.bit_hist_bytes, sizeof(uint16_t) * ns * q.bh_stride)) != WAM_OK) return rc;
+  if ((rc = ensure((void**)&fb.amp_hist, &fb.amp_hist_bytes, sizeof(float) * ns * q.ah_stride)) != WAM_OK) return rc;
+  if ((rc = ensure((void**)&fb.slab_list, &fb.slab_list_bytes, sizeof(int32_t) * ns * q.n_slabs)) != WAM_OK) return rc;
+  if ((rc = ensure((void**)&fb.slab_count, &fb.slab_count_bytes, sizeof(int32_t) * q.n_slabs)) != WAM_OK) return rc;
+  if ((rc = ensure((void**)&fb.hard_list, &fb.hard_list_bytes, sizeof(int32_t) * ns)) != WAM_OK) return rc;
+  if ((rc = ensure((void**)&fb.hard_mark, &fb.hard_mark_bytes, sizeof(uint32_t) * ns)) != WAM_OK) return rc;
+  const size_t nv = (size_t)kVerifyClasses * kVerifyCap;
+  if (!fb.scratch_ready) {
+    CUDA_TRY(cudaMalloc(&fb.hard_count, sizeof(int32_t) * 4));
+    CUDA_TRY(cudaMalloc(&fb.item_li, sizeof(int32_t) * nv));
+    CUDA_TRY(cudaMalloc(&fb.item_slab, sizeof(int32_t) * nv));
+    CUDA_TRY(cudaMalloc(&fb.item_count, sizeof(int32_t) * kVerifyClasses));
+    CUDA_TRY(cudaMalloc(&fb.iota, sizeof(int32_t) * nv));
+    std::vector<int32_t> h(nv);
+    for (size_t i = 0; i < nv; i++) h[i] = (int32_t)i;
+    CUDA_TRY(cudaMemcpy(fb.iota, h.data(), sizeof(int32_t) * nv, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&fb.sv_f64, sizeof(double) * F64_COUNT * nv));
+    CUDA_TRY(cudaMalloc(&fb.sv_u32, sizeof(uint32_t) * U32_COUNT * nv));
+    CUDA_TRY(cudaMalloc(&fb.sv_ring, sizeof(uint32_t) * (size_t)g.d.ring_words * nv));
+    CUDA_TRY(cudaMalloc(&fb.sv_amp, sizeof(float) * (size_t)g.d.amp_phys * nv));
+    CUDA_TRY(cudaMalloc(&fb.sv_out_len, sizeof(int32_t) * nv));
+    fb.scratch_ready = true;
+  }
+  if ((rc = ensure((void**)&fb.sv_samples, &fb.sv_samples_bytes, sizeof(float) * nv * q.sv_stride)) != WAM_OK) return rc;
+  if ((rc = ensure((void**)&fb.sv_out, &fb.sv_out_bytes, nv * (size_t)std::max<long>(q.out_stride, 1))) != WAM_OK) return rc;
+  CUDA_TRY(cudaMemsetAsync(fb.slab_count, 0, sizeof(int32_t) * q.n_slabs, st));
+  CUDA_TRY(cudaMemsetAsync(fb.hard_count, 0, sizeof(int32_t) * 4, st));
+  CUDA_TRY(cudaMemsetAsync(fb.item_count, 0, sizeof(int32_t) * kVerifyClasses, st));
+  (void)b;
+  return WAM_OK;
+}
+
+static int fast_streams(wam_fsk_batch* b) {
+  if (!b->slab_streams[0]) {
+    for (int i = 0; i < 8; i++) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&b->slab_streams[i], cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&b->slab_join[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&b->slab_fork, cudaEventDisableTiming));
+  }
+  return WAM_OK;
+}
+
+// L: the call's launch description (<= kFastGroupsPerLaunch groups, rows contiguous, TMA descriptors for the whole call).
+static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, const long* tmap_rows, long n, uint32_t flags,
+                           cudaStream_t st) {
+  const int G = L.n_groups;
+  const int W = L.block_begin[G];
+  const bool guarded = !(flags & WAM_BATCH_FAST_UNGUARDED);
+  const bool tap = (flags & WAM_BATCH_TAP_FAST_DECISION) != 0 && L.g[0].tap != nullptr;
+  const bool append = L.g[0].append != 0;
+  int rc = fast_streams(b);
+  if (rc != WAM_OK) return rc;
+  if (b->fast_per_sm < 0) {
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fsk_demod_fast_kernel<false>, 32, 0));
+    b->fast_per_sm = per_sm;
+  }
+  // slabs overlap on two streams per group when every CTA of the call is resident at once (see launch_slabbed);
+  // otherwise they follow one another on the caller's stream
+  const bool one_wave = W <= b->fast_per_sm * b->sm_count && !(flags & WAM_BATCH_NO_SLABS);
+  const long slab_len = (flags & WAM_BATCH_NO_SLABS) ? n : fast_slab_len(n);
+  const int n_slabs = (int)((n + slab_len - 1) / slab_len);
+
+  FastCtx ctx[kFastGroupsPerLaunch];
+  for (int gi = 0; gi < G; gi++) {
+    Group& g = *lg[gi];
+    const DemodArgs& a = L.g[gi];
+    if (g.doubt_state == 2) { rc = fast_clean_doubt(g, st); if (rc != WAM_OK) return rc; }
+    g.doubt_state = 1;
+    FastGeom q;
+    q.ns = (int)g.ids.size(); q.n = n; q.slab_len = slab_len; q.n_slabs = n_slabs;
+    q.ph = 2 * g.d.ring_words;
+    q.pa = (int)round_up((size_t)g.d.amp_cap, 16);
+    q.bh_stride = (long)round_up((size_t)q.ph + (size_t)(n / kTile), 8);
+    q.ah_stride = (long)round_up((size_t)q.pa + (size_t)(n / 2), 4);
+    q.sync_slabs = (int)((2L * g.d.total_bits + slab_len - 1) / slab_len) + 1;
+    q.out_stride = a.out_stride;
+    q.sv_stride = (long)kVerifyClasses * slab_len;
+    rc = fast_prepare_buffers(b, g, q, st);
+    if (rc != WAM_OK) return rc;
+    FastCtx& c = ctx[gi];
+    FastBuffers& fb = g.fb;
+    c.q = q; c.ring_words = g.d.ring_words; c.amp_phys = g.d.amp_phys; c.amp_cap = g.d.amp_cap;
+    c.f64 = g.f64; c.u32 = g.u32; c.ck_f64 = fb.ck_f64; c.ck_u32 = fb.ck_u32;
+    c.sync_ring = g.sync_ring; c.amp_ring = g.amp_ring; c.bit_hist = fb.bit_hist; c.amp_hist = fb.amp_hist;
+    c.slab_list = fb.slab_list; c.slab_count = fb.slab_count;
+    c.hard_list = fb.hard_list; c.hard_count = fb.hard_count; c.hard_mark = fb.hard_mark;
+    c.item_li = fb.item_li; c.item_slab = fb.item_slab; c.item_count = fb.item_count;
+    c.sv_f64 = fb.sv_f64; c.sv_u32 = fb.sv_u32; c.sv_ring = fb.sv_ring; c.sv_amp = fb.sv_amp;
+    c.sv_samples = fb.sv_samples; c.sv_out = fb.sv_out; c.sv_out_len = fb.sv_out_len;
+    c.samples = a.samples; c.stride = a.stride; c.ids = a.ids; c.id0 = a.id0; c.row_base = a.row_base;
+    c.out = a.out; c.out_len = a.out_len; c.append = append ? 1 : 0;
+    fast_prologue_kernel<<<q.ns, 128, 0, st>>>(c);
+  }
+  CUDA_TRY(cudaGetLastError());
+
+  // ---- fast pass: one launch per group and time slab
+  rc = ensure((void**)&b->slab_done, &b->slab_done_bytes, sizeof(int) * (size_t)W);
+  if (rc != WAM_OK) return rc;
+  CUDA_TRY(cudaMemsetAsync(b->slab_done, 0, sizeof(int) * (size_t)W, st));
+  const int n_str = one_wave ? 2 * G : 0;
+  if (one_wave) {
+    CUDA_TRY(cudaEventRecord(b->slab_fork, st));
+    for (int i = 0; i < n_str; i++) CUDA_TRY(cudaStreamWaitEvent(b->slab_streams[i], b->slab_fork, 0));
+  }
+  for (int slab = 0; slab < n_slabs; slab++) {
+    const long t0 = (long)slab * slab_len;
+    const long len = std::min(slab_len, n - t0);
+    for (int gi = 0; gi < G; gi++) {
+      Group& g = *lg[gi];
+      const FastGeom& q = ctx[gi].q;
+      DemodLaunch Lg;
+      memset(&Lg, 0, sizeof(Lg));
+      Lg.n_groups = 1;
+      Lg.block_begin[1] = L.block_begin[gi + 1] - L.block_begin[gi];
+      Lg.g[0] = L.g[gi];
+      DemodArgs& a = Lg.g[0];
+      a.samples = L.g[gi].samples + t0;
+      a.n = len;
+      if (slab > 0) a.append = 1;
+      if (!make_sample_tmap(&Lg.tmap[0], a.samples, a.stride, len, tmap_rows[gi]))
+        return fail(WAM_E_CUDA, "cuTensorMapEncodeTiled failed for a time slab");
+      Lg.slab = slab;
+      Lg.slab_done = one_wave ? b->slab_done + L.block_begin[gi] : nullptr;
+      const size_t ns = (size_t)q.ns;
+      a.f64 = slab == 0 ? g.f64 : g.fb.ck_f64 + (size_t)(slab - 1) * F64_COUNT * ns;
+      a.u32 = slab == 0 ? g.u32 : g.fb.ck_u32 + (size_t)(slab - 1) * U32_COUNT * ns;
+      a.f64_out = g.fb.ck_f64 + (size_t)slab * F64_COUNT * ns;
+      a.u32_out = g.fb.ck_u32 + (size_t)slab * U32_COUNT * ns;
+      a.bit_hist = g.fb.bit_hist; a.bh_stride = q.bh_stride; a.hist_t0 = q.ph + t0 / kTile;
+      a.amp_hist = g.fb.amp_hist; a.ah_stride = q.ah_stride; a.amp_t0 = q.pa + t0 / 2;
+      a.slab_list = g.fb.slab_list + (size_t)slab * ns; a.slab_count = g.fb.slab_count + slab;
+      cudaStream_t sg = one_wave ? b->slab_streams[2 * gi + (slab % 2)] : st;
+      if (tap) fsk_demod_fast_kernel<true><<<Lg.block_begin[1], 32, 0, sg>>>(Lg);
+      else fsk_demod_fast_kernel<false><<<Lg.block_begin[1], 32, 0, sg>>>(Lg);
+      b->launches++;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  if (one_wave)
+    for (int i = 0; i < n_str; i++) {
+      CUDA_TRY(cudaEventRecord(b->slab_join[i], b->slab_streams[i]));
+      CUDA_TRY(cudaStreamWaitEvent(st, b->slab_join[i], 0));
+    }
+  b->fast_calls++;
+
+  // ---- check of the doubtful decisions (window classes and groups side by side), hard list, epilogue
+  if (guarded) {
+    for (int gi = 0; gi < G; gi++) fast_collect_kernel<<<dim3(4, (unsigned)std::min(n_slabs, 64)), 256, 0, st>>>(ctx[gi]);
+    CUDA_TRY(cudaEventRecord(b->slab_fork, st));
+    for (int gi = 0; gi < G; gi++) {
+      Group& g = *lg[gi];
+      FastCtx& c = ctx[gi];
+      const FastGeom& q = c.q;
+      for (int cls = 0; cls < kVerifyClasses; cls++) {
+        if ((long)(cls + 1) * slab_len > n && cls > 0) continue;  // no window of the call is this long
+        cudaStream_t sv = b->slab_streams[gi * kVerifyClasses + cls];
+        CUDA_TRY(cudaStreamWaitEvent(sv, b->slab_fork, 0));
+        fast_gather_kernel<<<kVerifyCap, 128, 0, sv>>>(c, cls);
+        DemodLaunch Lv;
+        memset(&Lv, 0, sizeof(Lv));
+        DemodArgs& a = Lv.g[0];
+        a.d = g.d;
+        a.ids = nullptr; a.id0 = 0; a.row_base = 0;
+        a.n_local = kVerifyClasses * kVerifyCap;
+        a.f64 = g.fb.sv_f64; a.u32 = g.fb.sv_u32; a.sync_ring = g.fb.sv_ring; a.amp_ring = g.fb.sv_amp;
+        a.samples = g.fb.sv_samples; a.stride = q.sv_stride; a.n = (long)(cls + 1) * slab_len;
+        a.out = g.fb.sv_out; a.out_stride = q.out_stride; a.out_len = g.fb.sv_out_len;
+        rc = launch_exact_selected(b, Lv, g.fb.iota + cls * kVerifyCap, g.fb.item_count + cls, kVerifyCap, a.n, sv);
+        if (rc != WAM_OK) return rc;
+        fast_compare_kernel<<<kVerifyCap / 4, 128, 0, sv>>>(c, cls);
+        CUDA_TRY(cudaEventRecord(b->slab_join[gi * kVerifyClasses + cls], sv));
+        CUDA_TRY(cudaStreamWaitEvent(st, b->slab_join[gi * kVerifyClasses + cls], 0));
+      }
+    }
+    // whole-call float64 run of the hard lists, on the live state and rings
+    for (int gi = 0; gi < G; gi++) {
+      Group& g = *lg[gi];
+      fast_hard_prepare_kernel<<<8, 256, 0, st>>>(ctx[gi]);
+      DemodLaunch Lh;
+      memset(&Lh, 0, sizeof(Lh));
+      Lh.g[0] = L.g[gi];
+      Lh.g[0].append = 1;  // fast_hard_prepare_kernel has put the byte counts back to the start of the call
+      Lh.g[0].tap = nullptr;
+      rc = launch_exact_selected(b, Lh, g.fb.hard_list, g.fb.hard_count, ctx[gi].q.ns, n, st);
+      if (rc != WAM_OK) return rc;
+    }
+  }
+  for (int gi = 0; gi < G; gi++) fast_epilogue_kernel<<<ctx[gi].q.ns, 128, 0, st>>>(ctx[gi]);
+  CUDA_TRY(cudaGetLastError());
+  return WAM_OK;
+}

@@ -181,14 +181,19 @@ static void derive_fast(FskDerived& d) {
   d.f_lp_sg = (float)d.lp_nsg; d.f_lp_om = (float)d.lp_nom;
   {  // two samples per step
     const double sg = d.pre_nsg, om = d.pre_nom, k1 = d.pre_nk1, k2 = d.pre_nk2;
-    d.f_pre_A = (float)(sg * sg - om * om); d.f_pre_B = (float)(2 * sg * om);
-    d.f_pre_c1 = (float)(k1 * sg + k2 * om); d.f_pre_c2 = (float)(k2 * sg - k1 * om);
+    const float A = (float)(sg * sg - om * om), B = (float)(2 * sg * om);
+    d.f2_pre_ks0 = make_float2((float)d.pre_b0, (float)k1); d.f2_pre_ks1 = make_float2(0.0f, (float)d.pre_b0);
+    d.f2_pre_kw1 = make_float2((float)k1, (float)(k1 * sg + k2 * om));
+    d.f2_pre_kw2 = make_float2((float)k2, (float)(k2 * sg - k1 * om));
+    d.f2_pre_as0 = make_float2((float)sg, (float)om); d.f2_pre_as1 = make_float2(1.0f, 0.0f);
+    d.f2_pre_aw1 = make_float2(A, B); d.f2_pre_aw2 = make_float2(-B, A);
   }
   {
     const double sg = d.lp_nsg, om = d.lp_nom, k0 = d.lp_b0, k1 = d.lp_nk1, k2 = d.lp_nk2;
     d.f_lp_A = (float)(sg * sg - om * om); d.f_lp_B = (float)(2 * sg * om);
     d.f_lp_kx0 = (float)(k0 + k1);
     d.f_lp_kw1 = (float)(k1 * (1 + sg) + k2 * om); d.f_lp_kw2 = (float)(k2 * (1 + sg) - k1 * om);
+    d.f2_lp_pw1 = make_float2((float)sg, (float)om); d.f2_lp_pw2 = make_float2(-(float)om, (float)sg);
   }
   d.f_cw = (float)d.cos_omega; d.f_sw = (float)d.sin_omega;
   d.f_c2w = (float)cos(2 * d.omega); d.f_s2w = (float)sin(2 * d.omega);
@@ -199,6 +204,11 @@ static void derive_fast(FskDerived& d) {
   d.f_kappa = 3e-7f;
   d.f_eps0 = 3e-7f;
   d.f_bc_delta = 2e-6f;
+  d.f_gk2 = d.f_gamma * d.f_kappa * 0.5f;  // gamma e1 = (gamma kappa / 2) S (1 / (2 amp) + 1 / (2 amp_prev))
+  d.f_eps0r = (float)((double)d.f_eps0 * (1.0 - rho));
+  d.f_4og = 4.0f / d.f_gamma;
+  d.f_bc_thr = d.f_bc_delta - d.f_4og * d.f_eps0r;
+  d.f_g63 = 6.3f * d.f_gamma;
   d.f_amp_eps = 2e-6f;
   d.fast_ok = (!d.ring_fractional && d.eod_count > 16 && d.total_bits > 0 && d.check_period > 0 && rho < 1.0 &&
                d.amp_phys % 16 == 0) ? 1 : 0;
@@ -312,6 +322,40 @@ static int derive(const wam_fsk_config& c, FskDerived& d) {
 // ------------------------------------------------------------------------------------------
 // batch object
 // ------------------------------------------------------------------------------------------
+// Device buffers of the fast path, per configuration group (used by fast_host.inl).
+constexpr int kVerifyClasses = 4;    // verification windows of 1..4 time slabs
+constexpr int kVerifyCap = 1024;     // windows per class and call; the excess is re-run over the whole call
+struct FastBuffers {
+  // checkpoints 1..S of the per-stream state ([slab][field][stream]); checkpoint 0 is the live state
+  double* ck_f64 = nullptr; size_t ck_f64_bytes = 0;
+  uint32_t* ck_u32 = nullptr; size_t ck_u32_bytes = 0;
+  // per-call linear histories: hard bits (one half word per tile) and amplitudes, each behind a prefix taken from the rings
+  uint16_t* bit_hist = nullptr; size_t bit_hist_bytes = 0;
+  float* amp_hist = nullptr; size_t amp_hist_bytes = 0;
+  // streams flagged per time slab (li | cause << 24), their counts
+  int32_t* slab_list = nullptr; size_t slab_list_bytes = 0;
+  int32_t* slab_count = nullptr; size_t slab_count_bytes = 0;
+  // streams to re-run over the whole call (hard list, no duplicates: hard_mark), statistics of the last call
+  int32_t* hard_list = nullptr; size_t hard_list_bytes = 0;
+  int32_t* hard_count = nullptr;   // [0] hard streams, [1] windows verified, [2] windows that failed, [3] windows dropped
+  uint32_t* hard_mark = nullptr; size_t hard_mark_bytes = 0;
+  // verification scratch, per class c (window of c + 1 slabs): items, state, rings, samples, output
+  int32_t* item_li = nullptr; int32_t* item_slab = nullptr; int32_t* item_count = nullptr; int32_t* iota = nullptr;
+  double* sv_f64 = nullptr; uint32_t* sv_u32 = nullptr; uint32_t* sv_ring = nullptr; float* sv_amp = nullptr;
+  float* sv_samples = nullptr; size_t sv_samples_bytes = 0;
+  uint8_t* sv_out = nullptr; size_t sv_out_bytes = 0;
+  int32_t* sv_out_len = nullptr;
+  bool scratch_ready = false;
+  void release() {
+    for (void* q : {(void*)ck_f64, (void*)ck_u32, (void*)bit_hist, (void*)amp_hist, (void*)slab_list, (void*)slab_count,
+                    (void*)hard_list, (void*)hard_count, (void*)hard_mark, (void*)item_li, (void*)item_slab,
+                    (void*)item_count, (void*)iota, (void*)sv_f64, (void*)sv_u32, (void*)sv_ring, (void*)sv_amp,
+                    (void*)sv_samples, (void*)sv_out, (void*)sv_out_len})
+      if (q) cudaFree(q);
+    *this = FastBuffers();
+  }
+};
+
 struct Group {
   FskDerived d;
   wam_fsk_config cfg;
@@ -323,15 +367,7 @@ struct Group {
   uint32_t* sync_ring = nullptr;
   float* amp_ring = nullptr;
   uint32_t* tmpl = nullptr;  // expect[32][W] then mask[32][W]
-  // fast path: doubt ring, list of the streams flagged in the current call, shadow copy of the state at call start
-  uint32_t* dring = nullptr;
-  int32_t* flag_list = nullptr;
-  int32_t* flag_count = nullptr;
-  double* sh_f64 = nullptr;
-  uint32_t* sh_u32 = nullptr;
-  uint32_t* sh_sync_ring = nullptr;
-  uint32_t* sh_dring = nullptr;
-  float* sh_amp_ring = nullptr;
+  FastBuffers fb;  // fast path: checkpoints, histories, flag lists, verification scratch (fast_host.inl)
   int doubt_state = 0;  // 0: clean (fresh streams), 1: maintained by the fast kernel, 2: stale (an exact kernel ran since)
   bool unaligned = false;  // some call since reset() was not a whole number of 32-sample tiles: fast path closed
 };
@@ -359,13 +395,11 @@ struct wam_fsk_batch {
   uint8_t* stage_out[2] = {nullptr, nullptr};
   int32_t* stage_len[2] = {nullptr, nullptr};
   size_t stage_samples_bytes = 0, stage_out_bytes = 0, stage_len_bytes = 0;
-  int32_t* sh_out_len = nullptr;  // fast path: out_len at call start (append calls)
-  size_t sh_out_len_bytes = 0;
   long fast_calls = 0, fast_launches = 0;
   unsigned long long* phase_cycles = nullptr;  // debug: [max CTAs][4]
   // time slabs of the fused kernel: two streams whose launches overlap, fork / join events, per-CTA progress flags
-  cudaStream_t slab_streams[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t slab_fork = nullptr, slab_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t slab_streams[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t slab_fork = nullptr, slab_join[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int* slab_done = nullptr;
   size_t slab_done_bytes = 0;
   long phase_ctas = 0;
@@ -483,7 +517,6 @@ static int init_group_state(Group& g, cudaStream_t st) {
   CUDA_TRY(cudaMemsetAsync(g.u32, 0, sizeof(uint32_t) * U32_COUNT * n, st));
   CUDA_TRY(cudaMemsetAsync(g.sync_ring, 0, sizeof(uint32_t) * (size_t)g.d.ring_words * n, st));
   CUDA_TRY(cudaMemsetAsync(g.amp_ring, 0, sizeof(float) * (size_t)g.d.amp_phys * n, st));
-  if (g.dring) CUDA_TRY(cudaMemsetAsync(g.dring, 0, sizeof(uint32_t) * (size_t)g.d.ring_words * n, st));
   g.doubt_state = 0;
   g.unaligned = false;
   // AGC gain 1.0 (fsk.ts:46), silence threshold 0.01 (fsk.ts:128)
@@ -500,8 +533,7 @@ static void free_batch(wam_fsk_batch* b) {
   cudaSetDevice(b->device);
   for (auto& g : b->groups) {
     cudaFree(g.d_ids); cudaFree(g.f64); cudaFree(g.u32); cudaFree(g.sync_ring); cudaFree(g.amp_ring); cudaFree(g.tmpl);
-    cudaFree(g.dring); cudaFree(g.flag_list); cudaFree(g.flag_count);
-    cudaFree(g.sh_f64); cudaFree(g.sh_u32); cudaFree(g.sh_sync_ring); cudaFree(g.sh_dring); cudaFree(g.sh_amp_ring);
+    g.fb.release();
     tmpl_slot_release(b->device, g.d.tmpl_slot);
   }
   for (int i = 0; i < 2; i++) {
@@ -511,9 +543,8 @@ static void free_batch(wam_fsk_batch* b) {
     cudaFree(b->stage_samples[i]); cudaFree(b->stage_out[i]); cudaFree(b->stage_len[i]);
   }
   cudaFree(b->phase_cycles);
-  cudaFree(b->sh_out_len);
   cudaFree(b->slab_done);
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < 8; i++) {
     if (b->slab_streams[i]) cudaStreamDestroy(b->slab_streams[i]);
     if (b->slab_join[i]) cudaEventDestroy(b->slab_join[i]);
   }
@@ -680,6 +711,7 @@ static bool make_sample_tmap(CUtensorMap* m, float* d_samples, long stride, long
 // buffers is stream `row_base`.  All configuration groups go into one launch (up to
 // kMaxGroupsPerLaunch per launch) so their one-warp CTAs share the SMs.
 static int ensure(void** p, size_t* cur, size_t need);
+static int fast_streams(wam_fsk_batch* b);
 
 // The fused TMA kernel over a long call of many warps: the call is cut into time slabs of kSlabTiles tiles, one launch
 // per slab, alternating between two streams so that slab j + 1 starts on the SM slots slab j frees; a CTA of slab
@@ -691,19 +723,17 @@ static int ensure(void** p, size_t* cur, size_t need);
 // third waits for the first on its stream), and the earlier one is fully resident by then: no CTA waits on a CTA that
 // cannot run.
 typedef void (*demod_kernel_fn)(const DemodLaunch);
+// per_group: every configuration group of the call gets launches of its own (group 0 of a one-group DemodLaunch), on
+// its own pair of streams — the fast kernel addresses its group's coefficients as compile-time constants.
 static int launch_slabbed(wam_fsk_batch* b, const DemodLaunch& L0, const long* tmap_rows, long n, cudaStream_t st,
-                          demod_kernel_fn kern) {
+                          demod_kernel_fn kern, bool per_group = false) {
   const int W = L0.block_begin[L0.n_groups];
   const long slab_len = (long)kSlabTiles * kTile;
-  const int n_str = 2;
-  if (!b->slab_streams[0]) {
-    for (int i = 0; i < 4; i++) {
-      CUDA_TRY(cudaStreamCreateWithFlags(&b->slab_streams[i], cudaStreamNonBlocking));
-      CUDA_TRY(cudaEventCreateWithFlags(&b->slab_join[i], cudaEventDisableTiming));
-    }
-    CUDA_TRY(cudaEventCreateWithFlags(&b->slab_fork, cudaEventDisableTiming));
-  }
-  int rc = ensure((void**)&b->slab_done, &b->slab_done_bytes, sizeof(int) * (size_t)W);
+  const int n_str = per_group ? 2 * L0.n_groups : 2;
+  if (n_str > 4) return fail(WAM_E_INVALID, "too many groups for per-group slab launches");
+  int rc = fast_streams(b);
+  if (rc != WAM_OK) return rc;
+  rc = ensure((void**)&b->slab_done, &b->slab_done_bytes, sizeof(int) * (size_t)W);
   if (rc != WAM_OK) return rc;
   CUDA_TRY(cudaMemsetAsync(b->slab_done, 0, sizeof(int) * (size_t)W, st));
   CUDA_TRY(cudaEventRecord(b->slab_fork, st));
@@ -724,8 +754,23 @@ static int launch_slabbed(wam_fsk_batch* b, const DemodLaunch& L0, const long* t
     }
     L.slab = slab;
     L.slab_done = b->slab_done;
-    kern<<<W, 32, 0, b->slab_streams[slab % n_str]>>>(L);
-    b->launches++;
+    if (!per_group) {
+      kern<<<W, 32, 0, b->slab_streams[slab % 2]>>>(L);
+      b->launches++;
+    } else {
+      for (int g = 0; g < L.n_groups; g++) {
+        DemodLaunch Lg;
+        memset(&Lg, 0, sizeof(Lg));
+        Lg.tmap[0] = L.tmap[g];
+        Lg.n_groups = 1;
+        Lg.block_begin[1] = L.block_begin[g + 1] - L.block_begin[g];
+        Lg.slab = slab;
+        Lg.slab_done = b->slab_done + L.block_begin[g];
+        Lg.g[0] = L.g[g];
+        kern<<<Lg.block_begin[1], 32, 0, b->slab_streams[2 * g + (slab % 2)]>>>(Lg);
+        b->launches++;
+      }
+    }
   }
   CUDA_TRY(cudaGetLastError());
   for (int i = 0; i < n_str; i++) {
@@ -735,199 +780,7 @@ static int launch_slabbed(wam_fsk_batch* b, const DemodLaunch& L0, const long* t
   return WAM_OK;
 }
 
-// ------------------------------------------------------------------------------------------
-// fast path: float32 kernel with certified decisions + float64 re-run of the flagged streams
-// ------------------------------------------------------------------------------------------
-struct FastRestoreArgs {
-  double* f64; const double* sh_f64;
-  uint32_t* u32; const uint32_t* sh_u32;
-  uint32_t* ring; const uint32_t* sh_ring;
-  uint32_t* dring;
-  float* amp; const float* sh_amp;
-  const int32_t* list; const int32_t* count;
-  const int32_t* ids; int id0, row_base;
-  int32_t* out_len; const int32_t* sh_out_len;  // sh_out_len == nullptr: the call does not append
-  long n;
-  int ring_words, amp_phys;
-};
-// The streams the fast kernel flagged go back to the state they had at the start of the call (shadow copy); their
-// doubt-tracking state is set to "clean after a float64 run": no doubtful bits, the amplitude scale at a safe maximum.
-__global__ void fast_restore_kernel(const FastRestoreArgs r) {
-  const int cnt = *r.count;
-  for (int j = blockIdx.x; j < cnt; j += gridDim.x) {
-    const long li = r.list[j];
-    for (int t = threadIdx.x; t < F64_COUNT; t += blockDim.x) {
-      double v = r.sh_f64[(long)t * r.n + li];
-      if (t == F_FAST_S) v = 16.0;
-      if (t == F_FAST_E || t == F_FAST_RSP) v = 0.0;
-      r.f64[(long)t * r.n + li] = v;
-    }
-    for (int t = threadIdx.x; t < U32_COUNT; t += blockDim.x) {
-      if (t == U_FLAG || t == U_FLAG_EVER || t == U_DOUBT_SAMPLES || t == U_ERR) continue;
-      uint32_t v = r.sh_u32[(long)t * r.n + li];
-      if (t == U_DVOTE || t == U_SILX || t == U_LAST_DOUBT || t == U_DCNT) v = 0u;
-      r.u32[(long)t * r.n + li] = v;
-    }
-    for (int t = threadIdx.x; t < r.ring_words; t += blockDim.x) {
-      r.ring[li * r.ring_words + t] = r.sh_ring[li * r.ring_words + t];
-      r.dring[li * r.ring_words + t] = 0u;
-    }
-    for (int t = threadIdx.x; t < r.amp_phys; t += blockDim.x) r.amp[li * r.amp_phys + t] = r.sh_amp[li * r.amp_phys + t];
-    if (r.sh_out_len && threadIdx.x == 0) {
-      const long row = (r.ids ? r.ids[li] : r.id0 + li) - r.row_base;
-      r.out_len[row] = r.sh_out_len[row];
-    }
-  }
-}
-
-static int fast_buffers(Group& g, cudaStream_t st) {
-  const size_t n = g.ids.size();
-  if (g.dring) return WAM_OK;
-  const size_t rw = sizeof(uint32_t) * (size_t)g.d.ring_words * n;
-  CUDA_TRY(cudaMalloc(&g.dring, rw));
-  CUDA_TRY(cudaMalloc(&g.flag_list, sizeof(int32_t) * n));
-  CUDA_TRY(cudaMalloc(&g.flag_count, sizeof(int32_t)));
-  CUDA_TRY(cudaMalloc(&g.sh_f64, sizeof(double) * F64_COUNT * n));
-  CUDA_TRY(cudaMalloc(&g.sh_u32, sizeof(uint32_t) * U32_COUNT * n));
-  CUDA_TRY(cudaMalloc(&g.sh_sync_ring, rw));
-  CUDA_TRY(cudaMalloc(&g.sh_dring, rw));
-  CUDA_TRY(cudaMalloc(&g.sh_amp_ring, sizeof(float) * (size_t)g.d.amp_phys * n));
-  CUDA_TRY(cudaMemsetAsync(g.dring, 0, rw, st));
-  return WAM_OK;
-}
-
-// After a float64 kernel ran on a group the doubt-tracking state is stale: its bits are certain (no doubtful samples),
-// the error envelope restarts, and the amplitude scale — which the float64 kernels do not track — is set to a safe
-// maximum (it decays to the true scale within a few hundred decimated samples).
-static int fast_clean_doubt(Group& g, cudaStream_t st) {
-  const size_t n = g.ids.size();
-  CUDA_TRY(cudaMemsetAsync(g.dring, 0, sizeof(uint32_t) * (size_t)g.d.ring_words * n, st));
-  for (int u : {(int)U_DVOTE, (int)U_SILX, (int)U_LAST_DOUBT, (int)U_DCNT})
-    CUDA_TRY(cudaMemsetAsync(g.u32 + (size_t)u * n, 0, sizeof(uint32_t) * n, st));
-  for (int f : {(int)F_FAST_E, (int)F_FAST_RSP}) CUDA_TRY(cudaMemsetAsync(g.f64 + (size_t)f * n, 0, sizeof(double) * n, st));
-  fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g.f64 + (size_t)F_FAST_S * n, 16.0, (long)n);
-  CUDA_TRY(cudaGetLastError());
-  return WAM_OK;
-}
-
-// The float64 kernels over the streams named by each group's flag list (sub-selection launches: the list length is
-// read on the device, the grids are sized for the worst case and surplus CTAs leave at once).
-static int launch_exact_flagged(wam_fsk_batch* b, const DemodLaunch& L0, Group* const* lg, bool aligned, long n,
-                                cudaStream_t st) {
-  DemodLaunch L = L0;
-  L.slab = 0; L.slab_done = nullptr;
-  for (int g = 0; g < L.n_groups; g++) {
-    DemodArgs& a = L.g[g];
-    a.sel = lg[g]->flag_list; a.sel_count = lg[g]->flag_count;
-    a.flag_list = nullptr; a.flag_count = nullptr;
-    const int cnt = a.l_end - a.l_begin;
-    a.l_begin = 0; a.l_end = a.n_local;
-    L.block_begin[g + 1] = L.block_begin[g] + (cnt + 31) / 32;
-  }
-  const int W = L.block_begin[L.n_groups];
-  bool pipe = n >= 8 * kTile;
-  if (pipe) {
-    const int v = aligned ? 1 : 0;
-    auto kern = aligned ? fsk_demod_pipe_kernel<true> : fsk_demod_pipe_kernel<false>;
-    if (b->pipe_per_sm[v] < 0) {
-      int ring_words = 0;
-      for (auto& g : b->groups) ring_words = std::max(ring_words, g.d.ring_words);
-      b->pipe_smem = sizeof(PipeShared) + (size_t)ring_words * 32 * sizeof(uint32_t);
-      b->pipe_ring_smem = 1;
-      if (b->pipe_smem > 72 * 1024) { b->pipe_smem = sizeof(PipeShared); b->pipe_ring_smem = 0; }
-      int per_sm = 0;
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->pipe_smem));
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPipeThreads, b->pipe_smem));
-      b->pipe_per_sm[v] = per_sm;
-    }
-    L.pipe_ring_smem = b->pipe_ring_smem;
-    pipe = b->pipe_per_sm[v] > 0;
-    if (pipe) kern<<<W, kPipeThreads, b->pipe_smem, st>>>(L);
-  }
-  if (!pipe) {
-    if (aligned) fsk_demod_exact_kernel<true, false><<<W, 32, 0, st>>>(L);
-    else fsk_demod_exact_kernel<false, false><<<W, 32, 0, st>>>(L);
-  }
-  b->launches++;
-  CUDA_TRY(cudaGetLastError());
-  return WAM_OK;
-}
-
-static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, const long* tmap_rows, long n, uint32_t flags,
-                           cudaStream_t st) {
-  const int W = L.block_begin[L.n_groups];
-  long n_rows = 0;
-  for (int g = 0; g < L.n_groups; g++) n_rows = std::max(n_rows, tmap_rows[g]);
-  const bool append = L.g[0].append != 0;
-  const bool guarded = !(flags & WAM_BATCH_FAST_UNGUARDED);
-  const bool tap = (flags & WAM_BATCH_TAP_FAST_DECISION) != 0 && L.g[0].tap != nullptr;
-  for (int gi = 0; gi < L.n_groups; gi++) {
-    Group& g = *lg[gi];
-    const size_t ns = g.ids.size();
-    int rc = fast_buffers(g, st);
-    if (rc != WAM_OK) return rc;
-    if (g.doubt_state == 2) { rc = fast_clean_doubt(g, st); if (rc != WAM_OK) return rc; }
-    g.doubt_state = 1;
-    CUDA_TRY(cudaMemsetAsync(g.u32 + (size_t)U_FLAG * ns, 0, sizeof(uint32_t) * ns, st));
-    CUDA_TRY(cudaMemsetAsync(g.flag_count, 0, sizeof(int32_t), st));
-    if (guarded) {  // shadow copy of the state at the start of the call
-      const size_t rw = sizeof(uint32_t) * (size_t)g.d.ring_words * ns;
-      CUDA_TRY(cudaMemcpyAsync(g.sh_f64, g.f64, sizeof(double) * F64_COUNT * ns, cudaMemcpyDeviceToDevice, st));
-      CUDA_TRY(cudaMemcpyAsync(g.sh_u32, g.u32, sizeof(uint32_t) * U32_COUNT * ns, cudaMemcpyDeviceToDevice, st));
-      CUDA_TRY(cudaMemcpyAsync(g.sh_sync_ring, g.sync_ring, rw, cudaMemcpyDeviceToDevice, st));
-      CUDA_TRY(cudaMemcpyAsync(g.sh_amp_ring, g.amp_ring, sizeof(float) * (size_t)g.d.amp_phys * ns, cudaMemcpyDeviceToDevice, st));
-    }
-    DemodArgs& a = L.g[gi];
-    a.doubt_ring = g.dring; a.flag_list = g.flag_list; a.flag_count = g.flag_count;
-  }
-  if (guarded && append) {
-    int rc = ensure((void**)&b->sh_out_len, &b->sh_out_len_bytes, sizeof(int32_t) * (size_t)n_rows);
-    if (rc != WAM_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(b->sh_out_len, L.g[0].out_len, sizeof(int32_t) * (size_t)n_rows, cudaMemcpyDeviceToDevice, st));
-  }
-  // the fast kernel, in time slabs when the grid is one even wave (same rule as the float64 kernel)
-  const long n_tiles = (n + kTile - 1) / kTile;
-  if (b->fast_per_sm < 0) {
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fsk_demod_fast_kernel<false>, 32, 0));
-    b->fast_per_sm = per_sm;
-  }
-  const bool one_wave = W <= b->fast_per_sm * b->sm_count;
-  const double per_sched = (double)W / (4.0 * b->sm_count);
-  const double frac = per_sched - std::floor(per_sched);
-  const bool uneven = frac > 0.03 && frac < 0.7;
-  const bool force = (flags & WAM_BATCH_FORCE_SLABS) != 0;
-  if (!(flags & WAM_BATCH_NO_SLABS) && one_wave &&
-      ((W >= b->sm_count * 8 && n_tiles >= 4 * kSlabTiles && uneven) || (force && n_tiles > kSlabTiles))) {
-    int rc = launch_slabbed(b, L, tmap_rows, n, st, tap ? fsk_demod_fast_kernel<true> : fsk_demod_fast_kernel<false>);
-    if (rc != WAM_OK) return rc;
-  } else {
-    L.slab = 0; L.slab_done = nullptr;
-    if (tap) fsk_demod_fast_kernel<true><<<W, 32, 0, st>>>(L);
-    else fsk_demod_fast_kernel<false><<<W, 32, 0, st>>>(L);
-    b->launches++;
-    CUDA_TRY(cudaGetLastError());
-  }
-  b->fast_calls++;
-  if (!guarded) return WAM_OK;
-  // float64 re-run of the flagged streams from the state at the start of the call
-  for (int gi = 0; gi < L.n_groups; gi++) {
-    Group& g = *lg[gi];
-    const DemodArgs& a = L.g[gi];
-    FastRestoreArgs r;
-    r.f64 = g.f64; r.sh_f64 = g.sh_f64; r.u32 = g.u32; r.sh_u32 = g.sh_u32;
-    r.ring = g.sync_ring; r.sh_ring = g.sh_sync_ring; r.dring = g.dring;
-    r.amp = g.amp_ring; r.sh_amp = g.sh_amp_ring;
-    r.list = g.flag_list; r.count = g.flag_count;
-    r.ids = a.ids; r.id0 = a.id0; r.row_base = a.row_base;
-    r.out_len = a.out_len; r.sh_out_len = append ? b->sh_out_len : nullptr;
-    r.n = (long)g.ids.size(); r.ring_words = g.d.ring_words; r.amp_phys = g.d.amp_phys;
-    fast_restore_kernel<<<64, 128, 0, st>>>(r);
-  }
-  CUDA_TRY(cudaGetLastError());
-  const bool aligned = true;
-  return launch_exact_flagged(b, L, lg, aligned, n, st);
-}
+#include "fast_host.inl"
 
 static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base, float* d_samples, long stride, long n,
                               uint8_t* d_out, long out_stride, int32_t* d_out_len, float* d_tap, uint32_t flags,
@@ -948,7 +801,7 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
     // Fast path: float32 kernel with certified decisions, float64 re-run of the streams it flags.  Many streams and
     // long calls only (or WAM_BATCH_FORCE_FAST): short calls are latency-sized and stay with the float64 kernels.
     {
-      bool fast = aligned && !generic && !ragged && tma_ok && n % kTile == 0 &&
+      bool fast = aligned && !generic && !ragged && tma_ok && n % kTile == 0 && L.n_groups <= kFastGroupsPerLaunch &&
                   !(flags & (WAM_BATCH_NO_TMA | WAM_BATCH_EXACT_ONLY));
       for (int g = 0; g < L.n_groups && fast; g++)
         fast = L.g[g].d.fast_ok != 0 && L.g[g].d.tmpl0_words > 0 && !lg[g]->unaligned;
@@ -1050,7 +903,10 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
     tmap_rows[L.n_groups] = s1 - row_base;
     L.block_begin[L.n_groups + 1] = L.block_begin[L.n_groups] + (int)((hi - lo + 31) / 32);
     L.n_groups++;
-    if (L.n_groups == kMaxGroupsPerLaunch) {
+    // a launch that may take the fast path carries at most kFastGroupsPerLaunch groups
+    const bool fast_cand = aligned && !generic && !ragged && tma_ok && n % kTile == 0 &&
+                           !(flags & (WAM_BATCH_NO_TMA | WAM_BATCH_EXACT_ONLY));
+    if (L.n_groups == (fast_cand ? kFastGroupsPerLaunch : kMaxGroupsPerLaunch)) {
       int rc = flush();
       if (rc != WAM_OK) return rc;
     }
@@ -1257,10 +1113,13 @@ extern "C" int wam_fsk_batch_fast_stats(wam_fsk_batch* b, wam_fast_stats* out) {
       out->doubtful_samples += ds[i];
       out->error_flags |= er[i];
     }
-    if (g.flag_count) {
-      int32_t c = 0;
-      CUDA_TRY(cudaMemcpy(&c, g.flag_count, sizeof(c), cudaMemcpyDeviceToHost));
-      out->flagged_last_call += c;
+    if (g.fb.hard_count) {
+      int32_t c[4] = {0, 0, 0, 0};
+      CUDA_TRY(cudaMemcpy(c, g.fb.hard_count, sizeof(c), cudaMemcpyDeviceToHost));
+      out->flagged_last_call += c[0];
+      out->windows_confirmed += c[1];
+      out->windows_refuted += c[2];
+      out->windows_dropped += c[3];
     }
   }
   return WAM_OK;

@@ -76,7 +76,9 @@ struct FskDerived {
   float f_lp_k0, f_lp_k1, f_lp_k2, f_lp_sg, f_lp_om;
   // the same filters two input samples per step: state' = [[A, -B], [B, A]] state + (sg x0 + x1, om x0);
   // pre-filter second output y1 = k0 x1 + k1 x0 + c1 w1 + c2 w2; low-pass pair sum y0 + y1 = k0 x1 + kx0 x0 + kw1 w1 + kw2 w2
-  float f_pre_A, f_pre_B, f_pre_c1, f_pre_c2;
+  // pre-filter, packed: (p0, p1) = ks1 s1 + ks0 s0 + kw1 w1 + kw2 w2, (w1', w2') = as1 s1 + as0 s0 + aw1 w1 + aw2 w2
+  float2 f2_pre_ks0, f2_pre_ks1, f2_pre_kw1, f2_pre_kw2, f2_pre_as0, f2_pre_as1, f2_pre_aw1, f2_pre_aw2;
+  float2 f2_lp_pw1, f2_lp_pw2;  // post filter state step: (w1', w2') = (sg, om) w1 + (-om, sg) w2 + (x, 0)
   float f_lp_A, f_lp_B, f_lp_kx0, f_lp_kw1, f_lp_kw2;
   float f_cw, f_sw;       // float32 LO: phasor of sample 1 after a reset
   float f_c2w, f_s2w;     // rotation by 2 omega (the even and the odd phasor both turn once per pair)
@@ -86,6 +88,8 @@ struct FskDerived {
   float f_kappa;          // relative float32 error of an I/Q output against the recent amplitude scale
   float f_eps0;           // floor of the doubt band on |filteredPhaseDiff|
   float f_bc_delta;       // a raw phase difference this close to +-pi may have wrapped the other way
+  // the same constants folded for the kernel: gamma kappa / 2, eps0 (1 - rho), 4 / gamma, bc_delta - (4 / gamma) eps0 (1 - rho), 6.3 gamma
+  float f_gk2, f_eps0r, f_4og, f_bc_thr, f_g63;
   float f_amp_eps;        // relative doubt band of the silence compare
   int fast_ok;            // the configuration qualifies for the fast kernel (complex poles, integral ring, by-value template)
   // modulator (fsk.ts:389-424)
@@ -101,7 +105,7 @@ enum F64Field {
   F_OX1, F_OX2, F_OY1, F_OY2, F_LAST_PHASE, F_IACC, F_QACC, F_SIL_THR,
   F_RING_WI, F_RING_RI, F_RING_LEN,
   F_RAGGED_CALLS, F_RAGGED_TOTAL,  // demodulateData() calls / samples received through ragged launches (per stream)
-  F_FAST_S, F_FAST_E, F_FAST_RSP,  // fast path: amplitude scale, error envelope, 1 / (4 amplitude) of the last phasor
+  F_FAST_S, F_FAST_E, F_FAST_RSP,  // fast path: amplitude scale, error envelope, 1 / (2 amplitude) of the last phasor
   F64_COUNT
 };
 enum U32Field {
@@ -111,6 +115,7 @@ enum U32Field {
   // compare (bit 31) + the silent run it would add; ring position behind the newest doubtful hard bit (0: none);
   // causes flagged in the current call (bit = WAM_FLAG_*), and over the batch's life (statistics)
   U_DVOTE, U_SILX, U_LAST_DOUBT, U_DCNT, U_FLAG, U_FLAG_EVER, U_DOUBT_SAMPLES,
+  U_OUT_N,  // fast path: bytes this stream has produced so far in the current call (checkpointed per time slab)
   U32_COUNT
 };
 
@@ -147,9 +152,22 @@ struct DemodArgs {
   const int32_t* sel;
   const int32_t* sel_count;
   // fast path
-  uint32_t* doubt_ring;  // [n_local][ring_words]: 1 = that hard bit of the sync ring is doubtful
-  int32_t* flag_list;    // local indices of the streams flagged in this call, appended at *flag_count
+  uint32_t* doubt_ring;  // (unused by the second fast kernel)
+  int32_t* flag_list;    // local indices of the streams whose float64 re-run covers the whole call, appended at *flag_count
   int32_t* flag_count;
+  // fast path, per launch (= one time slab): the state is read from f64 / u32 and written to f64_out / u32_out (the
+  // slab's checkpoints); hard bits and amplitudes go to per-call LINEAR histories instead of the rings — stream li's
+  // tile t of this launch is half word bit_hist[li * bh_stride + hist_t0 + t] and amplitudes
+  // amp_hist[li * ah_stride + amp_t0 + 16 t ..]; both start with a prefix copied from the rings at the start of the
+  // call.  Streams in which this launch flagged a decision are appended to slab_list as li | cause << 24.
+  double* f64_out;
+  uint32_t* u32_out;
+  uint16_t* bit_hist;
+  long bh_stride, hist_t0;
+  float* amp_hist;
+  long ah_stride, amp_t0;
+  int32_t* slab_list;
+  int32_t* slab_count;
 };
 
 // All configuration groups of a batch run in ONE launch (one-warp CTAs; blockIdx selects the group)
