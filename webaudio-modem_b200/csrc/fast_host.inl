@@ -219,6 +219,7 @@ __global__ void fast_hard_prepare_kernel(const FastCtx c) {
     c.f64[(size_t)F_FAST_E * ns + li] = 0.0;
     c.f64[(size_t)F_FAST_RSP * ns + li] = 0.0;
     for (int k : {(int)U_DVOTE, (int)U_SILX, (int)U_LAST_DOUBT, (int)U_DCNT}) c.u32[(size_t)k * ns + li] = 0u;
+    c.u32[(size_t)U_SB_VALID * ns + li] = 0xffffffffu;
     c.out_len[fc_row(c, li)] = (int)c.u32[(size_t)U_OUT_N * ns + li];
   }
 }
@@ -256,6 +257,7 @@ static int fast_clean_doubt(Group& g, cudaStream_t st) {
   const size_t n = g.ids.size();
   for (int u : {(int)U_DVOTE, (int)U_SILX, (int)U_LAST_DOUBT, (int)U_DCNT})
     CUDA_TRY(cudaMemsetAsync(g.u32 + (size_t)u * n, 0, sizeof(uint32_t) * n, st));
+  CUDA_TRY(cudaMemsetAsync(g.u32 + (size_t)U_SB_VALID * n, 0xff, sizeof(uint32_t) * n, st));
   for (int f : {(int)F_FAST_E, (int)F_FAST_RSP}) CUDA_TRY(cudaMemsetAsync(g.f64 + (size_t)f * n, 0, sizeof(double) * n, st));
   fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g.f64 + (size_t)F_FAST_S * n, 16.0, (long)n);
   CUDA_TRY(cudaGetLastError());
@@ -375,7 +377,7 @@ static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, c
   if (rc != WAM_OK) return rc;
   if (b->fast_per_sm < 0) {
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fsk_demod_fast_kernel<false>, 32, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fsk_demod_fast_kernel<false, true>, 32, 0));
     b->fast_per_sm = per_sm;
   }
   // slabs overlap on two streams per group when every CTA of the call is resident at once (see launch_slabbed);
@@ -454,8 +456,10 @@ static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, c
       a.amp_hist = g.fb.amp_hist; a.ah_stride = q.ah_stride; a.amp_t0 = q.pa + t0 / 2;
       a.slab_list = g.fb.slab_list + (size_t)slab * ns; a.slab_count = g.fb.slab_count + slab;
       cudaStream_t sg = one_wave ? b->slab_streams[2 * gi + (slab % 2)] : st;
-      if (tap) fsk_demod_fast_kernel<true><<<Lg.block_begin[1], 32, 0, sg>>>(Lg);
-      else fsk_demod_fast_kernel<false><<<Lg.block_begin[1], 32, 0, sg>>>(Lg);
+      const bool agc = g.d.agc_enabled != 0;
+      auto kern = tap ? (agc ? fsk_demod_fast_kernel<true, true> : fsk_demod_fast_kernel<true, false>)
+                      : (agc ? fsk_demod_fast_kernel<false, true> : fsk_demod_fast_kernel<false, false>);
+      kern<<<Lg.block_begin[1], 32, 0, sg>>>(Lg);
       b->launches++;
     }
   }

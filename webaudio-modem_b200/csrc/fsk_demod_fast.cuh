@@ -52,6 +52,8 @@ struct FastB {     // state machine + doubt tracking, in registers for the whole
   uint32_t dlast, dcnt;  // ring position behind the newest doubtful hard bit (0: none yet); doubtful bits put since the
                          // last gap of total_bits + 32 positions without any (saturating)
   uint32_t sync_det, eod_ev;
+  uint32_t sb_ones;  // frame-search prefilter: ones in the running sub-block
+  int sb_valid;      // sub-blocks in the sub-ring since the check phase was last broken (-1: wait for a check instant)
 };
 
 __device__ __forceinline__ void reset_state_fdsp(FastDsp& s, const FskDerived& d) {
@@ -445,9 +447,110 @@ __device__ __forceinline__ bool sm_step_fast(FastB& b, int bit, bool sil, bool a
 __device__ __forceinline__ int sm_tile_events_fast(FastB& b, uint32_t bits, uint32_t dmask, uint32_t silent, uint32_t adoubt,
                                                    int b_from, uint32_t pos_t0, uint32_t len_t0, const uint32_t* hist,
                                                    uint32_t hpos_t0, const float* amp_t, uint32_t alen_t0,
-                                                   const DemodArgs& a, int li, uint8_t* out_row) {
+                                                   const DemodArgs& a, int li, uint8_t* out_row, uint32_t* sub) {
   const FskDerived& d = a.d;
   constexpr int nk = kTile / 2;
+  // ---- the usual tile in straight-line code: no silence event possible, and what is scheduled inside the tile — sync
+  // checks while searching, one bit decision while receiving — ends the ordinary way (no sync found and none in
+  // doubt; a data bit, a good start bit or a good stop bit).  Nothing is committed before that is known, so every
+  // other tile goes through the event loop below from the untouched state.
+  if (b_from == 0 && adoubt == 0u && d.dspb >= nk) {
+    const uint32_t have = b.sil_cnt + ((b.silx & 0x80000000u) ? (b.silx & 0x7fffffffu) : 0u);
+    bool simple = silent == 0u || have + (uint32_t)nk < (uint32_t)d.eod_count;
+    if (simple) {
+      if (!b.started) {
+        // Frame-search prefilter: the majority bit of every check_period samples goes into a 128-bit shift register
+        // (sub[w * 32], this lane's column of shared memory); a check whose window differs from the template in so
+        // many sub-blocks that the mismatches must exceed the threshold needs no search.  Noise and unsynchronised
+        // payload differ in about half of the 4 (nbits - 1) sub-blocks, so their searches all but disappear.
+        int kc = (int)((uint32_t)d.check_period - 1u - b.gmod);  // first sample of the tile after which a check is due
+        uint32_t ones = b.sb_ones, done = 0u;
+        int valid = b.sb_valid;
+        for (; kc < nk; kc += d.check_period) {
+          const uint32_t m = (2u << kc) - 1u;
+          bool hopeless = false;
+          if (d.sub_ok) {
+            if (valid >= 0) {
+              const uint32_t mb = 2u * (ones + (uint32_t)__popc(bits & m & ~done)) > (uint32_t)d.check_period ? 1u : 0u;
+              const uint32_t s0 = sub[0], s1 = sub[32], s2 = sub[64], s3 = sub[96];
+              const uint32_t n0 = (s0 << 1) | mb, n1 = __funnelshift_l(s0, s1, 1), n2 = __funnelshift_l(s1, s2, 1),
+                             n3 = __funnelshift_l(s2, s3, 1);
+              sub[0] = n0; sub[32] = n1; sub[64] = n2; sub[96] = n3;
+              valid = min(valid + 1, 128);
+              if (valid >= d.sub_blocks) {
+                const int msub = __popc((n0 ^ d.sub_expect[0]) & d.sub_mask[0]) + __popc((n1 ^ d.sub_expect[1]) & d.sub_mask[1]) +
+                                 __popc((n2 ^ d.sub_expect[2]) & d.sub_mask[2]) + __popc((n3 ^ d.sub_expect[3]) & d.sub_mask[3]);
+                hopeless = d.sub_half * msub > d.max_mismatch + (int)min(b.dcnt, 0xffffu);
+              }
+            } else {
+              valid = 0;  // the check phase is known again from here on
+            }
+            ones = 0u; done = m;
+          }
+          if (!hopeless && len_t0 + (uint32_t)kc + 1u >= (uint32_t)d.total_bits) {
+            const int D = b.dcnt != 0u ? doubt_bound(b, pos_t0 + (uint32_t)kc + 1u, d) : 0;
+            const int mism = sync_mismatches_fast_call(hist, hpos_t0 + (uint32_t)kc + 1u, d, d.max_mismatch + D, 0xffffffffu);
+            if (mism <= d.max_mismatch + D) { simple = false; break; }  // a sync, or one the doubtful bits could make
+          }
+        }
+        if (simple) {
+          b.gsc += (uint32_t)nk;
+          b.gmod = (uint32_t)d.check_period - 1u - (uint32_t)(kc - nk);
+          b.sb_ones = ones + (uint32_t)__popc(bits & 0xffffu & ~done);
+          b.sb_valid = valid;
+        }
+      } else {
+        const uint32_t nb = b.bsc + 1u;
+        const int kd = (int)(b.next_idx > nb ? b.next_idx - nb : 0u);  // the sample that completes the running vote
+        if (kd >= nk) {
+          b.bit_acc += (uint32_t)__popc(bits);
+          b.bit_cnt += (uint32_t)nk;
+          if (dmask) b.dvote += (uint32_t)__popc(bits & dmask) + ((uint32_t)__popc(~bits & dmask) << 16);
+        } else {
+          const uint32_t m = (2u << kd) - 1u;
+          const uint32_t acc = b.bit_acc + (uint32_t)__popc(bits & m), cnt = b.bit_cnt + (uint32_t)kd + 1u;
+          const uint32_t decided = 2u * acc > cnt ? 1u : 0u;  // acc > count / 2
+          uint32_t flag = 0u;
+          const uint32_t dm = dmask & m;
+          const uint32_t dv = b.dvote + (uint32_t)__popc(bits & dm) + ((uint32_t)__popc(~bits & dm) << 16);
+          const int bp = b.bitpos;
+          if (dv) {
+            const uint32_t d1 = dv & 0xffffu, d0 = dv >> 16;
+            if ((2u * (acc - d1) > cnt) != (2u * (acc + d0) > cnt))
+              flag = bp == 0 ? WAM_FLAG_VOTE_START : bp == d.stop_pos ? WAM_FLAG_VOTE_STOP : (bp <= 8 ? WAM_FLAG_VOTE_DATA : 0u);
+          }
+          // FSKCore.processByte (fsk.ts:346-375), the outcomes that keep the frame going
+          uint32_t current = b.current;
+          int nbp = bp + 1;
+          int out_n = b.out_n;
+          if (bp == 0) simple = decided == 0u;
+          else if (bp <= 8) current |= decided << (8 - bp);
+          else if (bp == d.stop_pos) {
+            simple = decided == 1u && out_n < a.out_stride;
+            if (simple) { out_row[out_n] = (uint8_t)current; out_n++; current = 0u; nbp = 0; }
+          } else simple = d.parity != 0 && bp == 9;
+          if (simple) {
+            b.flag |= flag;
+            b.current = current; b.bitpos = nbp; b.out_n = out_n;
+            const uint32_t rest = 0xffffu & ~m;
+            b.bit_acc = (uint32_t)__popc(bits & rest);
+            b.bit_cnt = (uint32_t)(nk - 1 - kd);
+            const uint32_t dr = dmask & rest;
+            b.dvote = (uint32_t)__popc(bits & dr) + ((uint32_t)__popc(~bits & dr) << 16);
+            b.next_idx += (uint32_t)d.dspb;
+          }
+        }
+        if (simple) { b.gsc += (uint32_t)nk; b.bsc += (uint32_t)nk; b.sb_valid = -1; }
+      }
+      if (simple) {
+        const uint32_t nz = ~silent & 0xffffu;
+        if (nz) { b.sil_cnt = (uint32_t)(nk - 1) - (31u - (uint32_t)__clz((int)nz)); b.silx = 0u; }
+        else b.sil_cnt += (uint32_t)nk;
+        return -1;
+      }
+    }
+  }
+  b.sb_valid = -1; b.sb_ones = 0u;  // the event loop does not keep the search prefilter's sub-blocks
   int k = b_from;
   while (k < nk) {
     // next sample at which an event can happen
@@ -516,11 +619,12 @@ __device__ __forceinline__ int sm_tile_events_fast(FastB& b, uint32_t bits, uint
 // Common case only (host: fast path eligibility): rows contiguous and 16-byte aligned, aligned calls (n a multiple of
 // 32 ever since reset), integral sync ring, eod_count > 16, by-value sync template, no write-back / ragged counts.
 // TAP: debug variant writing (filteredPhaseDiff, doubt band) per decimated sample into a.tap[row][2k, 2k + 1].
+// AGC: FSKConfig.agcEnabled of the launch's group.
 // GI: the configuration group of this CTA, a compile-time index into the launch parameters so that the group's
 // coefficients are direct constant-bank operands of the arithmetic (a run-time index costs an LDC per use).
-template <bool TAP, int GI>
+template <bool TAP, bool AGC, int GI>
 __device__ __forceinline__ void fsk_demod_fast_body(const DemodLaunch& L, float (*tiles)[kTile * kTile], uint64_t* tma_bar,
-                                                    float* pfbuf) {
+                                                    float* pfbuf, uint32_t* subring) {
   constexpr int gi = GI;
   const DemodArgs& a = L.g[GI];
   const int lane = threadIdx.x;
@@ -594,6 +698,9 @@ __device__ __forceinline__ void fsk_demod_fast_body(const DemodLaunch& L, float 
     b.flag = 0u;  // decisions flagged by THIS launch (its time slab)
     b.dcnt = u[U_DCNT * ns];
     b.sync_det = u[U_SYNC_DET * ns]; b.eod_ev = u[U_EOD_EV * ns];
+    b.sb_ones = u[U_SB_ONES * ns]; b.sb_valid = (int)u[U_SB_VALID * ns];
+    subring[lane] = u[U_SB0 * ns]; subring[32 + lane] = u[U_SB1 * ns]; subring[64 + lane] = u[U_SB2 * ns];
+    subring[96 + lane] = u[U_SB3 * ns];
   }
   uint8_t* out_row = a.out + (long)row * a.out_stride;
   // this launch's part of the stream's linear histories (hard bits: one half word per tile; amplitudes: 16 per tile)
@@ -602,7 +709,6 @@ __device__ __forceinline__ void fsk_demod_fast_body(const DemodLaunch& L, float 
   float* ah = a.amp_hist + (long)lq * a.ah_stride + a.amp_t0;
   float* tap_row = TAP ? a.tap + (long)row * a.stride : nullptr;
   uint32_t n_doubt = 0u;
-  const bool agc = d.agc_enabled != 0;
   const AgcConsts kagc = agc_consts(d);
 
   const long n_tiles = a.n / kTile;  // aligned calls: whole tiles only
@@ -643,7 +749,7 @@ __device__ __forceinline__ void fsk_demod_fast_body(const DemodLaunch& L, float 
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float s0 = xs[2 * j], s1 = xs[2 * j + 1];
-        if (agc) {
+        if (AGC) {  // compile-time: a run-time branch here would fence the AGC's dependency chain off from the filters
           s0 = fast_agc(gain, s0, kagc);
           s1 = fast_agc(gain, s1, kagc);
         }
@@ -677,7 +783,7 @@ __device__ __forceinline__ void fsk_demod_fast_body(const DemodLaunch& L, float 
         redo = false;
         const int k_reset = sm_tile_events_fast(b, bits, dmask, silent, adoubt, b_from, pos_t0, len_t0, hist,
                                                 (uint32_t)(a.hist_t0 + t) * (kTile / 2), ah + t * (kTile / 2), alen_t0, a, li,
-                                                out_row);
+                                                out_row, subring + lane);
         if (k_reset >= 0 && k_reset + 1 < kTile / 2) {
           // resetState(): A2 restarts from the zeroed state at the next pair (S is kept) and the rest of the tile is
           // decided again from the pre-filtered samples
@@ -748,6 +854,9 @@ __device__ __forceinline__ void fsk_demod_fast_body(const DemodLaunch& L, float 
     u[U_SYNC_DET * ns] = b.sync_det; u[U_EOD_EV * ns] = b.eod_ev;
     u[U_DOUBT_SAMPLES * ns] += n_doubt;
     u[U_OUT_N * ns] = (uint32_t)b.out_n;
+    u[U_SB_ONES * ns] = b.sb_ones; u[U_SB_VALID * ns] = (uint32_t)b.sb_valid;
+    u[U_SB0 * ns] = subring[lane]; u[U_SB1 * ns] = subring[32 + lane]; u[U_SB2 * ns] = subring[64 + lane];
+    u[U_SB3 * ns] = subring[96 + lane];
     a.out_len[row] = b.out_n < a.out_stride ? b.out_n : (int)a.out_stride;
     if (b.flag != 0u) {  // a decision of this time slab was doubtful: queue the stream for the float64 check of the slab
       u[U_FLAG * ns] |= b.flag;
@@ -765,12 +874,13 @@ constexpr int kFastGroupsPerLaunch = 2;  // configuration groups one fast call c
 // one-warp CTAs still fill the SMs together): the same code for every group keeps the hot loop in the instruction
 // cache — two copies of the body specialised on the group index in one launch drop its hit rate from 99 % to 77 %
 // and the kernel from 12.9 to 18.8 ms.
-template <bool TAP>
+template <bool TAP, bool AGC>
 __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_fast_kernel(const __grid_constant__ DemodLaunch L) {
   __shared__ __align__(1024) float tiles[kStages][kTile * kTile];
   __shared__ __align__(8) uint64_t tma_bar[kStages];
   __shared__ __align__(128) float pfbuf[kTile * 32];  // pre-filtered samples [i][lane] (replay after resetState())
-  fsk_demod_fast_body<TAP, 0>(L, tiles, tma_bar, pfbuf);
+  __shared__ uint32_t subring[4 * 32];                // frame-search prefilter: sub-block shift register [word][lane]
+  fsk_demod_fast_body<TAP, AGC, 0>(L, tiles, tma_bar, pfbuf, subring);
 }
 
 }  // namespace wam

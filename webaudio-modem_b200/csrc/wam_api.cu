@@ -210,6 +210,18 @@ static void derive_fast(FskDerived& d) {
   d.f_bc_thr = d.f_bc_delta - d.f_4og * d.f_eps0r;
   d.f_g63 = 6.3f * d.f_gamma;
   d.f_amp_eps = 2e-6f;
+  // frame-search prefilter (fsk_demod_fast.cuh): sub-block i (i = 0 newest) covers the samples i * cp .. (i + 1) * cp - 1
+  // back from the check instant, i.e. window j = i / 4 of fsk.ts:303-312 with expected bit pattern[nbits - j] (j = 0
+  // is never compared)
+  d.sub_ok = (d.check_period > 0 && d.dspb == 4 * d.check_period && 4 * d.nbits <= 128) ? 1 : 0;
+  d.sub_half = d.check_period / 2;
+  d.sub_blocks = 4 * d.nbits;
+  if (d.sub_ok)
+    for (int i = 4; i < 4 * d.nbits; i++) {
+      const int j = i / 4, k = d.nbits - j;
+      d.sub_mask[i >> 5] |= 1u << (i & 31);
+      if ((d.pattern[k >> 5] >> (k & 31)) & 1u) d.sub_expect[i >> 5] |= 1u << (i & 31);
+    }
   d.fast_ok = (!d.ring_fractional && d.eod_count > 16 && d.total_bits > 0 && d.check_period > 0 && rho < 1.0 &&
                d.amp_phys % 16 == 0) ? 1 : 0;
 }

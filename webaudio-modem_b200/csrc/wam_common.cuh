@@ -92,6 +92,11 @@ struct FskDerived {
   float f_gk2, f_eps0r, f_4og, f_bc_thr, f_g63;
   float f_amp_eps;        // relative doubt band of the silence compare
   int fast_ok;            // the configuration qualifies for the fast kernel (complex poles, integral ring, by-value template)
+  // frame-search prefilter: the window seen in sub-blocks of check_period samples (4 per line bit when dspb = 4 check_period):
+  // expected majority bit and compare mask per sub-block, newest first; a sub-block whose majority differs from the
+  // template holds at least sub_half mismatching samples, so sub_half * (differing sub-blocks) > max_mismatch rules a sync out
+  uint32_t sub_expect[4], sub_mask[4];
+  int sub_ok, sub_half, sub_blocks;
   // modulator (fsk.ts:389-424)
   double mark, space, fs;
   int n_preamble, n_sfd;
@@ -116,6 +121,10 @@ enum U32Field {
   // causes flagged in the current call (bit = WAM_FLAG_*), and over the batch's life (statistics)
   U_DVOTE, U_SILX, U_LAST_DOUBT, U_DCNT, U_FLAG, U_FLAG_EVER, U_DOUBT_SAMPLES,
   U_OUT_N,  // fast path: bytes this stream has produced so far in the current call (checkpointed per time slab)
+  // fast path, frame-search prefilter: ones in the running sub-block (check_period samples), sub-blocks in the
+  // sub-ring since the check phase was last broken (0xffffffff: wait for the next check instant), the sub-ring itself
+  // (majority bit per sub-block, newest in bit 0 of word 0)
+  U_SB_ONES, U_SB_VALID, U_SB0, U_SB1, U_SB2, U_SB3,
   U32_COUNT
 };
 
