@@ -7,7 +7,7 @@ timeout 300 python scripts/exp_fast_tap.py --streams 512 --out gpurun_out/fast_$
 tail -1 gpurun_out/fast_${tag}_tap.log | cut -c1-400
 timeout 500 python scripts/exp_fast_vs_exact.py --skip-a --iters 4 --out gpurun_out/fast_${tag}_vs_exact.jsonl > gpurun_out/fast_${tag}.log 2>&1
 tail -2 gpurun_out/fast_${tag}.log | cut -c1-420
-timeout 300 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:fsk_demod_fast -s 24 -c 24 --csv --log-file gpurun_out/fast_${tag}_ncu.csv python scripts/run_config2_once.py --flags 512 --iters 2 > gpurun_out/ncu_run.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:fsk_demod_fast\|fsk_demod_duo -s 24 -c 24 --csv --log-file gpurun_out/fast_${tag}_ncu.csv python scripts/run_config2_once.py --flags 512 --iters 2 > gpurun_out/ncu_run.log 2>&1
 python - <<PY
 import csv
 rows=list(csv.reader(open('gpurun_out/fast_${tag}_ncu.csv')))
