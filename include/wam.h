@@ -199,6 +199,8 @@ typedef struct wam_fast_stats {
   int64_t windows_confirmed, windows_refuted, windows_dropped;
 } wam_fast_stats;
 int wam_fsk_batch_fast_stats(wam_fsk_batch* b, wam_fast_stats* out);
+/* test hook: multiplies the fast kernel's doubt band (1 = calibrated); a wide band flags many decisions */
+int wam_fsk_batch_debug_fast_band(wam_fsk_batch* b, double scale);
 
 /* modulateData() for every stream: data uint8 [n_streams][data_stride], data_len[s] bytes each
  * (NULL = nbytes for all).  out float32 [n_streams][out_stride]; out_len[s] samples written.

@@ -171,6 +171,14 @@ static bool normal_form(double b0, double b1, double b2, double a1, double a2, d
   k2 = (b2 - b0 * a2 + k1 * sg) / om;
   return std::isfinite(k1) && std::isfinite(k2);
 }
+// the doubt band's constants as the kernel uses them (fast_decim)
+static void fold_band(FskDerived& d) {
+  d.f_gk2 = d.f_gamma * d.f_kappa * 0.5f;  // gamma e1 = (gamma kappa / 2) S (1 / (2 amp) + 1 / (2 amp_prev))
+  d.f_eps0r = (float)((double)d.f_eps0 * (1.0 - (double)d.f_rho_e));
+  d.f_4og = 4.0f / d.f_gamma;
+  d.f_bc_thr = d.f_bc_delta - d.f_4og * d.f_eps0r;
+  d.f_g63 = 6.3f * d.f_gamma;
+}
 static void derive_fast(FskDerived& d) {
   bool ok = normal_form(d.pre_b0, d.pre_b1, d.pre_b2, d.pre_a1, d.pre_a2, d.pre_nk1, d.pre_nk2, d.pre_nsg, d.pre_nom);
   ok = normal_form(d.lp_b0, d.lp_b1, d.lp_b2, d.lp_a1, d.lp_a2, d.lp_nk1, d.lp_nk2, d.lp_nsg, d.lp_nom) && ok;
@@ -204,12 +212,8 @@ static void derive_fast(FskDerived& d) {
   d.f_kappa = 3e-7f;
   d.f_eps0 = 3e-7f;
   d.f_bc_delta = 2e-6f;
-  d.f_gk2 = d.f_gamma * d.f_kappa * 0.5f;  // gamma e1 = (gamma kappa / 2) S (1 / (2 amp) + 1 / (2 amp_prev))
-  d.f_eps0r = (float)((double)d.f_eps0 * (1.0 - rho));
-  d.f_4og = 4.0f / d.f_gamma;
-  d.f_bc_thr = d.f_bc_delta - d.f_4og * d.f_eps0r;
-  d.f_g63 = 6.3f * d.f_gamma;
   d.f_amp_eps = 2e-6f;
+  fold_band(d);
   // frame-search prefilter (fsk_demod_fast.cuh): sub-block i (i = 0 newest) covers the samples i * cp .. (i + 1) * cp - 1
   // back from the check instant, i.e. window j = i / 4 of fsk.ts:303-312 with expected bit pattern[nbits - j] (j = 0
   // is never compared)
@@ -653,6 +657,19 @@ extern "C" int wam_fsk_batch_destroy(wam_fsk_batch* b) {
 
 // FSKCore.reset() on every stream — fsk.ts:464-469: resetState(), clear the sync ring, drop queued
 // bytes, zero the debug counters.  AGC, pre-filter, amplitude ring and silence threshold survive.
+// Test hook: widens (scale > 1) the fast kernel's doubt band — error floor, amplitude-relative term and the silence
+// compare's band — so that many decisions are flagged and the float64 checks carry real load.  Results must not change.
+extern "C" int wam_fsk_batch_debug_fast_band(wam_fsk_batch* b, double scale) {
+  if (!b || !(scale > 0)) return fail(WAM_E_INVALID, "bad argument");
+  for (auto& g : b->groups) {
+    g.d.f_kappa = 3e-7f * (float)scale;
+    g.d.f_eps0 = 3e-7f * (float)scale;
+    g.d.f_amp_eps = std::min(2e-6f * (float)scale, 0.5f);
+    fold_band(g.d);
+  }
+  return WAM_OK;
+}
+
 extern "C" int wam_fsk_batch_reset(wam_fsk_batch* b) {
   if (!b) return fail(WAM_E_INVALID, "batch is NULL");
   CUDA_TRY(cudaSetDevice(b->device));

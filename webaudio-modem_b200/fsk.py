@@ -254,6 +254,10 @@ class FSKBatch:
     def launch_count(self) -> int:
         return int(self._lib.wam_fsk_batch_launch_count(self._h))
 
+    def debug_fast_band(self, scale: float):
+        """Test hook: widen the fast kernel's doubt band (wam_fsk_batch_debug_fast_band)."""
+        L.check(self._lib.wam_fsk_batch_debug_fast_band(self._h, float(scale)))
+
     def fast_stats(self) -> dict:
         """Counters of the mixed-precision fast path (wam_fsk_batch_fast_stats)."""
         st = L.FastStats()
