@@ -199,6 +199,11 @@ typedef struct wam_fast_stats {
   int64_t windows_confirmed, windows_refuted, windows_dropped;
 } wam_fast_stats;
 int wam_fsk_batch_fast_stats(wam_fsk_batch* b, wam_fast_stats* out);
+/* Channel model of the synthetic workloads (BASELINE config 5: modulate -> AWGN -> demodulate): adds Gaussian noise
+ * of standard deviation d_sigma[row] in place to device rows (counter-based Philox4x32-10; seed, seq, row and column
+ * fix every value).  n and stride multiples of 4, rows 16-byte aligned.  Not part of FSKCore. */
+int wam_awgn_add_device(float* d_samples, long stride, long n_rows, long n, const float* d_sigma,
+                        unsigned long long seed, unsigned int seq, void* cuda_stream);
 /* test hook: multiplies the fast kernel's doubt band (1 = calibrated); a wide band flags many decisions */
 int wam_fsk_batch_debug_fast_band(wam_fsk_batch* b, double scale);
 

@@ -3,7 +3,7 @@
 import ctypes as C, importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-import bench_configs as bc
+import bench as bc  # (frame_samples / modulate_rows now take a Ctx: adapt before use)
 wam = bc.wam
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 baud = int(sys.argv[2]) if len(sys.argv) > 2 else 1200

@@ -123,6 +123,7 @@ SYMBOLS = {
     "wam_fsk_batch_launch_count": (C.c_long, [_vp]),
     "wam_fsk_batch_fast_stats": (C.c_int, [_vp, C.POINTER(FastStats)]),
     "wam_fsk_batch_debug_fast_band": (C.c_int, [_vp, C.c_double]),
+    "wam_awgn_add_device": (C.c_int, [_vp, C.c_long, C.c_long, C.c_long, _vp, C.c_ulonglong, C.c_uint, _vp]),
     "wam_fsk_batch_debug_phase_cycles": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_long]),
     "wam_fsk_batch_modulate": (C.c_int, [_vp, _vp, C.c_long, _vp, C.c_long, _vp, C.c_long, _vp]),
     "wam_fsk_batch_modulate_device": (C.c_int, [_vp, _vp, C.c_long, _vp, C.c_long, _vp, C.c_long, _vp, _vp]),

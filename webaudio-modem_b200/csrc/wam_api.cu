@@ -19,6 +19,7 @@
 #include "fsk_demod.cuh"
 #include "fsk_demod_pipe.cuh"
 #include "fsk_demod_fast.cuh"
+#include "awgn.cuh"
 #include "fsk_mod.cuh"
 #include "wam_common.cuh"
 
@@ -657,6 +658,21 @@ extern "C" int wam_fsk_batch_destroy(wam_fsk_batch* b) {
 
 // FSKCore.reset() on every stream — fsk.ts:464-469: resetState(), clear the sync ring, drop queued
 // bytes, zero the debug counters.  AGC, pre-filter, amplitude ring and silence threshold survive.
+// Channel model for the synthetic workloads (BASELINE config 5: modulate -> AWGN -> demodulate): Gaussian noise of
+// standard deviation d_sigma[row] added in place to device rows; (seed, seq, row, column) fixes every value.
+extern "C" int wam_awgn_add_device(float* d_samples, long stride, long n_rows, long n, const float* d_sigma,
+                                   unsigned long long seed, unsigned int seq, void* cuda_stream) {
+  if (!d_samples || !d_sigma || n_rows < 0 || n < 0 || stride < n) return fail(WAM_E_INVALID, "bad buffer description");
+  if ((n & 3) || (stride & 3) || (reinterpret_cast<uintptr_t>(d_samples) & 15))
+    return fail(WAM_E_INVALID, "wam_awgn_add_device needs 16-byte aligned rows and a multiple of 4 samples");
+  if (n_rows == 0 || n == 0) return WAM_OK;
+  const long total = n_rows * (n / 4);
+  const unsigned blocks = (unsigned)std::min<long>((total + 255) / 256, 148L * 32);
+  awgn_add_kernel<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(d_samples, stride, n_rows, n, d_sigma, seed, seq);
+  CUDA_TRY(cudaGetLastError());
+  return WAM_OK;
+}
+
 // Test hook: widens (scale > 1) the fast kernel's doubt band — error floor, amplitude-relative term and the silence
 // compare's band — so that many decisions are flagged and the float64 checks carry real load.  Results must not change.
 extern "C" int wam_fsk_batch_debug_fast_band(wam_fsk_batch* b, double scale) {
