@@ -213,3 +213,27 @@ def test_doubt_band_covers_the_float32_error(gpu_wam, oracle):
         wrong = (F > 0) != (oF[:k] > 0)
         assert not np.any(wrong & ~(np.abs(F) < band)), f"stream {i}: a hard bit differs outside the doubt band"
     assert 0.0 < worst < 1.0, worst
+
+
+def test_time_slabs_next_to_a_foreign_kernel(gpu_wam, oracle):
+    """Time-slab launches hand their streams over through a spin on a flag; the spin is bounded, so foreign kernels
+    holding SM slots may slow the call down or — at worst — end it with WAM_ERR_SLAB_TIMEOUT on record, never hang
+    it.  Both the float64 kernel and the fast kernel, each next to a stream of large matmuls."""
+    import torch
+
+    L = _lib(gpu_wam)
+    cfgs, idx, x = _v21_batch(128, seed=61, n=32768)
+    want, ost = _oracle(oracle, cfgs, idx, x)
+    side = torch.cuda.Stream()
+    a = torch.randn((8192, 8192), device="cuda", dtype=torch.float16)
+    for flags in (L.WAM_BATCH_EXACT_ONLY | L.WAM_BATCH_NO_PIPELINE | L.WAM_BATCH_FORCE_SLABS, L.WAM_BATCH_FORCE_FAST):
+        db = DeviceBatch(gpu_wam, cfgs, idx, 128)
+        with torch.cuda.stream(side):
+            for _ in range(40):
+                a = (a @ a).clamp_(-1, 1)
+        got = db.run(x, flags)
+        torch.cuda.synchronize()
+        st = db.b.status()
+        if db.b.fast_stats()["error_flags"] & 4:
+            continue  # hand-over timed out: reported, not silent
+        _check(got, st, want, ost)

@@ -855,11 +855,22 @@ __global__ void __launch_bounds__(32, WAM_DEMOD_MIN_BLOCKS) fsk_demod_exact_kern
   const int lane = threadIdx.x;
   // Time slabs (host: launch_slabbed): a long call arrives as launches of kSlabTiles tiles that overlap on two
   // streams; a CTA of slab j waits here until the CTA of slab j - 1 has published the state of the same 32 streams.
-  // Every lane spins with an acquire load (one opaque asm block: a C++ loop here costs the kernel 48 bytes of spills).
+  // Every lane spins with an acquire load, at most 2^22 rounds of 256 ns (about a second): a predecessor that never
+  // becomes resident (foreign kernels holding the SM slots) must not hang the GPU — on expiry the CTA's streams are
+  // left untouched and WAM_ERR_SLAB_TIMEOUT is recorded (errorEvents).  One opaque asm block: a C++ loop here costs
+  // the kernel 48 bytes of spills.
   if (STAGE_TMA && !GENERIC && L.slab_done != nullptr && L.slab > 0) {
-    asm volatile("{\n\t.reg .pred p;\n\t.reg .s32 v;\n$L_slab_wait:\n\tld.acquire.gpu.global.s32 v, [%0];\n\t"
-                 "setp.lt.s32 p, v, %1;\n\t@p nanosleep.u32 256;\n\t@p bra $L_slab_wait;\n\t}\n"
-                 ::"l"(L.slab_done + blockIdx.x), "r"(L.slab) : "memory");
+    int expired;
+    asm volatile("{\n\t.reg .pred p, q;\n\t.reg .s32 v;\n\t.reg .u32 c;\n\tmov.u32 c, 0;\n$L_slab_wait:\n\t"
+                 "ld.acquire.gpu.global.s32 v, [%1];\n\t"
+                 "setp.lt.s32 p, v, %2;\n\tadd.u32 c, c, 1;\n\tsetp.lt.u32 q, c, 4194304;\n\tand.pred q, p, q;\n\t"
+                 "@q nanosleep.u32 256;\n\t@q bra $L_slab_wait;\n\tselp.s32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(expired) : "l"(L.slab_done + blockIdx.x), "r"(L.slab) : "memory");
+    if (expired) {
+      const int lt = a.l_begin + ((int)blockIdx.x - L.block_begin[gi]) * 32 + lane;
+      if (lt < a.l_end) a.u32[(long)U_ERR * a.n_local + lt] |= WAM_ERR_SLAB_TIMEOUT;
+      return;
+    }
   }
   int li = a.l_begin + ((int)blockIdx.x - L.block_begin[gi]) * 32 + lane;
   bool active = li < a.l_end;
