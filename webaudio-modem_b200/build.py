@@ -1,6 +1,11 @@
-"""Builds libwam.so in-tree with nvcc for sm_100a (B200).  No torch involved."""
+"""Builds libwam.so in-tree with nvcc for sm_100a (B200).  No torch involved.
+
+The library is rebuilt whenever it was not produced from the sources in the tree: a sha256 over the CUDA sources,
+the public header and the nvcc flags is stored next to the library (libwam.so.srchash) and compared, so a stale or
+foreign .so (older checkout, other flags, copied file) never passes for a build of these sources."""
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -8,6 +13,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwam.so")
+STAMP = LIB + ".srchash"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
@@ -22,13 +28,26 @@ def _sources():
     return out
 
 
+def source_hash() -> str:
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    for p in _sources():
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
     if os.environ.get("WAM_LIB"):
         return False
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(s) > t for s in _sources())
+    try:
+        with open(STAMP) as f:
+            return f.read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -41,6 +60,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd.insert(2, "-v")
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    with open(STAMP, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB
 
 
