@@ -179,6 +179,20 @@ long wam_fsk_mux_pending(wam_fsk_mux* m, long session);
 long wam_fsk_mux_out_capacity(wam_fsk_mux* m);   /* bytes one flush can produce per session at most */
 int wam_fsk_mux_flush(wam_fsk_mux* m, uint8_t* out, long out_stride, int32_t* out_len);
 wam_fsk_batch* wam_fsk_mux_batch(wam_fsk_mux* m); /* the sessions' FSKCore instances (status, reset); owned by the mux */
+/* Send half: one ChunkedModulator (src/webaudio/chunked-modulator.ts:31-87) per session.  wam_fsk_mux_send queues a
+ * payload (startModulation; an empty payload resets the session), wam_fsk_mux_modulate runs modulateData() for every
+ * session that queued one as ONE batched GPU call, wam_fsk_mux_pull is getNextSamples(sampleCount): returns 1 and
+ * fills out / res while the session is sending, 0 when it is not (the reference returns null). */
+typedef struct wam_chunk_result {
+  long samples;          /* samples written to out (ChunkResult.signal.length) */
+  int isComplete;
+  long samplesConsumed;
+  long totalSamples;
+} wam_chunk_result;
+int wam_fsk_mux_send(wam_fsk_mux* m, long session, const uint8_t* data, long n);
+int wam_fsk_mux_modulate(wam_fsk_mux* m);
+int wam_fsk_mux_is_modulating(wam_fsk_mux* m, long session);
+int wam_fsk_mux_pull(wam_fsk_mux* m, long session, float* out, long sample_count, wam_chunk_result* res);
 /* per-stream getStatus(); st: host array [n_streams] */
 int wam_fsk_batch_status(wam_fsk_batch* b, wam_fsk_status* st);
 /* profiling aid: per-phase SM cycle counters of the demodulator (A1, A2, B, other), summed over CTAs */

@@ -220,3 +220,61 @@ def test_xmodem_batch_receive_reference_cases(gpu_wam, oracle):
     for i, (_, data, rep, received, dropped) in enumerate(cases):
         assert rx.received(i) == data and replies[i] == rep
         assert int(rx.state["packetsReceived"][i]) == received and int(rx.state["packetsDropped"][i]) == dropped
+
+
+# ---- send half: ChunkedModulator (tests/webaudio/chunked-modulator.node.test.ts) ------------------------------------
+def test_chunked_modulator_slices_equal_direct_signal(gpu_wam):
+    """chunked-modulator.node.test.ts:25-47 (same signal as direct generation), :49-54 (empty data), :57-80."""
+    m = gpu_wam.FSKCore()
+    m.configure({})
+    cm = gpu_wam.ChunkedModulator(m)
+    assert not cm.isModulating() and cm.getProgress() == 0
+    direct = m.modulateData(b"AB")
+    cm.startModulation(b"AB")
+    parts = []
+    while True:
+        r = cm.getNextSamples(128)
+        assert r is not None and 0 < len(r["signal"]) <= 128 and r["totalSamples"] == len(direct)
+        parts.append(r["signal"])
+        if r["isComplete"]:
+            assert r["samplesConsumed"] == len(direct)
+            break
+        assert len(r["signal"]) == 128
+    assert np.array_equal(np.concatenate(parts), direct)
+    assert not cm.isModulating() and cm.getNextSamples(128) is None
+    cm.startModulation(b"")
+    assert not cm.isModulating() and cm.getNextSamples(128) is None
+
+
+def test_session_mux_send_half_round_trip(gpu_wam):
+    """Many sessions queue payloads, one batched modulate, 128-sample pulls; the pulled signal demodulates to the
+    payload (chunked-modulator.node.test.ts:222-249) and equals the single-stream modulator's output."""
+    n = 48
+    mux = gpu_wam.FSKSessionMux(n, {}, max_block=256)
+    payloads = {s: bytes([0x41 + (s % 20)] * (1 + s % 5)) for s in range(0, n, 3)}
+    for s, p in payloads.items():
+        mux.send(s, p)
+    mux.send(1, b"")  # empty payload: the session stays idle
+    mux.modulate()
+    ref = gpu_wam.FSKCore()
+    ref.configure({})
+    for s in range(n):
+        if s not in payloads:
+            assert not mux.is_modulating(s) and mux.pull(s, 128) is None
+            continue
+        assert mux.is_modulating(s)
+        direct = ref.modulateData(payloads[s])
+        parts = []
+        while True:
+            r = mux.pull(s, 128)
+            parts.append(r["signal"])
+            assert r["totalSamples"] == len(direct)
+            if r["isComplete"]:
+                break
+            assert len(r["signal"]) == 128
+        sig = np.concatenate(parts)
+        assert np.array_equal(sig, direct)
+        assert not mux.is_modulating(s) and mux.pull(s, 128) is None
+        rx = gpu_wam.FSKCore()
+        rx.configure({})
+        assert bytes(rx.demodulateData(sig.copy())) == payloads[s]

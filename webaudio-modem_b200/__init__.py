@@ -5,6 +5,6 @@ Import with importlib (the directory name carries a hyphen):
 """
 from . import _lib  # noqa: F401
 from ._lib import WamError, lib  # noqa: F401
-from .fsk import DEFAULT_FSK_CONFIG, FSKBatch, FSKCore, FSKSessionMux, normalize_config  # noqa: F401
+from .fsk import DEFAULT_FSK_CONFIG, ChunkedModulator, FSKBatch, FSKCore, FSKSessionMux, normalize_config  # noqa: F401
 from .filters import FilterDesign, FilterFactory, FIRFilter, IIRFilter  # noqa: F401
 from .xmodem import CRC16, XModemPacket, XModemBatchReceiver, xmodem_batch_check, crc16_batch, PKT_STATUS  # noqa: F401

@@ -78,6 +78,11 @@ class FastStats(C.Structure):
                 ("windows_confirmed", C.c_int64), ("windows_refuted", C.c_int64), ("windows_dropped", C.c_int64)]
 
 
+class ChunkResult(C.Structure):
+    """wam_chunk_result (include/wam.h)"""
+    _fields_ = [("samples", C.c_long), ("isComplete", C.c_int), ("samplesConsumed", C.c_long), ("totalSamples", C.c_long)]
+
+
 class XmodemRxState(C.Structure):
     """wam_xmodem_rx_state (include/wam.h)"""
     _fields_ = [("expectedSequence", C.c_int32), ("retries", C.c_int32), ("done", C.c_int32),
@@ -123,6 +128,10 @@ SYMBOLS = {
     "wam_fsk_batch_launch_count": (C.c_long, [_vp]),
     "wam_fsk_batch_fast_stats": (C.c_int, [_vp, C.POINTER(FastStats)]),
     "wam_fsk_batch_debug_fast_band": (C.c_int, [_vp, C.c_double]),
+    "wam_fsk_mux_send": (C.c_int, [_vp, C.c_long, _vp, C.c_long]),
+    "wam_fsk_mux_modulate": (C.c_int, [_vp]),
+    "wam_fsk_mux_is_modulating": (C.c_int, [_vp, C.c_long]),
+    "wam_fsk_mux_pull": (C.c_int, [_vp, C.c_long, _vp, C.c_long, C.POINTER(ChunkResult)]),
     "wam_awgn_add_device": (C.c_int, [_vp, C.c_long, C.c_long, C.c_long, _vp, C.c_ulonglong, C.c_uint, _vp]),
     "wam_fsk_batch_debug_phase_cycles": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_long]),
     "wam_fsk_batch_modulate": (C.c_int, [_vp, _vp, C.c_long, _vp, C.c_long, _vp, C.c_long, _vp]),

@@ -1706,6 +1706,12 @@ struct wam_fsk_mux {
   uint8_t* h_out = nullptr;     // pinned [n_sessions][out_cap]
   int32_t* h_out_len = nullptr; // pinned [n_sessions]
   double flushes = 0, blocks = 0;
+  // send half (ChunkedModulator per session, src/webaudio/chunked-modulator.ts): queued payloads, the modulated
+  // signal of every session and how much of it has been handed out
+  std::vector<std::vector<uint8_t>> tx_queued;
+  std::vector<char> tx_has_queued;
+  std::vector<std::vector<float>> tx_signal;
+  std::vector<long> tx_pos;
 };
 
 extern "C" int wam_fsk_mux_destroy(wam_fsk_mux* m) {
@@ -1790,6 +1796,92 @@ extern "C" int wam_fsk_mux_flush(wam_fsk_mux* m, uint8_t* out, long out_stride, 
   }
   m->flushes += 1;
   return WAM_OK;
+}
+
+// ---- send half of the session multiplexer: ChunkedModulator (src/webaudio/chunked-modulator.ts:31-87) per session,
+// with the modulateData() calls of all sessions that queued a payload run as ONE batched modulate.
+extern "C" int wam_fsk_mux_send(wam_fsk_mux* m, long session, const uint8_t* data, long n) {
+  if (!m || session < 0 || session >= m->n_sessions || n < 0 || (n > 0 && !data)) return fail(WAM_E_INVALID, "bad argument");
+  if (m->tx_queued.empty()) {
+    m->tx_queued.resize((size_t)m->n_sessions); m->tx_has_queued.assign((size_t)m->n_sessions, 0);
+    m->tx_signal.resize((size_t)m->n_sessions); m->tx_pos.assign((size_t)m->n_sessions, 0);
+  }
+  if (n == 0) {  // startModulation(empty) resets (chunked-modulator.ts:32-35)
+    m->tx_has_queued[(size_t)session] = 0;
+    m->tx_signal[(size_t)session].clear();
+    m->tx_pos[(size_t)session] = 0;
+    return WAM_OK;
+  }
+  m->tx_queued[(size_t)session].assign(data, data + n);
+  m->tx_has_queued[(size_t)session] = 1;
+  return WAM_OK;
+}
+
+// modulateData() for every session with a queued payload, one batched GPU call; their signals replace whatever those
+// sessions were still sending (startModulation overwrites pendingSignal, chunked-modulator.ts:37-38).
+extern "C" int wam_fsk_mux_modulate(wam_fsk_mux* m) {
+  if (!m) return fail(WAM_E_INVALID, "mux is NULL");
+  if (m->tx_queued.empty()) return WAM_OK;
+  std::vector<long> who;
+  long nbytes = 0;
+  for (long s = 0; s < m->n_sessions; s++)
+    if (m->tx_has_queued[(size_t)s]) { who.push_back(s); nbytes = std::max<long>(nbytes, (long)m->tx_queued[(size_t)s].size()); }
+  if (who.empty()) return WAM_OK;
+  if (m->b->groups.size() != 1) return fail(WAM_E_UNSUPPORTED, "the mux's send half supports one configuration per mux");
+  // the batch modulates n_sessions rows: sessions without a payload get a zero-length row whose output is ignored
+  const long n = m->n_sessions;
+  std::vector<uint8_t> data((size_t)n * (size_t)nbytes, 0);
+  std::vector<int32_t> len((size_t)n, 0), out_len((size_t)n, 0);
+  for (long s : who) {
+    const auto& q = m->tx_queued[(size_t)s];
+    memcpy(data.data() + (size_t)s * (size_t)nbytes, q.data(), q.size());
+    len[(size_t)s] = (int32_t)q.size();
+  }
+  const long total = modulate_size(m->b->groups[0].d, nbytes);
+  std::vector<float> out((size_t)n * (size_t)total);
+  int rc = wam_fsk_batch_modulate(m->b, data.data(), nbytes, len.data(), nbytes, out.data(), total, out_len.data());
+  if (rc != WAM_OK) return rc;
+  for (long s : who) {
+    const float* row = out.data() + (size_t)s * (size_t)total;
+    m->tx_signal[(size_t)s].assign(row, row + out_len[(size_t)s]);
+    m->tx_pos[(size_t)s] = 0;
+    m->tx_has_queued[(size_t)s] = 0;
+  }
+  return WAM_OK;
+}
+
+extern "C" int wam_fsk_mux_is_modulating(wam_fsk_mux* m, long session) {
+  if (!m || session < 0 || session >= m->n_sessions) return fail(WAM_E_INVALID, "bad argument");
+  return (!m->tx_signal.empty() && !m->tx_signal[(size_t)session].empty()) ? 1 : 0;
+}
+
+// getNextSamples(sampleCount) (chunked-modulator.ts:41-81).  Returns 1 and fills res / out when the session is
+// sending, 0 when it is not (the reference returns null), negative on error.
+extern "C" int wam_fsk_mux_pull(wam_fsk_mux* m, long session, float* out, long sample_count, wam_chunk_result* res) {
+  if (!m || session < 0 || session >= m->n_sessions || sample_count < 0 || !res || (sample_count > 0 && !out))
+    return fail(WAM_E_INVALID, "bad argument");
+  memset(res, 0, sizeof(*res));
+  if (m->tx_signal.empty()) return 0;
+  auto& sig = m->tx_signal[(size_t)session];
+  long& pos = m->tx_pos[(size_t)session];
+  if (sig.empty()) return 0;
+  const long remaining = (long)sig.size() - pos;
+  if (remaining <= 0) return 0;
+  const long k = std::min(sample_count, remaining);
+  if (k > 0) memcpy(out, sig.data() + pos, sizeof(float) * (size_t)k);
+  pos += k;
+  res->samples = k;
+  res->totalSamples = (long)sig.size();
+  if (pos >= (long)sig.size()) {
+    res->isComplete = 1;
+    res->samplesConsumed = (long)sig.size();
+    sig.clear();
+    pos = 0;
+  } else {
+    res->isComplete = 0;
+    res->samplesConsumed = pos;
+  }
+  return 1;
 }
 
 extern "C" int wam_host_alloc(void** p, size_t bytes) {

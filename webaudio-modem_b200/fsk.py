@@ -336,6 +336,51 @@ class FSKBatch:
         return [_status_dict(st[i]) for i in range(self.n_streams)]
 
 
+class ChunkedModulator:
+    """Mirror of src/webaudio/chunked-modulator.ts: modulates once, hands the signal out in slices."""
+
+    def __init__(self, modulator):
+        self.modulator = modulator
+        self._signal = None
+        self._pos = 0
+
+    def startModulation(self, data):
+        data = bytes(data)
+        if not len(data):
+            self._reset()
+            return
+        self._signal = self.modulator.modulateData(data)
+        self._pos = 0
+
+    def getNextSamples(self, sampleCount: int):
+        if self._signal is None:
+            return None
+        remaining = len(self._signal) - self._pos
+        if remaining <= 0:
+            return None
+        k = min(sampleCount, remaining)
+        signal = self._signal[self._pos:self._pos + k].copy()
+        self._pos += k
+        if self._pos >= len(self._signal):
+            total = len(self._signal)
+            self._reset()
+            return dict(signal=signal, isComplete=True, samplesConsumed=total, totalSamples=total)
+        return dict(signal=signal, isComplete=False, samplesConsumed=self._pos, totalSamples=len(self._signal))
+
+    def isModulating(self) -> bool:
+        return self._signal is not None
+
+    def getProgress(self) -> float:
+        return self._pos / len(self._signal) if self._signal is not None else 0.0
+
+    def cancel(self):
+        self._reset()
+
+    def _reset(self):
+        self._signal = None
+        self._pos = 0
+
+
 class FSKSessionMux:
     """Host adapter for many concurrent block-wise callers (wam_fsk_mux_*): every session pushes its render quanta
     (FSKProcessor.process() delivers 128 samples per call, fsk-processor.ts:152-167), one flush() runs a single ragged
@@ -392,6 +437,29 @@ class FSKSessionMux:
         """flush() without building Python objects: (out uint8 [n_sessions, cap], out_len int32 [n_sessions]) views."""
         L.check(self._lib.wam_fsk_mux_flush(self._h, self._out.ctypes.data, self._cap, self._out_len.ctypes.data))
         return self._out, self._out_len
+
+    # -- send half: one ChunkedModulator per session (src/webaudio/chunked-modulator.ts:31-87) -----------
+    def send(self, session: int, data):
+        """startModulation(data) for one session; the signal exists after the next modulate()."""
+        a = np.frombuffer(bytes(data), dtype=np.uint8)
+        L.check(self._lib.wam_fsk_mux_send(self._h, session, a.ctypes.data if len(a) else None, len(a)))
+
+    def modulate(self):
+        """modulateData() of every session that queued a payload, one batched GPU call."""
+        L.check(self._lib.wam_fsk_mux_modulate(self._h))
+
+    def is_modulating(self, session: int) -> bool:
+        return bool(L.check(self._lib.wam_fsk_mux_is_modulating(self._h, session)))
+
+    def pull(self, session: int, sample_count: int = 128):
+        """getNextSamples(sampleCount): dict(signal, isComplete, samplesConsumed, totalSamples) or None."""
+        out = np.zeros(max(sample_count, 1), dtype=np.float32)
+        res = L.ChunkResult()
+        rc = L.check(self._lib.wam_fsk_mux_pull(self._h, session, out.ctypes.data, sample_count, C.byref(res)))
+        if rc == 0:
+            return None
+        return dict(signal=out[:res.samples].copy(), isComplete=bool(res.isComplete), samplesConsumed=int(res.samplesConsumed),
+                    totalSamples=int(res.totalSamples))
 
     def status(self) -> list[dict]:
         st = (L.StatusStruct * self.n_sessions)()
