@@ -86,6 +86,9 @@ def ncu_traffic_bytes():
         return None, 0, f"no committed ncu traffic ({e.__class__.__name__})"
 
 
+PCM_FULL_SCALE = 32.0  # config 2 as 16-bit PCM: +-32 spans the -15 dB streams' noise peaks
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -293,6 +296,10 @@ class Ctx:
         self.wam = importlib.import_module("webaudio-modem_b200")
         self.L = importlib.import_module("webaudio-modem_b200._lib")
         self.lib = self.wam.lib()
+        # host threads and the staging buffers they allocate live next to this rank's GPU (NUMA); the CPU legs put
+        # the full mask back (all_cpus)
+        self.all_cpus = os.sched_getaffinity(0)
+        self.near_cpus = 0 if args.no_affinity else int(self.lib.wam_host_bind_near_device(self.local_rank))
         self.stream = torch.cuda.current_stream()
         self.sp = self.stream.cuda_stream
         self.peak, self.peak_src = measured_peak_gbs()
@@ -437,7 +444,52 @@ def run_config2(c: Ctx):
         e2e = {"value": samples_per_step * e2e_steps / dt / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": int(S * N_SAMPLES * 4), "d2h_bytes_per_step": int(S * cap + S * 4),
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
-               "api": "wam_fsk_batch_demodulate (host buffers, pinned)"}
+               "api": "wam_fsk_batch_demodulate (host buffers, pinned)",
+               "host_cpus_near_gpu": c.near_cpus}
+
+        # ---- the same streams as 16-bit PCM (full scale = +-32 so that the -15 dB noise fits): half the PCIe bytes.
+        # Checked against a device-resident float64 run on the identical widened samples.
+        x = torch.empty((S, N_SAMPLES), dtype=torch.float32, device=c.dev)
+        x.copy_(hx)
+        x.mul_(32768.0 / PCM_FULL_SCALE).round_().clamp_(-32768.0, 32767.0)
+        d_pcm = x.to(torch.int16)
+        hp = hx.view(torch.int16).view(-1)[: S * N_SAMPLES].view(S, N_SAMPLES)  # reuse the pinned pages
+        hp.copy_(d_pcm)
+        x.copy_(d_pcm)
+        x.mul_(1.0 / 32768.0)
+        del d_pcm
+        batch.renew(sp)
+        demod(L.WAM_BATCH_EXACT_ONLY)
+        torch.cuda.synchronize()
+        pcm_len = d_len.cpu().numpy().copy()
+        pcm_out = d_out.cpu().numpy().copy()
+        del x
+
+        def pcm_step():
+            batch.renew(0)
+            rc = c.lib.wam_fsk_batch_demodulate_pcm16(batch._h, hp.data_ptr(), N_SAMPLES, N_SAMPLES, h_out.data_ptr(), cap,
+                                                      h_len.data_ptr(), 0)
+            if rc != 0:
+                raise RuntimeError(c.lib.wam_last_error().decode())
+
+        pcm_step()
+        c.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            pcm_step()
+        torch.cuda.synchronize()
+        dt = c.max_over_ranks(time.perf_counter() - t0)
+        ho, hl = h_out.numpy(), h_len.numpy()
+        pcm_same = bool((hl == pcm_len).all()) and all(
+            bytes(ho[i, : hl[i]]) == bytes(pcm_out[i, : pcm_len[i]]) for i in range(S))
+        parity["e2e_pcm16_equals_device_run_on_widened_samples"] = {"identical": bool(pcm_same), "streams": S,
+                                                                   "decoded_bytes": int(pcm_len.sum())}
+        parity_ok = parity_ok and pcm_same
+        e2e["pcm16"] = {"value": samples_per_step * e2e_steps / dt / 1e6, "unit": "Msamples/s",
+                        "h2d_bytes_per_step": int(S * N_SAMPLES * 2), "d2h_bytes_per_step": int(S * cap + S * 4),
+                        "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+                        "api": "wam_fsk_batch_demodulate_pcm16 (int16 host buffers, pinned; sample = pcm / 32768)",
+                        "pcm_full_scale": PCM_FULL_SCALE}
 
     if c.rank != 0:
         return c.finish(None, parity_ok)
@@ -480,6 +532,7 @@ def run_config2(c: Ctx):
         "parity": parity,
     }
     if not args.no_cpu:
+        os.sched_setaffinity(0, c.all_cpus)
         cores = host_cores()
         n_cpu = ORACLE_SAMPLE_STREAMS if not args.quick else 512
         total, times, bits = cpu_reference_run(n_cpu, 1, 0, cores, seed=1)
@@ -637,6 +690,7 @@ def run_long(c: Ctx, which: int):
         kept_x, kept_bytes = passes[0][2], passes[0][3]
         xs = np.concatenate(kept_x, axis=1)
         t0 = time.perf_counter()
+        os.sched_setaffinity(0, c.all_cpus)
         cores = host_cores()
         # one oracle batch per kept slab is not possible (state carries): run stream by stream over the concatenation
         res, _ = O.batch_demodulate([wam.normalize_config(cfg)], None, np.ascontiguousarray(xs), n_threads=cores, want_status=False)
@@ -788,6 +842,7 @@ def run_config5(c: Ctx):
         sub = min(10_000 if not args.quick else 1024, chunk)
         pick = np.linspace(0, chunk - 1, sub).astype(np.int64)  # all SNR levels
         xs = x[torch.from_numpy(pick).to(c.dev)].cpu().numpy()
+        os.sched_setaffinity(0, c.all_cpus)
         cores = host_cores()
         t0 = time.perf_counter()
         want, _ = O.batch_demodulate([wam.normalize_config(cfg)], None, xs, n_threads=cores, want_status=False)
@@ -860,6 +915,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="configs 3-5: fraction of the duration / packet count")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-affinity", action="store_true", help="leave the ranks' CPU affinity alone")
     ap.add_argument("--demod-flags", type=int, default=0, help="A/B experiments: WAM_BATCH_* flags for the timed calls (128 = float64 kernels only)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--quick", action="store_true", help="smaller oracle samples (experiments)")

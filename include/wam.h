@@ -153,6 +153,11 @@ int wam_fsk_batch_demodulate(wam_fsk_batch* b, float* samples, long stream_strid
 int wam_fsk_batch_demodulate_device(wam_fsk_batch* b, float* d_samples, long stream_stride, long n_samples,
                                     uint8_t* d_out, long out_stride, int32_t* d_out_len, float* d_tap,
                                     void* cuda_stream, uint32_t flags);
+/* As wam_fsk_batch_demodulate, the samples arriving as 16-bit PCM: int16 [n_streams][stream_stride],
+ * sample = pcm / 32768 (exact in float32), i.e. demodulateData(Float32Array.from(pcm, v => v / 32768)).
+ * Half the host->device bytes of the float32 entry; the widening runs on the device. */
+int wam_fsk_batch_demodulate_pcm16(wam_fsk_batch* b, const int16_t* samples, long stream_stride, long n_samples,
+                                   uint8_t* out, long out_stride, int32_t* out_len, uint32_t flags);
 /* Ragged batch: stream s receives demodulateData(samples[s][0 .. n_valid[s])) with 0 <= n_valid[s] <= n_samples;
  * n_valid[s] < 0 means demodulateData() is NOT called on stream s in this round (state and counters untouched,
  * out_len[s] = 0).  This is the entry point of a server that multiplexes many independent audio sessions, each
@@ -326,6 +331,10 @@ int wam_fir_process_batch(int device, const double* taps, int ntaps, const float
 int wam_debug_fastmath(int device, const double* y, const double* x, long n, double* out_atan2,
                        double* out_sqrt, double* out_rcp);
 
+/* Pins the calling thread to the CPUs local to `device` (sysfs local_cpulist of its PCIe address): staging buffers
+ * allocated and first touched afterwards are NUMA-local to the GPU.  Returns the CPU count of the new mask, 0 when the
+ * topology is not exposed or not allowed (nothing changed), negative on a CUDA error. */
+int wam_host_bind_near_device(int device);
 /* pinned host memory helpers (so the HOST-buffer entry points can overlap copies) */
 int wam_host_alloc(void** p, size_t bytes);
 int wam_host_free(void* p);

@@ -460,3 +460,45 @@ def test_dynamic_time_slabs_equal_one_pass_and_oracle(gpu_wam, oracle):
     bad = [i for i in range(n_streams) if got["slabs"][i] != want[i]]
     assert not bad, f"{len(bad)} streams differ, first {bad[:5]}"
     assert sum(len(w) for w in want) > 0
+
+
+@pytest.mark.parametrize("n", [16000, 16000 - 13])
+def test_pcm16_entry_equals_widened_float_samples(gpu_wam, oracle, n):
+    """wam_fsk_batch_demodulate_pcm16: int16 / 32768 widened on the device = demodulateData(Float32Array of pcm / 32768),
+    bytes and counters exact against the oracle (row lengths with and without 16-byte rows)."""
+    cfg = {}
+    n_streams = 96
+    snr = np.repeat(np.arange(-12, 36, 3), n_streams // 16)
+    x, _ = siggen.noisy_streams(cfg, n_streams, 16000, 30, snr, seed=0x9C)
+    x = x[:, :n]
+    pcm = np.clip(np.round(x * (32768.0 / 8.0)), -32768, 32767).astype(np.int16)
+    widened = (pcm.astype(np.float32) / np.float32(32768.0)).astype(np.float32)
+    want, ost = oracle.batch_demodulate([cfg], None, widened.copy(), n_threads=8)
+    b = gpu_wam.FSKBatch(n_streams, cfg)
+    out, out_len = b.demodulate_pcm16(np.ascontiguousarray(pcm))
+    got = [bytes(out[i, : out_len[i]]) for i in range(n_streams)]
+    assert got == want
+    gst = b.status()
+    for i in range(n_streams):
+        assert_status_equal(gst[i], ost[i], f"stream {i}")
+    assert sum(len(w) for w in want) > 0
+    # a second call continues the streams exactly like a second demodulateData()
+    b2 = gpu_wam.FSKBatch(n_streams, cfg)
+    h = (n // 2) // 32 * 32
+    o1, l1 = b2.demodulate_pcm16(np.ascontiguousarray(pcm[:, :h]))
+    o2, l2 = b2.demodulate_pcm16(np.ascontiguousarray(pcm[:, h:]))
+    assert [bytes(o1[i, : l1[i]]) + bytes(o2[i, : l2[i]]) for i in range(n_streams)] == want
+
+
+def test_host_bind_near_device_keeps_a_usable_mask(gpu_wam):
+    import os
+    before = os.sched_getaffinity(0)
+    n = gpu_wam.lib().wam_host_bind_near_device(0)
+    after = os.sched_getaffinity(0)
+    try:
+        assert n >= 0
+        assert after <= before and len(after) > 0
+        if n > 0:
+            assert len(after) == n
+    finally:
+        os.sched_setaffinity(0, before)

@@ -13,6 +13,9 @@
 #include <new>
 #include <string>
 #include <vector>
+#include <sched.h>
+#include <cctype>
+#include <cstdlib>
 
 #include "crc_xmodem.cuh"
 #include "filters.cuh"
@@ -409,6 +412,8 @@ struct wam_fsk_batch {
   cudaStream_t streams[2] = {nullptr, nullptr};
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   float* stage_samples[2] = {nullptr, nullptr};
+  int16_t* stage_pcm[2] = {nullptr, nullptr};  // 16-bit PCM staging of wam_fsk_batch_demodulate_pcm16
+  size_t stage_pcm_bytes = 0;
   uint8_t* stage_out[2] = {nullptr, nullptr};
   int32_t* stage_len[2] = {nullptr, nullptr};
   size_t stage_samples_bytes = 0, stage_out_bytes = 0, stage_len_bytes = 0;
@@ -558,6 +563,7 @@ static void free_batch(wam_fsk_batch* b) {
     if (b->ev_copied[i]) cudaEventDestroy(b->ev_copied[i]);
     if (b->ev_consumed[i]) cudaEventDestroy(b->ev_consumed[i]);
     cudaFree(b->stage_samples[i]); cudaFree(b->stage_out[i]); cudaFree(b->stage_len[i]);
+    cudaFree(b->stage_pcm[i]);
   }
   cudaFree(b->phase_cycles);
   cudaFree(b->slab_done);
@@ -1001,11 +1007,47 @@ static int ensure(void** p, size_t* cur, size_t need) {
   return WAM_OK;
 }
 
+// 16-bit PCM -> float32, sample / 32768 (exact: every int16 / 2^15 is a float32).  Rows of `len` samples; strides in
+// elements; eight samples per thread where both rows allow 16-byte accesses.
+__global__ void pcm16_to_f32_kernel(const int16_t* __restrict__ in, long in_stride, float* __restrict__ out, long out_stride,
+                                    long n_rows, long len, int vec) {
+  constexpr float k = 1.0f / 32768.0f;
+  if (vec) {
+    const long per_row = len / 8;
+    const long total = n_rows * per_row;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+      const long r = i / per_row, c = (i - r * per_row) * 8;
+      const int4 v = __ldcs(reinterpret_cast<const int4*>(in + r * in_stride + c));
+      const int w[4] = {v.x, v.y, v.z, v.w};
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { f[2 * j] = (float)(short)(w[j] & 0xffff) * k; f[2 * j + 1] = (float)(w[j] >> 16) * k; }
+      float4* o = reinterpret_cast<float4*>(out + r * out_stride + c);
+      o[0] = make_float4(f[0], f[1], f[2], f[3]);
+      o[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    const long tail = len - per_row * 8;
+    if (tail > 0)
+      for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows * tail; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / tail, c = per_row * 8 + (i - r * tail);
+        out[r * out_stride + c] = (float)in[r * in_stride + c] * k;
+      }
+  } else {
+    const long total = n_rows * len;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+      const long r = i / len, c = i - r * len;
+      out[r * out_stride + c] = (float)in[r * in_stride + c] * k;
+    }
+  }
+}
+
+// `pcm` != nullptr: the samples arrive as 16-bit PCM (half the PCIe bytes) and are widened on the device.
 static int demodulate_host_impl(wam_fsk_batch* b, float* samples, long stream_stride, long n_samples,
                                 const int32_t* n_valid, bool ragged, uint8_t* out, long out_stride, int32_t* out_len,
-                                uint32_t flags) {
+                                uint32_t flags, const int16_t* pcm = nullptr) {
   if (!b) return fail(WAM_E_INVALID, "batch is NULL");
-  if (n_samples < 0 || stream_stride < n_samples || out_stride < 0 || !out_len || (!samples && n_samples > 0) ||
+  if (pcm && (flags & WAM_BATCH_WRITEBACK_AGC)) return fail(WAM_E_INVALID, "WAM_BATCH_WRITEBACK_AGC needs float32 samples");
+  if (n_samples < 0 || stream_stride < n_samples || out_stride < 0 || !out_len || (!samples && !pcm && n_samples > 0) ||
       (!out && out_stride > 0) || (ragged && !n_valid))
     return fail(WAM_E_INVALID, "bad buffer description");
   CUDA_TRY(cudaSetDevice(b->device));
@@ -1048,6 +1090,15 @@ static int demodulate_host_impl(wam_fsk_batch* b, float* samples, long stream_st
       if (rc != WAM_OK) { b->stage_samples_bytes = 0; return rc; }
     }
     b->stage_samples_bytes = cs;
+    if (pcm) {
+      size_t cp = b->stage_pcm_bytes;
+      for (int i = 0; i < 2; i++) {
+        cp = b->stage_pcm_bytes;
+        int rc = ensure((void**)&b->stage_pcm[i], &cp, need_s / 2);
+        if (rc != WAM_OK) { b->stage_pcm_bytes = 0; return rc; }
+      }
+      b->stage_pcm_bytes = cp;
+    }
     int rc = ensure((void**)&b->stage_out[0], &co, need_o);
     if (rc == WAM_OK) rc = ensure((void**)&b->stage_len[0], &cl, need_l);
     if (rc != WAM_OK) { b->stage_out_bytes = b->stage_len_bytes = 0; return rc; }
@@ -1067,7 +1118,19 @@ static int demodulate_host_impl(wam_fsk_batch* b, float* samples, long stream_st
   for (long t0 = 0; t0 < n_samples || (n_samples == 0 && nslab == 0); t0 += slab, k ^= 1, nslab++) {
     const long len = std::min(slab, n_samples - t0);
     if (nslab >= 2) CUDA_TRY(cudaStreamWaitEvent(copy_st, b->ev_consumed[k], 0));  // staging buffer k is free again
-    if (len > 0) {
+    if (len > 0 && pcm) {
+      // half the bytes over PCIe; the widening pass runs on the copy stream right behind its slab's copy
+      if (stream_stride == dstride && len == dstride)
+        CUDA_TRY(cudaMemcpyAsync(b->stage_pcm[k], pcm, sizeof(int16_t) * (size_t)dstride * (size_t)b->n_streams,
+                                 cudaMemcpyHostToDevice, copy_st));
+      else
+        CUDA_TRY(cudaMemcpy2DAsync(b->stage_pcm[k], sizeof(int16_t) * (size_t)dstride, pcm + t0,
+                                   sizeof(int16_t) * (size_t)stream_stride, sizeof(int16_t) * (size_t)len,
+                                   (size_t)b->n_streams, cudaMemcpyHostToDevice, copy_st));
+      const int vec = (dstride % 8 == 0) ? 1 : 0;
+      pcm16_to_f32_kernel<<<148 * 8, 256, 0, copy_st>>>(b->stage_pcm[k], dstride, b->stage_samples[k], dstride, b->n_streams, len, vec);
+      CUDA_TRY(cudaGetLastError());
+    } else if (len > 0) {
       if (stream_stride == dstride && len == dstride)
         CUDA_TRY(cudaMemcpyAsync(b->stage_samples[k], samples, sizeof(float) * (size_t)dstride * (size_t)b->n_streams,
                                  cudaMemcpyHostToDevice, copy_st));
@@ -1099,6 +1162,12 @@ static int demodulate_host_impl(wam_fsk_batch* b, float* samples, long stream_st
 extern "C" int wam_fsk_batch_demodulate(wam_fsk_batch* b, float* samples, long stream_stride, long n_samples,
                                         uint8_t* out, long out_stride, int32_t* out_len, uint32_t flags) {
   return demodulate_host_impl(b, samples, stream_stride, n_samples, nullptr, false, out, out_stride, out_len, flags);
+}
+
+extern "C" int wam_fsk_batch_demodulate_pcm16(wam_fsk_batch* b, const int16_t* samples, long stream_stride, long n_samples,
+                                              uint8_t* out, long out_stride, int32_t* out_len, uint32_t flags) {
+  if (!samples && n_samples > 0) return fail(WAM_E_INVALID, "samples is NULL");
+  return demodulate_host_impl(b, nullptr, stream_stride, n_samples, nullptr, false, out, out_stride, out_len, flags, samples);
 }
 
 extern "C" int wam_fsk_batch_demodulate_ragged(wam_fsk_batch* b, float* samples, long stream_stride, long n_samples,
@@ -1882,6 +1951,40 @@ extern "C" int wam_fsk_mux_pull(wam_fsk_mux* m, long session, float* out, long s
     res->samplesConsumed = pos;
   }
   return 1;
+}
+
+// Pin the calling thread to the CPUs next to `device` (its PCIe root's NUMA node, from sysfs), so that host staging
+// buffers allocated and filled afterwards are node-local and the H2D copies do not cross the socket interconnect.
+// Returns the number of CPUs in the new mask, 0 when the topology is not exposed (nothing changed).
+extern "C" int wam_host_bind_near_device(int device) {
+  char bus[32] = {0};
+  CUDA_TRY(cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), device));
+  for (char* c = bus; *c; ++c) *c = (char)tolower((unsigned char)*c);
+  const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return 0;
+  char line[4096] = {0};
+  const bool got = fgets(line, (int)sizeof(line), f) != nullptr;
+  fclose(f);
+  if (!got) return 0;
+  cpu_set_t want, have;
+  CPU_ZERO(&want);
+  if (sched_getaffinity(0, sizeof(have), &have) != 0) return 0;
+  int count = 0;
+  for (char* p = line; *p && *p != '\n';) {  // "0-31,64-95"
+    char* e = nullptr;
+    const long lo = strtol(p, &e, 10);
+    if (e == p) break;
+    long hi = lo;
+    p = e;
+    if (*p == '-') { hi = strtol(p + 1, &e, 10); p = e; }
+    for (long c = lo; c <= hi && c < CPU_SETSIZE; ++c)
+      if (c >= 0 && CPU_ISSET((int)c, &have)) { CPU_SET((int)c, &want); ++count; }
+    if (*p == ',') ++p;
+  }
+  if (count == 0) return 0;  // the process may not run there (cgroup mask): leave it alone
+  if (sched_setaffinity(0, sizeof(want), &want) != 0) return 0;
+  return count;
 }
 
 extern "C" int wam_host_alloc(void** p, size_t bytes) {

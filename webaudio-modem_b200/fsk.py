@@ -279,6 +279,19 @@ class FSKBatch:
             (L.WAM_BATCH_WRITEBACK_AGC if writeback_agc else 0) | flags))
         return out, out_len
 
+    def demodulate_pcm16(self, samples: np.ndarray, flags: int = 0):
+        """samples int16 [n_streams, n] (16-bit PCM, value / 32768); same result as demodulate(samples / 32768)."""
+        assert samples.dtype == np.int16 and samples.ndim == 2 and samples.shape[0] == self.n_streams
+        n = samples.shape[1]
+        assert n == 0 or samples.strides[1] == 2
+        cap = self.out_capacity(n)
+        out = np.zeros((self.n_streams, cap), dtype=np.uint8)
+        out_len = np.zeros(self.n_streams, dtype=np.int32)
+        L.check(self._lib.wam_fsk_batch_demodulate_pcm16(
+            self._h, samples.ctypes.data if n else None, max(samples.strides[0] // 2, n), n, out.ctypes.data, cap,
+            out_len.ctypes.data, flags))
+        return out, out_len
+
     def demodulate_ragged(self, samples: np.ndarray, n_valid, flags: int = 0) -> list[bytes]:
         """samples float32 [n_streams, n_max]; stream s receives demodulateData(samples[s, :n_valid[s]]), a negative
         n_valid[s] means the stream is not called in this round.  Returns the bytes completed per stream."""
