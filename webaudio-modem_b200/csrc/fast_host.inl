@@ -13,6 +13,10 @@
 //                 decision in float64.  State machine and bytes at the window's end equal to the fast pass'
 //                 checkpoint: the fast results stand (the usual outcome: a doubtful sample is wrong 1 time in 300).
 //                 Otherwise, or when a window cannot be formed, the stream joins the hard list;
+//                 A doubtful END-OF-DATA decision (an amplitude inside the doubt band of the silence threshold) is
+//                 checked in two stages, because the threshold itself is a float32 mean in the fast pass: a window
+//                 around the sync detection that set the threshold yields the float64 threshold, a window around the
+//                 doubtful decision then runs with that threshold and refuses compares closer than 1e-9 to it;
 //   4. hard list  those streams run through the float64 kernel over the whole call from the live state (checkpoint
 //                 0, untouched so far) and the rings (untouched too);
 //   5. epilogue   every other stream's last checkpoint becomes its live state, the histories' tails its rings.
@@ -28,6 +32,7 @@ struct FastGeom {
   int pa;            // prefix of the amplitude history, entries (amp_cap rounded up to 16)
   long bh_stride, ah_stride;
   int sync_slabs;    // window length, in slabs, that checks a doubtful sync decision
+  int e1_len, e2_len;  // two-stage check of a doubtful end-of-data decision: window lengths in slabs (0: not available)
   long out_stride;
   long sv_stride;    // samples per row of the verification scratch (kVerifyClasses slabs)
 };
@@ -41,7 +46,7 @@ struct FastCtx {  // what the small kernels below need, by value
   uint16_t* bit_hist; float* amp_hist;
   int32_t* slab_list; int32_t* slab_count;
   int32_t* hard_list; int32_t* hard_count; uint32_t* hard_mark;
-  int32_t* item_li; int32_t* item_slab; int32_t* item_count;
+  int32_t* item_li; int32_t* item_slab; int32_t* item_count; int32_t* item_res;
   double* sv_f64; uint32_t* sv_u32; uint32_t* sv_ring; float* sv_amp; float* sv_samples; uint8_t* sv_out; int32_t* sv_out_len;
   const float* samples; long stride;       // the call's sample buffer
   const int32_t* ids; int id0, row_base;
@@ -58,6 +63,19 @@ __device__ __forceinline__ const uint32_t* fc_ck_u32(const FastCtx& c, int k) {
 }
 __device__ __forceinline__ void fc_hard(const FastCtx& c, int li) {  // onto the hard list, once
   if (atomicExch(c.hard_mark + li, 1u) == 0u) c.hard_list[atomicAdd(c.hard_count, 1)] = li;
+}
+
+// Window of an item of class `cls` (v = its item_slab entry): first slab, length in slabs, checkpoint behind it.
+// Classes 0..kVerifyClasses-1: cls + 1 slabs ending with slab v.  kStageE1: e1_len slabs ending with slab v (the sync
+// detection that set the silence threshold; v = -1: none in this call, the entry is a placeholder), pushed forward
+// when it would start before the call.  kStageE2: e2_len slabs ending with slab v, likewise.
+__device__ __forceinline__ void fc_window(const FastCtx& c, int cls, int v, int& j0, int& wl, int& end) {
+  if (cls < kVerifyClasses) { j0 = v - cls; wl = cls + 1; end = v + 1; }
+  else if (cls == kStageE1) { wl = c.q.e1_len; j0 = max(v - wl + 1, 0); end = j0 + wl; }
+  else { wl = c.q.e2_len; end = max(v + 1, wl); j0 = end - wl; }
+}
+__device__ __forceinline__ int fc_count(const FastCtx& c, int cls) {  // both stages share one item count
+  return min(c.item_count[cls == kStageE2 ? kStageE1 : cls], kVerifyCap);
 }
 
 // (1) prologue: a block per stream
@@ -98,12 +116,45 @@ __global__ void fast_collect_kernel(const FastCtx c) {
       const int v = c.slab_list[(size_t)j * ns + e];
       const int li = v & 0xffffff;
       const uint32_t cause = (uint32_t)v >> 24;
-      bool hard = (cause & (WAM_FLAG_EOD | WAM_FLAG_RANGE)) != 0;
+      bool hard = (cause & WAM_FLAG_RANGE) != 0;
       // a short last slab has no window class of its own
       if (j == c.q.n_slabs - 1 && c.q.n != (long)c.q.n_slabs * c.q.slab_len) hard = true;
       const int want = (cause & WAM_FLAG_SYNC) ? c.q.sync_slabs : 2;
       if (want > kVerifyClasses) hard = true;
-      if (!hard) {
+      if (!hard && (cause & WAM_FLAG_EOD)) {
+        // two stages: the threshold's origin (last slab before the window in which a sync was detected), then the window
+        int j0, wl, e2;
+        fc_window(c, kStageE2, j, j0, wl, e2);
+        bool ok = c.q.e2_len >= want;
+        const uint32_t sd0 = fc_ck_u32(c, j0)[(size_t)U_SYNC_DET * ns + li];
+        ok = ok && fc_ck_u32(c, e2)[(size_t)U_SYNC_DET * ns + li] == sd0;  // no new threshold inside the window
+        int js = -1;
+        if (ok) {
+          uint32_t later = sd0;
+          for (int k = j0 - 1; k >= 0; --k) {
+            const uint32_t sd = fc_ck_u32(c, k)[(size_t)U_SYNC_DET * ns + li];
+            if (sd != later) { js = k; break; }
+            later = sd;
+          }
+          if (js >= 0) {
+            int s1, wl1, e1;
+            fc_window(c, kStageE1, js, s1, wl1, e1);
+            // the stage-1 window must end under the threshold that is in force in the stage-2 window
+            ok = fc_ck_u32(c, e1)[(size_t)U_SYNC_DET * ns + li] == sd0;
+          }
+        }
+        if (ok) {
+          const int slot = atomicAdd(c.item_count + kStageE1, 1);
+          if (slot < kVerifyCap) {
+            c.item_li[kStageE1 * kVerifyCap + slot] = li; c.item_slab[kStageE1 * kVerifyCap + slot] = js;
+            c.item_li[kStageE2 * kVerifyCap + slot] = li; c.item_slab[kStageE2 * kVerifyCap + slot] = j;
+          } else {
+            ok = false;
+            atomicAdd(c.hard_count + 3, 1);
+          }
+        }
+        if (!ok) hard = true;
+      } else if (!hard) {
         const int len = min(want, j + 1);  // windows are cut at the start of the call (checkpoint 0 is the exact state)
         const int slot = atomicAdd(c.item_count + (len - 1), 1);
         if (slot < kVerifyCap) {
@@ -114,6 +165,21 @@ __global__ void fast_collect_kernel(const FastCtx c) {
           atomicAdd(c.hard_count + 3, 1);
         }
       }
+      {
+        // A window cut at the start of the call trusts checkpoint 0.  Doubt carried over from the previous call (a
+        // running vote, a silent run or ring bits read in float32 whose samples are gone) cannot be checked any more:
+        // the stream is re-run in float64 from checkpoint 0 and the condition is put on record.
+        const int need = (cause & WAM_FLAG_EOD) ? c.q.e2_len : want;
+        if (j + 1 < need) {
+          const uint32_t* u0 = c.u32;
+          bool carried = false;
+          if (cause & (WAM_FLAG_VOTE_START | WAM_FLAG_VOTE_DATA | WAM_FLAG_VOTE_STOP)) carried = carried || u0[(size_t)U_DVOTE * ns + li] != 0u;
+          if (cause & WAM_FLAG_SYNC) carried = carried || u0[(size_t)U_DCNT * ns + li] != 0u;
+          if (cause & WAM_FLAG_EOD) carried = carried || (u0[(size_t)U_SILX * ns + li] >> 31) != 0u;
+          if (carried) { hard = true; atomicOr(c.u32 + (size_t)U_ERR * ns + li, WAM_ERR_CARRIED_DOUBT); }
+        }
+      }
+      if (hard) atomicOr(c.u32 + (size_t)U_FLAG_EVER * ns + li, cause);  // the statistics see the hard streams' causes too
       if (hard) fc_hard(c, li);
     }
   }
@@ -123,13 +189,13 @@ __global__ void fast_collect_kernel(const FastCtx c) {
 // cls * kVerifyCap + i.
 __global__ void fast_gather_kernel(const FastCtx c, int cls) {
   const int i = blockIdx.x;
-  if (i >= min(c.item_count[cls], kVerifyCap)) return;
+  if (i >= fc_count(c, cls)) return;
   const int ns = c.q.ns;
   const int li = c.item_li[cls * kVerifyCap + i];
-  const int j = c.item_slab[cls * kVerifyCap + i];
-  const int j0 = j - cls;  // first slab of the window = the checkpoint it starts from
+  int j0, wslabs, wend;  // first slab of the window = the checkpoint it starts from
+  fc_window(c, cls, c.item_slab[cls * kVerifyCap + i], j0, wslabs, wend);
   const size_t si = (size_t)cls * kVerifyCap + i;
-  const size_t nv = (size_t)kVerifyClasses * kVerifyCap;  // streams of the scratch batch
+  const size_t nv = (size_t)kAllClasses * kVerifyCap;  // streams of the scratch batch
   const double* f = fc_ck_f64(c, j0);
   const uint32_t* u = fc_ck_u32(c, j0);
   for (int k = threadIdx.x; k < F64_COUNT; k += blockDim.x) {
@@ -159,11 +225,17 @@ __global__ void fast_gather_kernel(const FastCtx c, int cls) {
     ar[slot] = ah[-1 - k];
   }
   // the window's samples
-  const long wlen = (long)(cls + 1) * c.q.slab_len;
+  const long wlen = (long)wslabs * c.q.slab_len;
   const float4* src = reinterpret_cast<const float4*>(c.samples + fc_row(c, li) * c.stride + (long)j0 * c.q.slab_len);
   float4* dst = reinterpret_cast<float4*>(c.sv_samples + si * c.q.sv_stride);
   for (long k = threadIdx.x; k < wlen / 4; k += blockDim.x) dst[k] = src[k];
   if (threadIdx.x == 0) c.sv_out_len[si] = 0;
+  if (cls == kStageE2) {
+    // the float64 silence threshold from stage 1 (its run and its check are ahead of this kernel on the same stream)
+    __syncthreads();
+    if (threadIdx.x == 0 && c.item_slab[kStageE1 * kVerifyCap + i] >= 0)
+      c.sv_f64[(size_t)F_SIL_THR * nv + si] = c.sv_f64[(size_t)F_SIL_THR * nv + (size_t)kStageE1 * kVerifyCap + i];
+  }
 }
 
 // (3c) compare: a warp per window.  The float64 run of the window must end in the state machine state of the fast
@@ -171,37 +243,45 @@ __global__ void fast_gather_kernel(const FastCtx c, int cls) {
 __global__ void fast_compare_kernel(const FastCtx c, int cls) {
   const int i = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x & 31;
-  if (i >= min(c.item_count[cls], kVerifyCap)) return;
+  if (i >= fc_count(c, cls)) return;
   const int ns = c.q.ns;
   const int li = c.item_li[cls * kVerifyCap + i];
-  const int j = c.item_slab[cls * kVerifyCap + i];
+  if (cls == kStageE1 && c.item_slab[cls * kVerifyCap + i] < 0) return;  // placeholder: the threshold predates the call
+  int j0, wslabs, wend;
+  fc_window(c, cls, c.item_slab[cls * kVerifyCap + i], j0, wslabs, wend);
   const size_t si = (size_t)cls * kVerifyCap + i;
-  const size_t nv = (size_t)kVerifyClasses * kVerifyCap;
-  const uint32_t* ue = fc_ck_u32(c, j + 1);   // fast pass, behind the window
-  const uint32_t* us = fc_ck_u32(c, j - cls); // fast pass, at the window's start
-  const double* fe = fc_ck_f64(c, j + 1);
+  const size_t nv = (size_t)kAllClasses * kVerifyCap;
+  const uint32_t* ue = fc_ck_u32(c, wend);  // fast pass, behind the window
+  const uint32_t* us = fc_ck_u32(c, j0);    // fast pass, at the window's start
+  const double* fe = fc_ck_f64(c, wend);
   bool same = true;
+  int why = 0;  // debug record: bit k = field k of the list differs, 16 threshold, 17 error flag, 18 byte count, 19 bytes
   if (lane == 0) {
     const int fields[] = {U_GSC, U_BSC, U_NEXT_IDX, U_BIT_ACC, U_BIT_CNT, U_STARTED, U_BITPOS, U_CURRENT, U_SIL_CNT,
                           U_SYNC_DET, U_EOD_EV, U_RING_POS, U_RING_LEN, U_AMP_POS, U_AMP_LEN, U_DSC};
-    for (int k : fields) same = same && c.sv_u32[(size_t)k * nv + si] == ue[(size_t)k * ns + li];
-    if (!ue[(size_t)U_STARTED * ns + li]) same = same && c.sv_u32[(size_t)U_GMOD * nv + si] == ue[(size_t)U_GMOD * ns + li];
+    int fi = 0;
+    for (int k : fields) { if (c.sv_u32[(size_t)k * nv + si] != ue[(size_t)k * ns + li]) why |= 1 << fi; ++fi; }
+    if (!ue[(size_t)U_STARTED * ns + li] && c.sv_u32[(size_t)U_GMOD * nv + si] != ue[(size_t)U_GMOD * ns + li])
+      why |= 1 << 20;  // (the check phase only exists while searching)
     // the silence threshold is a float32 mean in one run and a float64 mean in the other
     const double ta = c.sv_f64[(size_t)F_SIL_THR * nv + si], tb = fe[(size_t)F_SIL_THR * ns + li];
-    same = same && fabs(ta - tb) <= 1e-5 * fabs(tb);
-    same = same && (c.sv_u32[(size_t)U_ERR * nv + si] == 0u);
+    if (!(fabs(ta - tb) <= 1e-5 * fabs(tb))) why |= 1 << 16;
+    if (c.sv_u32[(size_t)U_ERR * nv + si] != 0u) why |= 1 << 17;
   }
   const int o0 = (int)us[(size_t)U_OUT_N * ns + li], o1 = (int)ue[(size_t)U_OUT_N * ns + li];
   const int nb = c.sv_out_len[si];
-  if (lane == 0) same = same && nb == o1 - o0;
-  same = __shfl_sync(0xffffffffu, same ? 1 : 0, 0) != 0;
+  if (lane == 0 && nb != o1 - o0) why |= 1 << 18;
+  why = __shfl_sync(0xffffffffu, why, 0);
+  same = why == 0;
   if (same) {
     const uint8_t* pa = c.sv_out + si * c.q.out_stride;
     const uint8_t* pb = c.out + fc_row(c, li) * c.q.out_stride + o0;
     bool eq = true;
     for (int k = lane; k < nb && o0 + k < c.q.out_stride; k += 32) eq = eq && pa[k] == pb[k];
     same = __all_sync(0xffffffffu, eq);
+    if (!same) why |= 1 << 19;
   }
+  if (lane == 0) c.item_res[si] = same ? 1 : (why | (1 << 30));
   if (lane == 0) {
     atomicAdd(c.hard_count + (same ? 1 : 2), 1);
     if (!same) fc_hard(c, li);
@@ -328,12 +408,13 @@ static int fast_prepare_buffers(wam_fsk_batch* b, Group& g, const FastGeom& q, c
   if ((rc = ensure((void**)&fb.slab_count, &fb.slab_count_bytes, sizeof(int32_t) * q.n_slabs)) != WAM_OK) return rc;
   if ((rc = ensure((void**)&fb.hard_list, &fb.hard_list_bytes, sizeof(int32_t) * ns)) != WAM_OK) return rc;
   if ((rc = ensure((void**)&fb.hard_mark, &fb.hard_mark_bytes, sizeof(uint32_t) * ns)) != WAM_OK) return rc;
-  const size_t nv = (size_t)kVerifyClasses * kVerifyCap;
+  const size_t nv = (size_t)kAllClasses * kVerifyCap;
   if (!fb.scratch_ready) {
     CUDA_TRY(cudaMalloc(&fb.hard_count, sizeof(int32_t) * 4));
     CUDA_TRY(cudaMalloc(&fb.item_li, sizeof(int32_t) * nv));
     CUDA_TRY(cudaMalloc(&fb.item_slab, sizeof(int32_t) * nv));
-    CUDA_TRY(cudaMalloc(&fb.item_count, sizeof(int32_t) * kVerifyClasses));
+    CUDA_TRY(cudaMalloc(&fb.item_res, sizeof(int32_t) * nv));
+    CUDA_TRY(cudaMalloc(&fb.item_count, sizeof(int32_t) * kAllClasses));
     CUDA_TRY(cudaMalloc(&fb.iota, sizeof(int32_t) * nv));
     std::vector<int32_t> h(nv);
     for (size_t i = 0; i < nv; i++) h[i] = (int32_t)i;
@@ -349,14 +430,14 @@ static int fast_prepare_buffers(wam_fsk_batch* b, Group& g, const FastGeom& q, c
   if ((rc = ensure((void**)&fb.sv_out, &fb.sv_out_bytes, nv * (size_t)std::max<long>(q.out_stride, 1))) != WAM_OK) return rc;
   CUDA_TRY(cudaMemsetAsync(fb.slab_count, 0, sizeof(int32_t) * q.n_slabs, st));
   CUDA_TRY(cudaMemsetAsync(fb.hard_count, 0, sizeof(int32_t) * 4, st));
-  CUDA_TRY(cudaMemsetAsync(fb.item_count, 0, sizeof(int32_t) * kVerifyClasses, st));
+  CUDA_TRY(cudaMemsetAsync(fb.item_count, 0, sizeof(int32_t) * kAllClasses, st));
   (void)b;
   return WAM_OK;
 }
 
 static int fast_streams(wam_fsk_batch* b) {
   if (!b->slab_streams[0]) {
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < kSlabStreams; i++) {
       CUDA_TRY(cudaStreamCreateWithFlags(&b->slab_streams[i], cudaStreamNonBlocking));
       CUDA_TRY(cudaEventCreateWithFlags(&b->slab_join[i], cudaEventDisableTiming));
     }
@@ -399,6 +480,14 @@ static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, c
     q.bh_stride = (long)round_up((size_t)q.ph + (size_t)(n / kTile), 8);
     q.ah_stride = (long)round_up((size_t)q.pa + (size_t)(n / 2), 4);
     q.sync_slabs = (int)((2L * g.d.total_bits + slab_len - 1) / slab_len) + 1;
+    {
+      // two-stage end-of-data check: amplitude ring + warm-up before the sync; silent run + one slab + warm-up
+      const int l1 = (int)((2L * g.d.amp_cap + slab_len - 1) / slab_len) + 2;
+      const int l2 = (int)((2L * g.d.eod_count + slab_len - 1) / slab_len) + 2;
+      const bool whole = n == (long)n_slabs * slab_len;
+      const bool ok = whole && l1 <= kVerifyClasses && l2 <= kVerifyClasses && l1 <= n_slabs && l2 <= n_slabs;
+      q.e1_len = ok ? l1 : 0; q.e2_len = ok ? l2 : 0;
+    }
     q.out_stride = a.out_stride;
     q.sv_stride = (long)kVerifyClasses * slab_len;
     rc = fast_prepare_buffers(b, g, q, st);
@@ -410,7 +499,7 @@ static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, c
     c.sync_ring = g.sync_ring; c.amp_ring = g.amp_ring; c.bit_hist = fb.bit_hist; c.amp_hist = fb.amp_hist;
     c.slab_list = fb.slab_list; c.slab_count = fb.slab_count;
     c.hard_list = fb.hard_list; c.hard_count = fb.hard_count; c.hard_mark = fb.hard_mark;
-    c.item_li = fb.item_li; c.item_slab = fb.item_slab; c.item_count = fb.item_count;
+    c.item_li = fb.item_li; c.item_slab = fb.item_slab; c.item_count = fb.item_count; c.item_res = fb.item_res;
     c.sv_f64 = fb.sv_f64; c.sv_u32 = fb.sv_u32; c.sv_ring = fb.sv_ring; c.sv_amp = fb.sv_amp;
     c.sv_samples = fb.sv_samples; c.sv_out = fb.sv_out; c.sv_out_len = fb.sv_out_len;
     c.samples = a.samples; c.stride = a.stride; c.ids = a.ids; c.id0 = a.id0; c.row_base = a.row_base;
@@ -479,25 +568,32 @@ static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, c
       Group& g = *lg[gi];
       FastCtx& c = ctx[gi];
       const FastGeom& q = c.q;
-      for (int cls = 0; cls < kVerifyClasses; cls++) {
-        if ((long)(cls + 1) * slab_len > n && cls > 0) continue;  // no window of the call is this long
-        cudaStream_t sv = b->slab_streams[gi * kVerifyClasses + cls];
-        CUDA_TRY(cudaStreamWaitEvent(sv, b->slab_fork, 0));
+      for (int cls = 0; cls < kAllClasses; cls++) {
+        if (cls < kVerifyClasses && (long)(cls + 1) * slab_len > n && cls > 0) continue;  // no window of the call is this long
+        if (cls >= kVerifyClasses && q.e2_len == 0) continue;
+        // the two stages follow one another on one stream
+        const int sidx = gi * (kVerifyClasses + 1) + std::min(cls, kVerifyClasses);
+        cudaStream_t sv = b->slab_streams[sidx];
+        if (cls != kStageE2) CUDA_TRY(cudaStreamWaitEvent(sv, b->slab_fork, 0));
         fast_gather_kernel<<<kVerifyCap, 128, 0, sv>>>(c, cls);
         DemodLaunch Lv;
         memset(&Lv, 0, sizeof(Lv));
         DemodArgs& a = Lv.g[0];
         a.d = g.d;
         a.ids = nullptr; a.id0 = 0; a.row_base = 0;
-        a.n_local = kVerifyClasses * kVerifyCap;
+        a.n_local = kAllClasses * kVerifyCap;
         a.f64 = g.fb.sv_f64; a.u32 = g.fb.sv_u32; a.sync_ring = g.fb.sv_ring; a.amp_ring = g.fb.sv_amp;
-        a.samples = g.fb.sv_samples; a.stride = q.sv_stride; a.n = (long)(cls + 1) * slab_len;
+        a.samples = g.fb.sv_samples; a.stride = q.sv_stride;
+        a.n = (long)(cls < kVerifyClasses ? cls + 1 : cls == kStageE1 ? q.e1_len : q.e2_len) * slab_len;
         a.out = g.fb.sv_out; a.out_stride = q.out_stride; a.out_len = g.fb.sv_out_len;
-        rc = launch_exact_selected(b, Lv, g.fb.iota + cls * kVerifyCap, g.fb.item_count + cls, kVerifyCap, a.n, sv);
+        a.thin_margin = cls == kStageE2 ? 1e-9 : 0.0;
+        rc = launch_exact_selected(b, Lv, g.fb.iota + cls * kVerifyCap, g.fb.item_count + (cls == kStageE2 ? kStageE1 : cls),
+                                   kVerifyCap, a.n, sv);
         if (rc != WAM_OK) return rc;
         fast_compare_kernel<<<kVerifyCap / 4, 128, 0, sv>>>(c, cls);
-        CUDA_TRY(cudaEventRecord(b->slab_join[gi * kVerifyClasses + cls], sv));
-        CUDA_TRY(cudaStreamWaitEvent(st, b->slab_join[gi * kVerifyClasses + cls], 0));
+        if (cls == kStageE1) continue;
+        CUDA_TRY(cudaEventRecord(b->slab_join[sidx], sv));
+        CUDA_TRY(cudaStreamWaitEvent(st, b->slab_join[sidx], 0));
       }
     }
     // whole-call float64 run of the hard lists, on the live state and rings

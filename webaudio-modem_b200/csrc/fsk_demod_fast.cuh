@@ -600,14 +600,15 @@ __device__ __forceinline__ int sm_tile_events_fast(FastB& b, uint32_t bits, uint
     if (thr_changed) {
       // new silence threshold: the flags of the rest of the tile from the amplitudes just stored
       const float* ar = amp_t;
-      uint32_t lo = 0u, hi = 0u;
+      uint32_t lo = 0u, hi = 0u, mid = 0u;
       for (int kk = k_evt + 1; kk < nk; ++kk) {
         const float av = ar[kk];
         lo |= (av < b.thr_lo ? 1u : 0u) << kk;
         hi |= (av < b.thr_hi ? 1u : 0u) << kk;
+        mid |= (av < b.sil_thr ? 1u : 0u) << kk;
       }
       const uint32_t keep = (2u << k_evt) - 1u;
-      silent = (silent & keep) | hi;
+      silent = (silent & keep) | (hi & ~(lo ^ hi)) | (mid & (lo ^ hi));
       adoubt = (adoubt & keep) | (lo ^ hi);
     }
     k = k_evt + 1;
@@ -769,6 +770,15 @@ __device__ __forceinline__ void fsk_demod_fast_body(const DemodLaunch& L, float 
     // sample 0 of the tile sits in bit 15 of each mask: turn them round
     bits = __brev(bits) >> 16; dmask = __brev(dmask) >> 16; slo = __brev(slo) >> 16; shi = __brev(shi) >> 16;
     uint32_t silent = shi, adoubt = slo ^ shi;
+    if (adoubt != 0u && active) {
+      // amplitudes inside the doubt band of the threshold (rare): our own reading is the plain float32 compare, so that
+      // the float64 check of a decision that hinges on one of them usually agrees
+      const float* ar = ah + t * (kTile / 2);
+      for (uint32_t m = adoubt; m != 0u; m &= m - 1u) {
+        const int k = __ffs((int)m) - 1;
+        if (!(ar[k] < b.sil_thr)) silent &= ~(1u << k);
+      }
+    }
     __syncwarp();  // every lane is done with the input tile
 
     // ---------------- B, with replay of A2 on resetState() ----------------
@@ -802,7 +812,7 @@ __device__ __forceinline__ void fsk_demod_fast_body(const DemodLaunch& L, float 
             bits |= (__float_as_uint(nf) >> 31) << k;
             dmask |= (__float_as_uint(dv) >> 31) << k;
             const uint32_t lo = __float_as_uint(am - b.thr_lo) >> 31, hi = __float_as_uint(am - b.thr_hi) >> 31;
-            silent |= hi << k;
+            silent |= (lo != hi ? (am < b.sil_thr ? 1u : 0u) : hi) << k;
             adoubt |= (lo ^ hi) << k;
           }
           redo = true;

@@ -344,6 +344,8 @@ static int derive(const wam_fsk_config& c, FskDerived& d) {
 // ------------------------------------------------------------------------------------------
 // Device buffers of the fast path, per configuration group (used by fast_host.inl).
 constexpr int kVerifyClasses = 4;    // verification windows of 1..4 time slabs
+constexpr int kStageE1 = kVerifyClasses, kStageE2 = kVerifyClasses + 1, kAllClasses = kVerifyClasses + 2;  // two-stage end-of-data check
+constexpr int kSlabStreams = 12;
 constexpr int kVerifyCap = 1024;     // windows per class and call; the excess is re-run over the whole call
 struct FastBuffers {
   // checkpoints 1..S of the per-stream state ([slab][field][stream]); checkpoint 0 is the live state
@@ -361,6 +363,7 @@ struct FastBuffers {
   uint32_t* hard_mark = nullptr; size_t hard_mark_bytes = 0;
   // verification scratch, per class c (window of c + 1 slabs): items, state, rings, samples, output
   int32_t* item_li = nullptr; int32_t* item_slab = nullptr; int32_t* item_count = nullptr; int32_t* iota = nullptr;
+  int32_t* item_res = nullptr;  // per window: 1 = the fast results stand, else 1 << 30 | bits naming what differed
   double* sv_f64 = nullptr; uint32_t* sv_u32 = nullptr; uint32_t* sv_ring = nullptr; float* sv_amp = nullptr;
   float* sv_samples = nullptr; size_t sv_samples_bytes = 0;
   uint8_t* sv_out = nullptr; size_t sv_out_bytes = 0;
@@ -420,8 +423,8 @@ struct wam_fsk_batch {
   long fast_calls = 0, fast_launches = 0;
   unsigned long long* phase_cycles = nullptr;  // debug: [max CTAs][4]
   // time slabs of the fused kernel: two streams whose launches overlap, fork / join events, per-CTA progress flags
-  cudaStream_t slab_streams[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t slab_fork = nullptr, slab_join[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t slab_streams[kSlabStreams] = {};
+  cudaEvent_t slab_fork = nullptr, slab_join[kSlabStreams] = {};
   int* slab_done = nullptr;
   size_t slab_done_bytes = 0;
   long phase_ctas = 0;
@@ -567,7 +570,7 @@ static void free_batch(wam_fsk_batch* b) {
   }
   cudaFree(b->phase_cycles);
   cudaFree(b->slab_done);
-  for (int i = 0; i < 8; i++) {
+  for (int i = 0; i < kSlabStreams; i++) {
     if (b->slab_streams[i]) cudaStreamDestroy(b->slab_streams[i]);
     if (b->slab_join[i]) cudaEventDestroy(b->slab_join[i]);
   }
@@ -1237,6 +1240,30 @@ extern "C" int wam_fsk_batch_fast_stats(wam_fsk_batch* b, wam_fast_stats* out) {
     }
   }
   return WAM_OK;
+}
+
+// Debug: the verification windows of the last fast call of configuration group `group`: per class c (0..3: windows
+// of c + 1 slabs, 4 / 5: the two stages of an end-of-data check) counts[c] items, and for item i of class c
+// items[(c * cap + i) * 3 + {0, 1, 2}] = stream (local index), slab, result (1 = confirmed, else 1 << 30 | what differed).
+// Returns cap (the per-class capacity), negative on error.
+extern "C" int wam_fsk_batch_debug_fast_windows(wam_fsk_batch* b, int group, int32_t* counts6, int32_t* items, long items_cap) {
+  if (!b || group < 0 || group >= (int)b->groups.size() || !counts6) return fail(WAM_E_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  FastBuffers& fb = b->groups[(size_t)group].fb;
+  for (int c = 0; c < kAllClasses; c++) counts6[c] = 0;
+  if (!fb.scratch_ready) return kVerifyCap;
+  CUDA_TRY(cudaMemcpy(counts6, fb.item_count, sizeof(int32_t) * kAllClasses, cudaMemcpyDeviceToHost));
+  counts6[kStageE2] = counts6[kStageE1];
+  const size_t nv = (size_t)kAllClasses * kVerifyCap;
+  if (items && items_cap >= (long)(nv * 3)) {
+    std::vector<int32_t> li(nv), sl(nv), rs(nv);
+    CUDA_TRY(cudaMemcpy(li.data(), fb.item_li, sizeof(int32_t) * nv, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(sl.data(), fb.item_slab, sizeof(int32_t) * nv, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(rs.data(), fb.item_res, sizeof(int32_t) * nv, cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < nv; k++) { items[3 * k] = li[k]; items[3 * k + 1] = sl[k]; items[3 * k + 2] = rs[k]; }
+  }
+  return kVerifyCap;
 }
 
 // Debug: enable (enable != 0) / read-and-clear per-phase SM cycle counters of the demodulator kernel.

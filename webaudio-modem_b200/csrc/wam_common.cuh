@@ -158,6 +158,7 @@ struct DemodArgs {
   unsigned long long* phase_cycles;  // debug (nullable): [CTA][4] SM cycles spent in A1, A2, B, staging/other
   // sub-selection (exact re-run of the streams the fast kernel flagged): local index j -> sel[j], and the number of
   // entries read from device memory (the host launches a grid for the worst case; surplus CTAs leave at once)
+  double thin_margin;    // > 0: flag silence compares closer than this (relative) to the threshold (WAM_ERR_THIN_COMPARE)
   const int32_t* sel;
   const int32_t* sel_count;
   // fast path
@@ -199,6 +200,8 @@ struct DemodLaunch {
 #define WAM_ERR_OUT_OVERFLOW 1u
 #define WAM_ERR_PIPE_TIMEOUT 2u
 #define WAM_ERR_SLAB_TIMEOUT 4u
+#define WAM_ERR_CARRIED_DOUBT 16u  // a doubtful decision depended on float32 readings of the previous call (see fast_host.inl)
+#define WAM_ERR_THIN_COMPARE 8u  // verification scratch only: an amplitude within thin_margin of the silence threshold
 
 // causes of a flagged (doubtful) decision in the fast kernel
 #define WAM_FLAG_VOTE_START 1u

@@ -279,6 +279,19 @@ class FSKBatch:
             (L.WAM_BATCH_WRITEBACK_AGC if writeback_agc else 0) | flags))
         return out, out_len
 
+    def debug_fast_windows(self, group: int = 0):
+        """Verification windows of the last fast call: list of dict(cls, stream, slab, result)."""
+        counts = np.zeros(6, dtype=np.int32)
+        cap = L.check(self._lib.wam_fsk_batch_debug_fast_windows(self._h, group, counts.ctypes.data, None, 0))
+        items = np.zeros(6 * cap * 3, dtype=np.int32)
+        L.check(self._lib.wam_fsk_batch_debug_fast_windows(self._h, group, counts.ctypes.data, items.ctypes.data, items.size))
+        out = []
+        for c in range(6):
+            for i in range(min(int(counts[c]), cap)):
+                k = (c * cap + i) * 3
+                out.append(dict(cls=c, stream=int(items[k]), slab=int(items[k + 1]), result=int(items[k + 2])))
+        return out
+
     def demodulate_pcm16(self, samples: np.ndarray, flags: int = 0):
         """samples int16 [n_streams, n] (16-bit PCM, value / 32768); same result as demodulate(samples / 32768)."""
         assert samples.dtype == np.int16 and samples.ndim == 2 and samples.shape[0] == self.n_streams
