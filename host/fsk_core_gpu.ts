@@ -10,18 +10,37 @@
 import { BaseModulator, type ModulationType, type SignalQuality } from '../src/core';
 import { DEFAULT_FSK_CONFIG, type FSKConfig } from '../src/modems/fsk';
 
+type Rows = { bytes: Uint8Array; lengths: Int32Array; stride: number };
+type Chunk = { signal: Float32Array; isComplete: boolean; samplesConsumed: number; totalSamples: number };
+
 // eslint-disable-next-line @typescript-eslint/no-var-requires
 const native = require('./build/Release/wam_napi.node') as {
+  // one stream (wam_fsk_*)
   fskCreate(device: number): object;
   fskConfigure(h: object, cfg: FSKConfig): void;
   fskModulate(h: object, data: Uint8Array): Promise<Float32Array>;
   fskDemodulate(h: object, samples: Float32Array): Promise<{ bytes: Uint8Array; eod: number }>;
   fskReset(h: object): void;
   fskStatus(h: object): Record<string, number | boolean>;
+  // batch (wam_fsk_batch_*); Int16Array samples take the 16-bit PCM entry (sample = pcm / 32768)
   batchCreate(device: number, nStreams: number, cfgs: FSKConfig[], cfgIndex?: Int32Array): object;
-  batchDemodulate(h: object, samples: Float32Array, nSamples: number): Promise<{ bytes: Uint8Array; lengths: Int32Array; stride: number }>;
-  batchModulate(h: object, data: Uint8Array, nBytes: number): Promise<{ samples: Float32Array; stride: number }>;
+  batchDemodulate(h: object, samples: Float32Array | Int16Array, nSamples: number): Promise<Rows>;
+  batchModulate(h: object, data: Uint8Array, nBytes: number, samplesPerRow: number, lengths?: Int32Array):
+    Promise<{ samples: Float32Array; lengths: Int32Array; stride: number }>;
+  batchStatus(h: object): Record<string, number | boolean>[];
   xmodemBatchCheck(device: number, bytes: Uint8Array, stride: number, lengths: Int32Array, expectedSeq?: Int32Array): Int32Array;
+  // session multiplexer (wam_fsk_mux_*): receive half and send half
+  muxCreate(device: number, nSessions: number, cfgs: FSKConfig[], cfgIndex: Int32Array | undefined, maxBlock: number): object;
+  muxPush(h: object, session: number, quantum: Float32Array): void;
+  muxFlush(h: object): Promise<Rows>;
+  muxSend(h: object, session: number, data: Uint8Array): void;
+  muxModulate(h: object): Promise<void>;
+  muxPull(h: object, session: number, sampleCount: number): Chunk | null;
+  // batched XModem receiver (wam_xmodem_batch_receive)
+  xmodemReceiverCreate(device: number, nSessions: number, maxRetries: number, maxDataBytes?: number): object;
+  xmodemReceiverFeed(h: object, bytes: Uint8Array, stride: number, lengths: Int32Array):
+    Promise<{ replies: Uint8Array; replyCounts: Int32Array; replyStride: number; consumed: Int32Array; done: Int32Array }>;
+  xmodemReceiverData(h: object, session: number): Uint8Array;
 };
 
 /** README-only names (README.md:33-38) accepted as aliases of the real FSKConfig fields. */
@@ -85,17 +104,30 @@ export class FSKCoreGPU extends BaseModulator<FSKConfig> {
 /** Batched entry point: thousands of independent streams with device-resident streaming state. */
 export class FSKBatchGPU {
   private readonly handle: object;
+  private readonly config: FSKConfig;
   constructor(readonly nStreams: number, configs: FSKConfigInput[] | FSKConfigInput, cfgIndex?: Int32Array, device = 0) {
     const list = (Array.isArray(configs) ? configs : [configs]).map((c) => ({ ...DEFAULT_FSK_CONFIG, ...c }) as FSKConfig);
+    if (list.length !== 1 && cfgIndex === undefined) throw new Error('cfgIndex is required with more than one configuration');
+    this.config = list[0]; // modulate() supports one configuration per batch
     this.handle = native.batchCreate(device, nStreams, list, cfgIndex);
   }
-  /** samples: [nStreams][nSamples] row-major; resolves to the bytes each stream completed in this call. */
-  async demodulate(samples: Float32Array, nSamples: number): Promise<Uint8Array[]> {
+  /** samples: [nStreams][nSamples] row-major (Float32Array, or Int16Array = 16-bit PCM, half the PCIe bytes);
+   *  resolves to the bytes each stream completed in this call. */
+  async demodulate(samples: Float32Array | Int16Array, nSamples: number): Promise<Uint8Array[]> {
     const { bytes, lengths, stride } = await native.batchDemodulate(this.handle, samples, nSamples);
     return Array.from(lengths, (n, s) => bytes.subarray(s * stride, s * stride + n));
   }
-  async modulate(data: Uint8Array, nBytes: number) {
-    return native.batchModulate(this.handle, data, nBytes);
+  /** data: [nStreams][nBytes] row-major, lengths[s] <= nBytes bytes used per stream; resolves to one signal per stream. */
+  async modulate(data: Uint8Array, nBytes: number, lengths?: Int32Array): Promise<Float32Array[]> {
+    const c = this.config;
+    const bitsPerByte = 8 + c.startBits + c.stopBits + (c.parity !== 'none' ? 1 : 0); // fsk.ts:384-386
+    const samplesPerBit = Math.floor(c.sampleRate / c.baudRate); // fsk.ts:97
+    const perRow = (c.preamblePattern.length + c.sfdPattern.length + nBytes) * bitsPerByte * samplesPerBit + samplesPerBit * 2; // fsk.ts:388-391
+    const r = await native.batchModulate(this.handle, data, nBytes, perRow, lengths);
+    return Array.from(r.lengths, (n, s) => r.samples.subarray(s * r.stride, s * r.stride + n));
+  }
+  getStatus() {
+    return native.batchStatus(this.handle);
   }
 }
 
@@ -118,6 +150,18 @@ export class FSKSessionMuxGPU {
     const { bytes, lengths, stride } = await native.muxFlush(this.handle);
     return Array.from(lengths, (n: number, s: number) => bytes.subarray(s * stride, s * stride + n));
   }
+  /** ChunkedModulator.startModulation(data) of one session (chunked-modulator.ts:31-39); the signal exists after modulate() */
+  send(session: number, data: Uint8Array): void {
+    native.muxSend(this.handle, session, data);
+  }
+  /** modulateData() of every session that queued a payload, as one batched GPU call (wam_fsk_mux_modulate) */
+  async modulate(): Promise<void> {
+    await native.muxModulate(this.handle);
+  }
+  /** ChunkedModulator.getNextSamples(sampleCount) (chunked-modulator.ts:41-81): the next slice, or null when idle */
+  pull(session: number, sampleCount = 128): Chunk | null {
+    return native.muxPull(this.handle, session, sampleCount);
+  }
 }
 
 /**
@@ -130,8 +174,19 @@ export class XModemBatchReceiverGPU {
   constructor(readonly nSessions: number, maxRetries = 10, device = 0) {
     this.handle = native.xmodemReceiverCreate(device, nSessions, maxRetries);
   }
-  async feed(bursts: Uint8Array[]): Promise<Uint8Array[]> {
-    return native.xmodemReceiverFeed(this.handle, bursts); // replies per session: 0x06 ACK / 0x15 NAK in order
+  /** bursts[s]: the bytes session s demodulated since the last call.  Resolves to the replies per session
+   *  (0x06 ACK / 0x15 NAK, in order), how many bytes of each burst were used, and the sessions' done flags. */
+  async feed(bursts: Uint8Array[]) {
+    const stride = Math.max(1, ...bursts.map((b) => b.length));
+    const bytes = new Uint8Array(stride * this.nSessions);
+    const lengths = Int32Array.from(bursts, (b) => b.length);
+    bursts.forEach((b, s) => bytes.set(b, s * stride));
+    const r = await native.xmodemReceiverFeed(this.handle, bytes, stride, lengths);
+    return {
+      replies: Array.from(r.replyCounts, (n, s) => r.replies.subarray(s * r.replyStride, s * r.replyStride + Math.min(n, r.replyStride))),
+      consumed: r.consumed,
+      done: r.done, // 0 running, 1 EOT received and ACKed, 2 failed after maxRetries
+    };
   }
   received(session: number): Uint8Array {
     return native.xmodemReceiverData(this.handle, session); // assembleData(receive.data), xmodem.ts:323-334

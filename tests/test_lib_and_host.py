@@ -100,3 +100,53 @@ def test_host_math_equals_oracle(wam, oracle):
         wam.XModemPacket.createData(1, bytes(256))
     with pytest.raises(ValueError, match="cannot be empty"):
         wam.IIRFilter([], [1])
+
+
+# ---- the boundary seen from C and from the Node side --------------------------------------------------------------
+def test_c_abi_layouts_match_the_ctypes_mirror(tmp_path):
+    """tests/c_abi_smoke.c (plain C over include/wam.h) prints every boundary struct's size and field offsets; the
+    ctypes structs in _lib.py must agree field by field."""
+    import ctypes as C
+    import importlib
+    import json
+    import subprocess
+
+    exe = tmp_path / "c_abi_smoke"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-o", str(exe), os.path.join(ROOT, "tests", "c_abi_smoke.c")],
+                   check=True)
+    layout = json.loads(subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout)
+    L = importlib.import_module("webaudio-modem_b200._lib")
+    mirror = {"wam_fsk_config": L.FSKConfigStruct, "wam_fsk_status": L.StatusStruct, "wam_pkt_result": L.PktResult,
+              "wam_xmodem_rx_state": L.XmodemRxState, "wam_chunk_result": L.ChunkResult, "wam_fast_stats": L.FastStats}
+    assert set(layout) == set(mirror)
+    for name, st in mirror.items():
+        want = layout[name]
+        assert C.sizeof(st) == want["size"], name
+        fields = {f[0]: getattr(st, f[0]).offset for f in st._fields_}
+        listed = {k: v for k, v in want.items() if k != "size"}
+        if listed:
+            assert fields == listed, name
+
+
+def test_napi_addon_is_valid_c_against_the_header_and_binds_what_the_ts_host_calls():
+    """host/wam_napi.c compiles (syntax + types, -Wall -Wextra -Werror) against include/wam.h and a stub node_api.h, and
+    registers every native that host/fsk_core_gpu.ts declares or calls."""
+    import re
+    import subprocess
+
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "tests", "stubs"),
+                    os.path.join(ROOT, "host", "wam_napi.c")], check=True)
+    c_src = open(os.path.join(ROOT, "host", "wam_napi.c")).read()
+    ts_src = open(os.path.join(ROOT, "host", "fsk_core_gpu.ts")).read()
+    registered = set(re.findall(r'\{"(\w+)", NULL, \w+, NULL', c_src))
+    called = set(re.findall(r"native\.(\w+)\(", ts_src))
+    block = ts_src[ts_src.index("const native = require"):ts_src.index("};", ts_src.index("const native = require"))]
+    declared = set(re.findall(r"^\s{2}(\w+)\(", block, flags=re.M))
+    assert called and called <= declared, called - declared
+    assert declared <= registered, declared - registered
+    assert registered <= declared, registered - declared
+    # every libwam function the addon calls is declared in the header
+    header = open(os.path.join(ROOT, "include", "wam.h")).read()
+    for fn in set(re.findall(r"\b(wam_\w+)\(", c_src)):
+        assert re.search(r"\b%s\(" % fn, header), fn
+    assert os.path.exists(os.path.join(ROOT, "host", "alias-hook.mjs")) and os.path.exists(os.path.join(ROOT, "host", "alias-hook-impl.mjs"))
