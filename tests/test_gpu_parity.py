@@ -502,3 +502,32 @@ def test_host_bind_near_device_keeps_a_usable_mask(gpu_wam):
             assert len(after) == n
     finally:
         os.sched_setaffinity(0, before)
+
+
+@pytest.mark.parametrize("start_bits,stop_bits", [(5, 4), (16, 16), (3, 1)])
+def test_wide_framing_long_frames(gpu_wam, oracle, start_bits, stop_bits):
+    """startBits + stopBits > 2 (bits per byte 17 and 40): line bits of bytes beyond 240 of a frame (the modulator's
+    bit-index division), and a demodulator that completes a byte every stop_pos + 1 decided bits whatever the framing
+    says, so that the output capacity must not be sized by bits per byte."""
+    cfg = dict(baudRate=1200, startBits=start_bits, stopBits=stop_bits)
+    payload = bytes((i * 37 + 11) & 0xFF for i in range(300))
+    want = siggen.modulate(cfg, payload)
+    m = gpu_wam.FSKCore()
+    m.configure(cfg)
+    got = m.modulateData(payload)
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=0, atol=TOL)
+    # batch modulator (bit table kernel + sample kernel, other chunk size) on the same frame
+    b = gpu_wam.FSKBatch(3, cfg)
+    sig, out_len = b.modulate(np.frombuffer(payload, dtype=np.uint8)[None, :].repeat(3, axis=0))
+    assert out_len.tolist() == [len(want)] * 3
+    np.testing.assert_allclose(sig[1], want, rtol=0, atol=TOL)
+    # demodulated bytes and counters equal to the reference algorithm's on the same samples
+    x = np.concatenate([want, np.zeros(4000, dtype=np.float32)]).astype(np.float32)
+    exp, ost = oracle.batch_demodulate([cfg], None, x[None, :].copy(), n_threads=1)
+    rx = gpu_wam.FSKBatch(1, cfg)
+    out = rx.demodulate_bytes(x[None, :].copy())
+    assert out[0] == exp[0]
+    st = rx.status()[0]
+    assert_status_equal(st, ost[0], "wide framing")
+    assert st["errorEvents"] == 0

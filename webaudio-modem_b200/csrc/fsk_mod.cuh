@@ -97,7 +97,9 @@ __device__ __forceinline__ void bit_phase_fill(const ModArgs& a, int s, uint32_t
   const int total = d.n_preamble + d.n_sfd + nbytes;
   const uint8_t* row = a.data + (long)s * a.data_stride;
   const double spb_d = (double)d.spb, inv_fs = 1.0 / d.fs;
-  const uint32_t bpb_magic = 65536u / (uint32_t)d.bpb + 1u;  // i / bpb for i < 65536 / bpb
+  // i / bpb as a multiply-high: magic = ceil(2^32 / bpb) is exact while i * (magic * bpb - 2^32) < 2^32, i.e. for every
+  // i < 2^32 / bpb — the line bits of a chunk number NT * bpb at most
+  const uint32_t bpb_magic = (uint32_t)((0x100000000ull + (uint32_t)d.bpb - 1u) / (uint32_t)d.bpb);
   uint32_t carry = 0;
   for (int base = 0; base < total; base += NT) {
     const int k = base + tid;
@@ -123,7 +125,7 @@ __device__ __forceinline__ void bit_phase_fill(const ModArgs& a, int s, uint32_t
     __syncthreads();
     const int nb = min(NT, total - base);
     for (int i = tid; i < nb * d.bpb; i += NT) {
-      const int kk = (int)(((uint32_t)i * bpb_magic) >> 16);
+      const int kk = (int)__umulhi((uint32_t)i, bpb_magic);
       const int b = i - kk * d.bpb;
       const int by = s_byte[kk];
       const int marks = (int)s_pre[kk] + framed_ones_before(d, by, b);

@@ -722,8 +722,10 @@ extern "C" long wam_fsk_batch_out_capacity(wam_fsk_batch* b, long n_samples) {
   long cap = 0;
   for (auto& g : b->groups) {
     if (g.ids.empty()) continue;
-    // a byte needs at least (bpb - 1) * dspb + 1 decimated samples = 2x input samples
-    const long per = 2L * ((long)(g.d.bpb - 1) * g.d.dspb + 1);
+    // processByte completes a byte every stop_pos + 1 decided bits whatever startBits / stopBits say (fsk.ts:346-375),
+    // i.e. after at least (min(bpb, stop_pos + 1) - 1) * dspb + 1 decimated samples = 2x input samples
+    const long bits = std::min<long>(g.d.bpb, g.d.stop_pos + 1);
+    const long per = 2L * ((bits - 1) * g.d.dspb + 1);
     cap = std::max(cap, n_samples / per + 2);
   }
   return (cap + 15) / 16 * 16;
@@ -1520,9 +1522,11 @@ extern "C" int wam_fsk_demodulate(wam_fsk* m, float* samples, long n, uint8_t* o
   if (!m->ready) return fail(WAM_E_NOT_CONFIGURED, "FSK demodulator not configured");
   *n_out = 0;
   CUDA_TRY(cudaSetDevice(m->device));
+  const long ocap = wam_fsk_batch_out_capacity(m->b, n);
+  // refused before a sample is consumed: afterwards the bytes could not be handed over and would be lost
+  if (cap < ocap || (!out && cap > 0)) return fail(WAM_E_CAPACITY, "output buffer smaller than wam_fsk_batch_out_capacity(n) bytes");
   m->demodulation_calls += 1;
   m->total_samples += (double)n;
-  const long ocap = wam_fsk_batch_out_capacity(m->b, n);
   if (m->h_samples_n < (size_t)n || !m->h_samples) {
     cudaFreeHost(m->h_samples); m->h_samples = nullptr;
     const size_t want = std::max<size_t>((size_t)n, 4096);
@@ -1874,8 +1878,10 @@ extern "C" int wam_fsk_mux_flush(wam_fsk_mux* m, uint8_t* out, long out_stride, 
     const int32_t p = m->h_pending[s];
     m->h_nvalid[s] = p > 0 ? p : -1;
     n_max = std::max<long>(n_max, p);
-    m->h_pending[s] = 0;
   }
+  // refused before the state advances; the pushed samples stay queued until a flush succeeds
+  if (n_max > 0 && out_stride < m->out_cap)
+    return fail(WAM_E_CAPACITY, "out_stride smaller than wam_fsk_mux_out_capacity()");
   if (n_max == 0) {
     memset(out_len, 0, sizeof(int32_t) * (size_t)m->n_sessions);
     return WAM_OK;
@@ -1885,8 +1891,8 @@ extern "C" int wam_fsk_mux_flush(wam_fsk_mux* m, uint8_t* out, long out_stride, 
                                 m->h_out, m->out_cap, m->h_out_len, 0);
   if (rc != WAM_OK) return rc;
   for (long s = 0; s < m->n_sessions; s++) {
+    m->h_pending[s] = 0;
     const int32_t n = m->h_out_len[s];
-    if (n > out_stride) return fail(WAM_E_CAPACITY, "out_stride smaller than the bytes a session produced");
     out_len[s] = n;
     if (n > 0) memcpy(out + (size_t)s * (size_t)out_stride, m->h_out + (size_t)s * (size_t)m->out_cap, (size_t)n);
   }
