@@ -330,6 +330,16 @@ int wam_iir_process_batch(int device, const double* b, int nb, const double* a, 
  * [n_streams][ntaps-1] most-recent-first input history, NULL = fresh. */
 int wam_fir_process_batch(int device, const double* taps, int ntaps, const float* in, float* out,
                           long stride, long n, long n_streams, double* state);
+/* The same with DEVICE buffers on the current device, asynchronous on cuda_stream (the measured entry points:
+ * bench_extra.py).  IIR: d_state (nullable) is read and written in place; d_scratch of wam_iir_scratch_bytes(n,
+ * n_streams) bytes holds the look-back records of the call.  FIR: d_taps in device memory; d_state (nullable) is updated
+ * through d_state_scratch (same size). */
+size_t wam_iir_scratch_bytes(long n, long n_streams);
+int wam_iir_process_batch_device(const double* b, int nb, const double* a, int na, const float* d_in, float* d_out,
+                                 long stride, long n, long n_streams, double* d_state, void* d_scratch,
+                                 size_t scratch_bytes, void* cuda_stream);
+int wam_fir_process_batch_device(const double* d_taps, int ntaps, const float* d_in, float* d_out, long stride,
+                                 long n, long n_streams, double* d_state, double* d_state_scratch, void* cuda_stream);
 
 /* test hook: the device float64 primitives of the discriminator (fast_atan2 / fast_sqrt / fast_rcp)
  * evaluated on host arrays; used by tests/test_gpu_fastmath.py to bound their error against libm. */

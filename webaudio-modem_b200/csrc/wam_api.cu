@@ -1740,24 +1740,52 @@ extern "C" long wam_iir_state_size(int nb, int na) {
   return (long)(nb - 1) + (long)(na - 1);
 }
 
-extern "C" int wam_iir_process_batch(int device, const double* b, int nb, const double* a, int na, const float* in,
-                                     float* out, long stride, long n, long n_streams, double* state) {
+static int iir_fill_args(IirArgs& ia, const double* b, int nb, const double* a, int na) {
   if (!b || nb <= 0) return fail(WAM_E_FILTER_B_EMPTY, wam_error_string(WAM_E_FILTER_B_EMPTY));
   if (!a || na <= 0) return fail(WAM_E_FILTER_A_EMPTY, wam_error_string(WAM_E_FILTER_A_EMPTY));
   if (a[0] == 0) return fail(WAM_E_FILTER_A0_ZERO, wam_error_string(WAM_E_FILTER_A0_ZERO));
-  if (nb > kMaxIirTaps || na > kMaxIirTaps) return fail(WAM_E_UNSUPPORTED, "IIR order above 8 not supported");
-  if (n < 0 || n_streams < 0 || stride < n || (n > 0 && n_streams > 0 && (!in || !out))) return fail(WAM_E_INVALID, "bad argument");
-  int rc = select_device(device);
-  if (rc != WAM_OK) return rc;
-  if (n == 0 || n_streams == 0) return WAM_OK;
-  IirArgs ia;
+  if (nb > kMaxIirTaps || na > kMaxIirTaps) return fail(WAM_E_UNSUPPORTED, "IIR order above 7 not supported");
   memset(&ia, 0, sizeof(ia));
   // a0 normalisation — filters.ts:30-39
   ia.nb = nb; ia.na = na;
   for (int i = 0; i < nb; i++) ia.b[i] = (a[0] != 1) ? b[i] / a[0] : b[i];
   for (int i = 1; i < na; i++) ia.a[i] = (a[0] != 1) ? a[i] / a[0] : a[i];
   ia.a[0] = 1;
+  return WAM_OK;
+}
+
+extern "C" int wam_iir_process_batch(int device, const double* b, int nb, const double* a, int na, const float* in,
+                                     float* out, long stride, long n, long n_streams, double* state) {
+  IirArgs ia;
+  int rc = iir_fill_args(ia, b, nb, a, na);
+  if (rc != WAM_OK) return rc;
+  if (n < 0 || n_streams < 0 || stride < n || (n > 0 && n_streams > 0 && (!in || !out))) return fail(WAM_E_INVALID, "bad argument");
+  rc = select_device(device);
+  if (rc != WAM_OK) return rc;
+  if (n == 0 || n_streams == 0) return WAM_OK;
   return iir_process_batch_host(ia, in, out, stride, n, n_streams, state);
+}
+
+extern "C" size_t wam_iir_scratch_bytes(long n, long n_streams) { return iir_scratch_bytes(n, n_streams); }
+
+// DEVICE buffers on the current device, asynchronous on cuda_stream; d_state (nullable) is read and written in place.
+extern "C" int wam_iir_process_batch_device(const double* b, int nb, const double* a, int na, const float* d_in, float* d_out,
+                                            long stride, long n, long n_streams, double* d_state, void* d_scratch,
+                                            size_t scratch_bytes, void* cuda_stream) {
+  IirArgs ia;
+  int rc = iir_fill_args(ia, b, nb, a, na);
+  if (rc != WAM_OK) return rc;
+  if (n < 0 || n_streams < 0 || stride < n || (n > 0 && n_streams > 0 && (!d_in || !d_out))) return fail(WAM_E_INVALID, "bad argument");
+  return iir_process_batch_device(ia, d_in, d_out, stride, n, n_streams, d_state, d_scratch, scratch_bytes, (cudaStream_t)cuda_stream);
+}
+
+// DEVICE buffers (taps included); d_state (nullable) [n_streams][ntaps - 1] is updated in place through d_state_scratch.
+extern "C" int wam_fir_process_batch_device(const double* d_taps, int ntaps, const float* d_in, float* d_out, long stride,
+                                            long n, long n_streams, double* d_state, double* d_state_scratch, void* cuda_stream) {
+  if (ntaps < 0 || (ntaps > 0 && !d_taps)) return fail(WAM_E_INVALID, "bad taps");
+  if (ntaps > kMaxFirTaps) return fail(WAM_E_UNSUPPORTED, "FIR longer than 1024 taps not supported");
+  if (n < 0 || n_streams < 0 || stride < n || (n > 0 && n_streams > 0 && (!d_in || !d_out))) return fail(WAM_E_INVALID, "bad argument");
+  return fir_process_batch_device(d_taps, ntaps, d_in, d_out, stride, n, n_streams, d_state, d_state_scratch, (cudaStream_t)cuda_stream);
 }
 
 extern "C" int wam_fir_process_batch(int device, const double* taps, int ntaps, const float* in, float* out,
