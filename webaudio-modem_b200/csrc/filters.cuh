@@ -80,6 +80,7 @@ __device__ __forceinline__ void mat_apply(const double* Tm, int M, const double*
 template <bool WRITE, int NXT, int MT>
 __device__ __forceinline__ void iir_run_chunk(const IirArgs& a, float* xs, int len, double* xh, double* yh) {
   const int NX = NXT >= 0 ? NXT : a.nb - 1, M = MT >= 0 ? MT : a.na - 1;
+#pragma unroll 8
   for (int i = 0; i < len; ++i) {
     const double x0 = (double)xs[i];
     double y = a.b[0] * x0;  // accumulation order of filters.ts:56-66
@@ -172,7 +173,9 @@ __global__ void __launch_bounds__(kIirWarps * 32) iir_scan_kernel(const __grid_c
     xh0[k] = 0.0;
     if (k < NX) {
       const long idx = start - 1 - k;
-      if (idx >= 0) xh0[k] = (idx < a.n) ? (double)in[idx] : 0.0;
+      const int rel = chunk * kIirChunk - 1 - k;  // position inside the staged tile
+      if (rel >= 0) xh0[k] = (idx < a.n) ? (double)smem[(rel / kIirChunk) * kIirPitch + rel % kIirChunk] : 0.0;
+      else if (idx >= 0) xh0[k] = (idx < a.n) ? (double)in[idx] : 0.0;
       else if (a.state) xh0[k] = a.state[s * stw + (int)(-idx - 1)];
     }
     xh[k] = xh0[k]; yh[k] = 0.0;
