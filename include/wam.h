@@ -216,6 +216,9 @@ typedef struct wam_fast_stats {
   /* most recent fast call: doubtful decisions checked by a float64 run of a short window around them, by outcome
    * (confirmed: the fast results stand; refuted or dropped for lack of room: the stream is re-run over the whole call) */
   int64_t windows_confirmed, windows_refuted, windows_dropped;
+  /* streams whose open float32 readings at the end of a fast call were re-read in float64 at the start of the next
+   * call (over the batch's life), and how many of them the float64 reading changed */
+  int64_t carried_settled, carried_corrected;
 } wam_fast_stats;
 int wam_fsk_batch_fast_stats(wam_fsk_batch* b, wam_fast_stats* out);
 /* Channel model of the synthetic workloads (BASELINE config 5: modulate -> AWGN -> demodulate): adds Gaussian noise

@@ -130,6 +130,41 @@ def test_streaming_calls_carry_state(gpu_wam, oracle):
         assert db.b.fast_stats()["fast_calls"] == sum(1 for f in plan if f == L.WAM_BATCH_FORCE_FAST)
 
 
+@pytest.mark.parametrize("scale", [1.0, 300.0])
+def test_open_readings_are_settled_at_the_next_call(gpu_wam, oracle, scale):
+    """Streams that end a fast call with float32 readings still open (running vote, silent run, ring bits inside the
+    doubt band) keep their last slabs; the next call — fast or float64 — begins by re-reading them in float64.  With a
+    wide band nearly every stream carries; results stay the oracle's and nothing is left on record as unverifiable."""
+    L = _lib(gpu_wam)
+    cfgs, idx, x = _v21_batch(160, seed=41)
+    chunks = [9600, 19200, 9600, 9600]
+    want, ost = _oracle(oracle, cfgs, idx, x, chunks)
+    for plan in ([L.WAM_BATCH_FORCE_FAST] * 4,
+                 [L.WAM_BATCH_FORCE_FAST, L.WAM_BATCH_FORCE_FAST, L.WAM_BATCH_EXACT_ONLY, L.WAM_BATCH_FORCE_FAST]):
+        db = DeviceBatch(gpu_wam, cfgs, idx, 160)
+        db.b.debug_fast_band(scale)
+        got = [b""] * 160
+        pos = 0
+        for c, fl in zip(chunks, plan):
+            part = db.run(x[:, pos:pos + c], fl)
+            got = [g + p for g, p in zip(got, part)]
+            pos += c
+        fs = db.b.fast_stats()
+        _check(got, db.b.status(), want, ost)
+        assert fs["error_flags"] == 0, fs
+        if scale > 1.0:
+            assert fs["carried_settled"] > 0, fs
+    # reset() and renew() drop what was carried
+    db = DeviceBatch(gpu_wam, cfgs, idx, 160)
+    db.b.debug_fast_band(300.0)
+    db.run(x[:, :9600], L.WAM_BATCH_FORCE_FAST)
+    db.b.renew()
+    db.b.debug_fast_band(300.0)
+    got = db.run(x, L.WAM_BATCH_FORCE_FAST)
+    want1, ost1 = _oracle(oracle, cfgs, idx, x)
+    _check(got, db.b.status(), want1, ost1)
+
+
 def test_interleaved_groups_fall_back_to_float64(gpu_wam, oracle):
     L = _lib(gpu_wam)
     cfgs, idx, x = _v21_batch(64, seed=37, n=24000, interleaved=True)

@@ -75,7 +75,8 @@ class FastStats(C.Structure):
     """wam_fast_stats (include/wam.h)"""
     _fields_ = [("fast_calls", C.c_int64), ("flagged_last_call", C.c_int64), ("flagged_streams", C.c_int64),
                 ("doubtful_samples", C.c_int64), ("flag_causes", C.c_uint32), ("error_flags", C.c_uint32),
-                ("windows_confirmed", C.c_int64), ("windows_refuted", C.c_int64), ("windows_dropped", C.c_int64)]
+                ("windows_confirmed", C.c_int64), ("windows_refuted", C.c_int64), ("windows_dropped", C.c_int64),
+                ("carried_settled", C.c_int64), ("carried_corrected", C.c_int64)]
 
 
 class ChunkResult(C.Structure):

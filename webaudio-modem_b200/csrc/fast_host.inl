@@ -185,40 +185,36 @@ __global__ void fast_collect_kernel(const FastCtx c) {
   }
 }
 
-// (3b) gather: a block per window of class `cls` (cls + 1 slabs).  Scratch index of window i of class cls:
-// cls * kVerifyCap + i.
-__global__ void fast_gather_kernel(const FastCtx c, int cls) {
-  const int i = blockIdx.x;
-  if (i >= fc_count(c, cls)) return;
+// Scratch entry `si` of a scratch batch of `nv` streams <- stream li as of checkpoint j0: state (doubt tracking cleared),
+// rings rebuilt from the histories, and wslabs slabs of samples.  One block.
+struct FastScratch {
+  double* f64; uint32_t* u32; uint32_t* ring; float* amp; float* samples; long stride; int32_t* out_len;
+};
+__device__ __forceinline__ void fc_gather_body(const FastCtx& c, const FastScratch& d, int li, int j0, int wslabs, size_t si, size_t nv) {
   const int ns = c.q.ns;
-  const int li = c.item_li[cls * kVerifyCap + i];
-  int j0, wslabs, wend;  // first slab of the window = the checkpoint it starts from
-  fc_window(c, cls, c.item_slab[cls * kVerifyCap + i], j0, wslabs, wend);
-  const size_t si = (size_t)cls * kVerifyCap + i;
-  const size_t nv = (size_t)kAllClasses * kVerifyCap;  // streams of the scratch batch
   const double* f = fc_ck_f64(c, j0);
   const uint32_t* u = fc_ck_u32(c, j0);
   for (int k = threadIdx.x; k < F64_COUNT; k += blockDim.x) {
     double v = f[(size_t)k * ns + li];
     if (k == F_FAST_E || k == F_FAST_RSP) v = 0.0;
-    c.sv_f64[(size_t)k * nv + si] = v;
+    d.f64[(size_t)k * nv + si] = v;
   }
   for (int k = threadIdx.x; k < U32_COUNT; k += blockDim.x) {
     uint32_t v = u[(size_t)k * ns + li];
     if (k == U_DVOTE || k == U_SILX || k == U_LAST_DOUBT || k == U_DCNT || k == U_FLAG || k == U_ERR) v = 0u;
-    c.sv_u32[(size_t)k * nv + si] = v;
+    d.u32[(size_t)k * nv + si] = v;
   }
   // rings as of the window's start, from the histories
   const uint32_t ring_pos = u[(size_t)U_RING_POS * ns + li];
   const uint32_t amp_pos = u[(size_t)U_AMP_POS * ns + li];
   const long tiles_per_slab = c.q.slab_len / kTile;
   const uint16_t* bh = c.bit_hist + (size_t)li * c.q.bh_stride + c.q.ph + (long)j0 * tiles_per_slab;  // behind the newest tile
-  uint16_t* ring16 = reinterpret_cast<uint16_t*>(c.sv_ring + si * c.ring_words);
+  uint16_t* ring16 = reinterpret_cast<uint16_t*>(d.ring + si * c.ring_words);
   const uint32_t hmask = (uint32_t)(2 * c.ring_words - 1);
   const uint32_t p16 = ring_pos >> 4;
   for (int m = threadIdx.x; m < 2 * c.ring_words; m += blockDim.x) ring16[(p16 - 1u - (uint32_t)m) & hmask] = bh[-1 - m];
   const float* ah = c.amp_hist + (size_t)li * c.q.ah_stride + c.q.pa + (long)j0 * (c.q.slab_len / 2);
-  float* ar = c.sv_amp + si * c.amp_phys;
+  float* ar = d.amp + si * c.amp_phys;
   for (int k = threadIdx.x; k < c.amp_cap; k += blockDim.x) {
     int slot = (int)amp_pos - 1 - k;
     if (slot < 0) slot += c.amp_phys;
@@ -227,14 +223,109 @@ __global__ void fast_gather_kernel(const FastCtx c, int cls) {
   // the window's samples
   const long wlen = (long)wslabs * c.q.slab_len;
   const float4* src = reinterpret_cast<const float4*>(c.samples + fc_row(c, li) * c.stride + (long)j0 * c.q.slab_len);
-  float4* dst = reinterpret_cast<float4*>(c.sv_samples + si * c.q.sv_stride);
+  float4* dst = reinterpret_cast<float4*>(d.samples + si * d.stride);
   for (long k = threadIdx.x; k < wlen / 4; k += blockDim.x) dst[k] = src[k];
-  if (threadIdx.x == 0) c.sv_out_len[si] = 0;
+  if (threadIdx.x == 0) d.out_len[si] = 0;
+}
+
+// (3b) gather: a block per window of class `cls`.  Scratch index of window i of class cls: cls * kVerifyCap + i.
+__global__ void fast_gather_kernel(const FastCtx c, int cls) {
+  const int i = blockIdx.x;
+  if (i >= fc_count(c, cls)) return;
+  const int li = c.item_li[cls * kVerifyCap + i];
+  int j0, wslabs, wend;  // first slab of the window = the checkpoint it starts from
+  fc_window(c, cls, c.item_slab[cls * kVerifyCap + i], j0, wslabs, wend);
+  const size_t si = (size_t)cls * kVerifyCap + i;
+  const size_t nv = (size_t)kAllClasses * kVerifyCap;  // streams of the scratch batch
+  const FastScratch d = {c.sv_f64, c.sv_u32, c.sv_ring, c.sv_amp, c.sv_samples, c.q.sv_stride, c.sv_out_len};
+  fc_gather_body(c, d, li, j0, wslabs, si, nv);
   if (cls == kStageE2) {
     // the float64 silence threshold from stage 1 (its run and its check are ahead of this kernel on the same stream)
     __syncthreads();
     if (threadIdx.x == 0 && c.item_slab[kStageE1 * kVerifyCap + i] >= 0)
       c.sv_f64[(size_t)F_SIL_THR * nv + si] = c.sv_f64[(size_t)F_SIL_THR * nv + (size_t)kStageE1 * kVerifyCap + i];
+  }
+}
+
+// ---- carry: what a call leaves undecided is re-read in float64 at the start of the next call ----
+// A stream that ends a fast call with float32 readings still open — a running vote with a doubtful sample, a silent
+// run with a doubtful compare, ring bits inside the doubt band — cannot have them checked later: the samples belong to
+// the caller and are gone.  So the call's last slabs of every such stream are kept (state of the checkpoint at their
+// start, rings, samples), and the next call — fast or not — begins by running them through the float64 kernel and
+// comparing the result with the live state.  Equal (the usual case): the open readings were right, the doubt records are
+// cleared.  Different: the float64 result replaces the live state.  Either way the call starts from certified readings.
+struct CarryCtx {
+  int ns, cap, ring_words, amp_phys, amp_cap;
+  double* f64; uint32_t* u32; uint32_t* sync_ring; float* amp_ring;   // live
+  const int32_t* li; int32_t* count;
+  double* cv_f64; uint32_t* cv_u32; uint32_t* cv_ring; float* cv_amp;
+};
+
+// (6a) which streams carry: a thread per stream, final checkpoint
+__global__ void fast_carry_collect_kernel(const FastCtx c, int32_t* carry_li, int32_t* carry_count, int cap) {
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ns = c.q.ns;
+  if (li >= ns || c.hard_mark[li]) return;  // (hard streams end the call in the float64 kernel's state)
+  const uint32_t* u = fc_ck_u32(c, c.q.n_slabs);
+  const bool open = u[(size_t)U_DVOTE * ns + li] != 0u || (u[(size_t)U_SILX * ns + li] >> 31) != 0u || u[(size_t)U_DCNT * ns + li] != 0u;
+  if (!open) return;
+  const int slot = atomicAdd(carry_count, 1);
+  if (slot < cap) carry_li[slot] = li;
+}
+// (6b) keep their last `wslabs` slabs: a block per entry
+__global__ void fast_carry_gather_kernel(const FastCtx c, const int32_t* carry_li, const int32_t* carry_count, int cap, int wslabs,
+                                         FastScratch d) {
+  const int i = blockIdx.x;
+  if (i >= min(carry_count[0], cap)) return;
+  fc_gather_body(c, d, carry_li[i], c.q.n_slabs - wslabs, wslabs, (size_t)i, (size_t)cap);
+}
+// (6c) after the float64 run of the kept slabs: a warp per entry compares with the live state and, where they differ,
+// puts the float64 result in its place
+__global__ void fast_carry_apply_kernel(const CarryCtx c) {
+  const int i = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
+  if (i >= min(c.count[0], c.cap)) return;
+  const int li = c.li[i];
+  const size_t ns = (size_t)c.ns, nv = (size_t)c.cap;
+  const int fields[] = {U_GSC, U_BSC, U_NEXT_IDX, U_BIT_ACC, U_BIT_CNT, U_STARTED, U_BITPOS, U_CURRENT, U_SIL_CNT,
+                        U_SYNC_DET, U_EOD_EV, U_RING_POS, U_RING_LEN, U_AMP_POS, U_AMP_LEN, U_DSC};
+  bool same = true;
+  if (lane == 0) {
+    for (int k : fields) same = same && c.cv_u32[(size_t)k * nv + i] == c.u32[(size_t)k * ns + li];
+    if (!c.u32[(size_t)U_STARTED * ns + li]) same = same && c.cv_u32[(size_t)U_GMOD * nv + i] == c.u32[(size_t)U_GMOD * ns + li];
+    const double ta = c.cv_f64[(size_t)F_SIL_THR * nv + i], tb = c.f64[(size_t)F_SIL_THR * ns + li];
+    same = same && fabs(ta - tb) <= 1e-5 * fabs(tb);
+    same = same && c.cv_u32[(size_t)U_ERR * nv + i] == 0u;
+  }
+  // ring contents, half word by half word (aligned calls put 16 bits at a time)
+  const uint16_t* ra = reinterpret_cast<const uint16_t*>(c.cv_ring + (size_t)i * c.ring_words);
+  const uint16_t* rb = reinterpret_cast<const uint16_t*>(c.sync_ring + (size_t)li * c.ring_words);
+  const uint32_t hmask = (uint32_t)(2 * c.ring_words - 1);
+  const uint32_t p16 = c.u32[(size_t)U_RING_POS * ns + li] >> 4;
+  const uint32_t halves = min(c.u32[(size_t)U_RING_LEN * ns + li] >> 4, (uint32_t)(2 * c.ring_words - 2));
+  for (uint32_t m = lane; m < halves; m += 32) same = same && ra[(p16 - 1u - m) & hmask] == rb[(p16 - 1u - m) & hmask];
+  same = __all_sync(0xffffffffu, same);
+  if (!same) {
+    // the float64 reading replaces the live state (the fast-path fields keep their values: they are bounds, not readings)
+    for (int k = lane; k < F64_COUNT; k += 32)
+      if (k != F_FAST_S && k != F_FAST_E && k != F_FAST_RSP) c.f64[(size_t)k * ns + li] = c.cv_f64[(size_t)k * nv + i];
+    for (int k = lane; k < U32_COUNT; k += 32)
+      if (k != U_ERR && k != U_FLAG_EVER && k != U_DOUBT_SAMPLES && k != U_OUT_N && k != U_FLAG && k != U_SB_ONES && k != U_SB_VALID &&
+          k != U_SB0 && k != U_SB1 && k != U_SB2 && k != U_SB3)
+        c.u32[(size_t)k * ns + li] = c.cv_u32[(size_t)k * nv + i];
+    uint32_t* dr = c.sync_ring + (size_t)li * c.ring_words;
+    const uint32_t* sr = c.cv_ring + (size_t)i * c.ring_words;
+    for (int k = lane; k < c.ring_words; k += 32) dr[k] = sr[k];
+    float* da = c.amp_ring + (size_t)li * c.amp_phys;
+    const float* sa = c.cv_amp + (size_t)i * c.amp_phys;
+    for (int k = lane; k < c.amp_phys; k += 32) da[k] = sa[k];
+    if (lane == 0) c.u32[(size_t)U_SB_VALID * ns + li] = 0xffffffffu;  // the search prefilter starts over
+  }
+  if (lane == 0) {
+    // certified either way: nothing is open any more
+    for (int k : {(int)U_DVOTE, (int)U_SILX, (int)U_LAST_DOUBT, (int)U_DCNT}) c.u32[(size_t)k * ns + li] = 0u;
+    atomicAdd(c.count + 1, 1);
+    if (!same) atomicAdd(c.count + 2, 1);
   }
 }
 
@@ -446,6 +537,74 @@ static int fast_streams(wam_fsk_batch* b) {
   return WAM_OK;
 }
 
+// The kept slabs of the last fast call through the float64 kernel, then fast_carry_apply_kernel.  Runs on `st` ahead of
+// whatever the call does next.
+static int fast_carry_settle(wam_fsk_batch* b, Group& g, cudaStream_t st) {
+  FastBuffers& fb = g.fb;
+  if (!fb.carry_pending) return WAM_OK;
+  fb.carry_pending = false;
+  DemodLaunch Lv;
+  memset(&Lv, 0, sizeof(Lv));
+  DemodArgs& a = Lv.g[0];
+  a.d = g.d;
+  a.ids = nullptr; a.id0 = 0; a.row_base = 0;
+  a.n_local = fb.carry_cap;
+  a.f64 = fb.cv_f64; a.u32 = fb.cv_u32; a.sync_ring = fb.cv_ring; a.amp_ring = fb.cv_amp;
+  a.samples = fb.cv_samples; a.stride = fb.carry_n; a.n = fb.carry_n;
+  a.out = fb.cv_out; a.out_stride = fb.carry_out_stride; a.out_len = fb.cv_out_len;
+  int rc = launch_exact_selected(b, Lv, fb.cv_iota, fb.carry_count, fb.carry_cap, a.n, st);
+  if (rc != WAM_OK) return rc;
+  CarryCtx cc;
+  cc.ns = (int)g.ids.size(); cc.cap = fb.carry_cap; cc.ring_words = g.d.ring_words; cc.amp_phys = g.d.amp_phys; cc.amp_cap = g.d.amp_cap;
+  cc.f64 = g.f64; cc.u32 = g.u32; cc.sync_ring = g.sync_ring; cc.amp_ring = g.amp_ring;
+  cc.li = fb.carry_li; cc.count = fb.carry_count;
+  cc.cv_f64 = fb.cv_f64; cc.cv_u32 = fb.cv_u32; cc.cv_ring = fb.cv_ring; cc.cv_amp = fb.cv_amp;
+  fast_carry_apply_kernel<<<(unsigned)((fb.carry_cap + 3) / 4), 128, 0, st>>>(cc);
+  CUDA_TRY(cudaGetLastError());
+  return WAM_OK;
+}
+
+// End of a fast call: keep the last slabs of the streams with open readings (see above).
+static int fast_carry_save(wam_fsk_batch* b, Group& g, const FastCtx& c, long out_cap_per_window, cudaStream_t st) {
+  (void)b;
+  FastBuffers& fb = g.fb;
+  const FastGeom& q = c.q;
+  const int need = std::max(std::max(q.sync_slabs, q.e2_len), 2);
+  if (need > kVerifyClasses || q.n != (long)q.n_slabs * q.slab_len) return WAM_OK;  // no window could settle them: the record stays
+  const int wslabs = std::min(need, q.n_slabs);
+  const int cap = (std::max(1024, (q.ns + 3) / 4) + 31) / 32 * 32;  // (a multiple of the warp size: see the sub-selection in the kernels)
+  if (!fb.carry_li || fb.carry_cap != cap) {
+    for (void* p : {(void*)fb.carry_li, (void*)fb.carry_count, (void*)fb.cv_iota, (void*)fb.cv_f64, (void*)fb.cv_u32, (void*)fb.cv_ring,
+                    (void*)fb.cv_amp, (void*)fb.cv_out_len})
+      if (p) cudaFree(p);
+    fb.carry_cap = cap;
+    CUDA_TRY(cudaMalloc(&fb.carry_li, sizeof(int32_t) * (size_t)cap));
+    CUDA_TRY(cudaMalloc(&fb.carry_count, sizeof(int32_t) * 4));
+    CUDA_TRY(cudaMemsetAsync(fb.carry_count, 0, sizeof(int32_t) * 4, st));
+    CUDA_TRY(cudaMalloc(&fb.cv_iota, sizeof(int32_t) * (size_t)cap));
+    std::vector<int32_t> h((size_t)cap);
+    for (int i = 0; i < cap; i++) h[(size_t)i] = i;
+    CUDA_TRY(cudaMemcpy(fb.cv_iota, h.data(), sizeof(int32_t) * (size_t)cap, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&fb.cv_f64, sizeof(double) * F64_COUNT * (size_t)cap));
+    CUDA_TRY(cudaMalloc(&fb.cv_u32, sizeof(uint32_t) * U32_COUNT * (size_t)cap));
+    CUDA_TRY(cudaMalloc(&fb.cv_ring, sizeof(uint32_t) * (size_t)g.d.ring_words * (size_t)cap));
+    CUDA_TRY(cudaMalloc(&fb.cv_amp, sizeof(float) * (size_t)g.d.amp_phys * (size_t)cap));
+    CUDA_TRY(cudaMalloc(&fb.cv_out_len, sizeof(int32_t) * (size_t)cap));
+  }
+  fb.carry_n = (long)wslabs * q.slab_len;
+  fb.carry_out_stride = std::max<long>(out_cap_per_window, 16);
+  int rc;
+  if ((rc = ensure((void**)&fb.cv_samples, &fb.cv_samples_bytes, sizeof(float) * (size_t)cap * (size_t)fb.carry_n)) != WAM_OK) return rc;
+  if ((rc = ensure((void**)&fb.cv_out, &fb.cv_out_bytes, (size_t)cap * (size_t)fb.carry_out_stride)) != WAM_OK) return rc;
+  CUDA_TRY(cudaMemsetAsync(fb.carry_count, 0, sizeof(int32_t), st));  // ([1], [2]: running totals for the statistics)
+  fast_carry_collect_kernel<<<(unsigned)((q.ns + 255) / 256), 256, 0, st>>>(c, fb.carry_li, fb.carry_count, cap);
+  const FastScratch d = {fb.cv_f64, fb.cv_u32, fb.cv_ring, fb.cv_amp, fb.cv_samples, fb.carry_n, fb.cv_out_len};
+  fast_carry_gather_kernel<<<(unsigned)cap, 128, 0, st>>>(c, fb.carry_li, fb.carry_count, cap, wslabs, d);
+  CUDA_TRY(cudaGetLastError());
+  fb.carry_pending = true;
+  return WAM_OK;
+}
+
 // L: the call's launch description (<= kFastGroupsPerLaunch groups, rows contiguous, TMA descriptors for the whole call).
 static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, const long* tmap_rows, long n, uint32_t flags,
                            cudaStream_t st) {
@@ -471,6 +630,7 @@ static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, c
   for (int gi = 0; gi < G; gi++) {
     Group& g = *lg[gi];
     const DemodArgs& a = L.g[gi];
+    if (g.fb.carry_pending) { rc = fast_carry_settle(b, g, st); if (rc != WAM_OK) return rc; }
     if (g.doubt_state == 2) { rc = fast_clean_doubt(g, st); if (rc != WAM_OK) return rc; }
     g.doubt_state = 1;
     FastGeom q;
@@ -611,5 +771,10 @@ static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, c
   }
   for (int gi = 0; gi < G; gi++) fast_epilogue_kernel<<<ctx[gi].q.ns, 128, 0, st>>>(ctx[gi]);
   CUDA_TRY(cudaGetLastError());
+  if (guarded)
+    for (int gi = 0; gi < G; gi++) {
+      const long wcap = wam_fsk_batch_out_capacity(b, (long)kVerifyClasses * slab_len);
+      if ((rc = fast_carry_save(b, *lg[gi], ctx[gi], wcap, st)) != WAM_OK) return rc;
+    }
   return WAM_OK;
 }

@@ -369,7 +369,22 @@ struct FastBuffers {
   uint8_t* sv_out = nullptr; size_t sv_out_bytes = 0;
   int32_t* sv_out_len = nullptr;
   bool scratch_ready = false;
+  // carry: streams that ended the last fast call with float32 readings still undecided (a running vote, a silent run,
+  // ring bits inside the doubt band) keep the call's last slabs — state, rings, samples — so that the next call can
+  // begin by re-reading them in float64 (fast_carry_settle)
+  int32_t* carry_li = nullptr; int32_t* carry_count = nullptr;  // carry_count[0] entries, [1] settled so far, [2] corrected so far
+  int32_t* cv_iota = nullptr;
+  double* cv_f64 = nullptr; uint32_t* cv_u32 = nullptr; uint32_t* cv_ring = nullptr; float* cv_amp = nullptr;
+  float* cv_samples = nullptr; size_t cv_samples_bytes = 0;
+  uint8_t* cv_out = nullptr; size_t cv_out_bytes = 0;
+  int32_t* cv_out_len = nullptr;
+  int carry_cap = 0;
+  long carry_n = 0, carry_out_stride = 0;  // samples per entry, bytes of scratch output per entry
+  bool carry_pending = false;
   void release() {
+    for (void* q : {(void*)carry_li, (void*)carry_count, (void*)cv_iota, (void*)cv_f64, (void*)cv_u32, (void*)cv_ring, (void*)cv_amp,
+                    (void*)cv_samples, (void*)cv_out, (void*)cv_out_len})
+      if (q) cudaFree(q);
     for (void* q : {(void*)ck_f64, (void*)ck_u32, (void*)bit_hist, (void*)amp_hist, (void*)slab_list, (void*)slab_count,
                     (void*)hard_list, (void*)hard_count, (void*)hard_mark, (void*)item_li, (void*)item_slab,
                     (void*)item_count, (void*)iota, (void*)sv_f64, (void*)sv_u32, (void*)sv_ring, (void*)sv_amp,
@@ -544,6 +559,7 @@ static int init_group_state(Group& g, cudaStream_t st) {
   CUDA_TRY(cudaMemsetAsync(g.amp_ring, 0, sizeof(float) * (size_t)g.d.amp_phys * n, st));
   g.doubt_state = 0;
   g.unaligned = false;
+  g.fb.carry_pending = false;  // fresh streams carry nothing
   // AGC gain 1.0 (fsk.ts:46), silence threshold 0.01 (fsk.ts:128)
   const unsigned blocks = (unsigned)((n + 255) / 256);
   fill_f64_kernel<<<blocks, 256, 0, st>>>(g.f64 + (size_t)F_GAIN * n, 1.0, (long)n);
@@ -711,6 +727,8 @@ extern "C" int wam_fsk_batch_reset(wam_fsk_batch* b) {
     for (int u : u_zero) CUDA_TRY(cudaMemset(g.u32 + (size_t)u * n, 0, sizeof(uint32_t) * n));
     fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256>>>(g.f64 + (size_t)F_LO_C * n, 1.0, (long)n);
     CUDA_TRY(cudaGetLastError());
+    g.doubt_state = 2;            // the doubt tracking restarts with the state machine
+    g.fb.carry_pending = false;   // reset() empties the rings and counters the carried readings were about
   }
   b->demodulation_calls = 0;
   b->total_samples = 0;
@@ -870,7 +888,11 @@ static int launch_demod_range(wam_fsk_batch* b, long s0, long s1, long row_base,
         tma_ok = aligned;
         return rc;
       }
-      for (int g = 0; g < L.n_groups; g++) lg[g]->doubt_state = 2;  // a float64 kernel is about to run on these groups
+      for (int g = 0; g < L.n_groups; g++) {
+        // a float64 kernel is about to run on these groups: first settle what the last fast call left undecided
+        if (lg[g]->fb.carry_pending) { int rc = fast_carry_settle(b, *lg[g], st); if (rc != WAM_OK) return rc; }
+        lg[g]->doubt_state = 2;
+      }
     }
     // Few streams (<= 5 three-warp CTAs per SM): the warp-specialised pipeline (fsk_demod_pipe.cuh) advances a
     // stream at the longest of the three phase chains instead of their sum.  Many streams: the fused kernel,
@@ -1239,6 +1261,12 @@ extern "C" int wam_fsk_batch_fast_stats(wam_fsk_batch* b, wam_fast_stats* out) {
       out->windows_confirmed += c[1];
       out->windows_refuted += c[2];
       out->windows_dropped += c[3];
+    }
+    if (g.fb.carry_count) {
+      int32_t c[4] = {0, 0, 0, 0};
+      CUDA_TRY(cudaMemcpy(c, g.fb.carry_count, sizeof(c), cudaMemcpyDeviceToHost));
+      out->carried_settled += c[1];
+      out->carried_corrected += c[2];
     }
   }
   return WAM_OK;
