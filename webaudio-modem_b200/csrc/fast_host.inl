@@ -258,6 +258,7 @@ struct CarryCtx {
   int ns, cap, ring_words, amp_phys, amp_cap;
   double* f64; uint32_t* u32; uint32_t* sync_ring; float* amp_ring;   // live
   const int32_t* li; int32_t* count;
+  const uint32_t* hard_mark;  // of the call that kept the slabs: those streams ended it in the float64 kernel's own state
   double* cv_f64; uint32_t* cv_u32; uint32_t* cv_ring; float* cv_amp;
 };
 
@@ -265,7 +266,7 @@ struct CarryCtx {
 __global__ void fast_carry_collect_kernel(const FastCtx c, int32_t* carry_li, int32_t* carry_count, int cap) {
   const int li = blockIdx.x * blockDim.x + threadIdx.x;
   const int ns = c.q.ns;
-  if (li >= ns || c.hard_mark[li]) return;  // (hard streams end the call in the float64 kernel's state)
+  if (li >= ns) return;  // (runs beside the checks: streams that end up on the hard list are skipped when settling)
   const uint32_t* u = fc_ck_u32(c, c.q.n_slabs);
   const bool open = u[(size_t)U_DVOTE * ns + li] != 0u || (u[(size_t)U_SILX * ns + li] >> 31) != 0u || u[(size_t)U_DCNT * ns + li] != 0u;
   if (!open) return;
@@ -286,6 +287,7 @@ __global__ void fast_carry_apply_kernel(const CarryCtx c) {
   const int lane = threadIdx.x & 31;
   if (i >= min(c.count[0], c.cap)) return;
   const int li = c.li[i];
+  if (c.hard_mark[li]) return;
   const size_t ns = (size_t)c.ns, nv = (size_t)c.cap;
   const int fields[] = {U_GSC, U_BSC, U_NEXT_IDX, U_BIT_ACC, U_BIT_CNT, U_STARTED, U_BITPOS, U_CURRENT, U_SIL_CNT,
                         U_SYNC_DET, U_EOD_EV, U_RING_POS, U_RING_LEN, U_AMP_POS, U_AMP_LEN, U_DSC};
@@ -557,7 +559,7 @@ static int fast_carry_settle(wam_fsk_batch* b, Group& g, cudaStream_t st) {
   CarryCtx cc;
   cc.ns = (int)g.ids.size(); cc.cap = fb.carry_cap; cc.ring_words = g.d.ring_words; cc.amp_phys = g.d.amp_phys; cc.amp_cap = g.d.amp_cap;
   cc.f64 = g.f64; cc.u32 = g.u32; cc.sync_ring = g.sync_ring; cc.amp_ring = g.amp_ring;
-  cc.li = fb.carry_li; cc.count = fb.carry_count;
+  cc.li = fb.carry_li; cc.count = fb.carry_count; cc.hard_mark = fb.hard_mark;
   cc.cv_f64 = fb.cv_f64; cc.cv_u32 = fb.cv_u32; cc.cv_ring = fb.cv_ring; cc.cv_amp = fb.cv_amp;
   fast_carry_apply_kernel<<<(unsigned)((fb.carry_cap + 3) / 4), 128, 0, st>>>(cc);
   CUDA_TRY(cudaGetLastError());
@@ -724,6 +726,16 @@ static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, c
   if (guarded) {
     for (int gi = 0; gi < G; gi++) fast_collect_kernel<<<dim3(4, (unsigned)std::min(n_slabs, 64)), 256, 0, st>>>(ctx[gi]);
     CUDA_TRY(cudaEventRecord(b->slab_fork, st));
+    {
+      // beside the checks: keep the last slabs of the streams that end the call with open readings
+      cudaStream_t sc = b->slab_streams[kSlabStreams - 1];
+      CUDA_TRY(cudaStreamWaitEvent(sc, b->slab_fork, 0));
+      const long wcap = wam_fsk_batch_out_capacity(b, (long)kVerifyClasses * slab_len);
+      for (int gi = 0; gi < G; gi++)
+        if ((rc = fast_carry_save(b, *lg[gi], ctx[gi], wcap, sc)) != WAM_OK) return rc;
+      CUDA_TRY(cudaEventRecord(b->slab_join[kSlabStreams - 1], sc));
+      CUDA_TRY(cudaStreamWaitEvent(st, b->slab_join[kSlabStreams - 1], 0));
+    }
     for (int gi = 0; gi < G; gi++) {
       Group& g = *lg[gi];
       FastCtx& c = ctx[gi];
@@ -771,10 +783,5 @@ static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, c
   }
   for (int gi = 0; gi < G; gi++) fast_epilogue_kernel<<<ctx[gi].q.ns, 128, 0, st>>>(ctx[gi]);
   CUDA_TRY(cudaGetLastError());
-  if (guarded)
-    for (int gi = 0; gi < G; gi++) {
-      const long wcap = wam_fsk_batch_out_capacity(b, (long)kVerifyClasses * slab_len);
-      if ((rc = fast_carry_save(b, *lg[gi], ctx[gi], wcap, st)) != WAM_OK) return rc;
-    }
   return WAM_OK;
 }
