@@ -226,11 +226,13 @@ int wam_fsk_batch_fast_stats(wam_fsk_batch* b, wam_fast_stats* out);
  * fix every value).  n and stride multiples of 4, rows 16-byte aligned.  Not part of FSKCore. */
 int wam_awgn_add_device(float* d_samples, long stride, long n_rows, long n, const float* d_sigma,
                         unsigned long long seed, unsigned int seq, void* cuda_stream);
-/* Debug: the float64 verification windows of the last fast call of configuration group `group`.  counts6[c] = items of
- * class c (0..3: windows of c + 1 time slabs; 4 and 5: the two stages of an end-of-data check); with items != NULL and
- * items_cap >= 6 * cap * 3, items[(c * cap + i) * 3 + {0,1,2}] = stream (index inside the group), slab, result
- * (1 = the fast results stand, else 1 << 30 | bits naming what differed).  Returns cap, negative on error. */
-int wam_fsk_batch_debug_fast_windows(wam_fsk_batch* b, int group, int32_t* counts6, int32_t* items, long items_cap);
+/* Debug: the float64 verification windows of the last fast call of configuration group `group`.  *n_classes = number
+ * of window classes C (0..C-3: windows of c + 1 time slabs; C-2 and C-1: the two stages of an end-of-data check);
+ * counts (nullable) [C] items per class; items (nullable, items_cap >= C * cap * 3):
+ * items[(c * cap + i) * 3 + {0,1,2}] = stream (index inside the group), slab, result (1 = the fast results stand, else
+ * 1 << 30 | bits naming what differed).  Returns cap, negative on error. */
+int wam_fsk_batch_debug_fast_windows(wam_fsk_batch* b, int group, int* n_classes, int32_t* counts, int32_t* items,
+                                     long items_cap);
 /* test hook: multiplies the fast kernel's doubt band (1 = calibrated); a wide band flags many decisions */
 int wam_fsk_batch_debug_fast_band(wam_fsk_batch* b, double scale);
 

@@ -131,7 +131,7 @@ SYMBOLS = {
     "wam_fsk_batch_debug_fast_band": (C.c_int, [_vp, C.c_double]),
     "wam_fsk_batch_demodulate_pcm16": (C.c_int, [_vp, _vp, C.c_long, C.c_long, _vp, C.c_long, _vp, C.c_uint32]),
     "wam_host_bind_near_device": (C.c_int, [C.c_int]),
-    "wam_fsk_batch_debug_fast_windows": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_long]),
+    "wam_fsk_batch_debug_fast_windows": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_long]),
     "wam_iir_scratch_bytes": (C.c_size_t, [C.c_long, C.c_long]),
     "wam_iir_process_batch_device": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_long, C.c_long, C.c_long, _vp, _vp, C.c_size_t, _vp]),
     "wam_fir_process_batch_device": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_long, C.c_long, C.c_long, _vp, _vp, _vp]),

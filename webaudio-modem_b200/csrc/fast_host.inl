@@ -476,17 +476,18 @@ static int launch_exact_selected(wam_fsk_batch* b, DemodLaunch& L, const int32_t
 
 static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
-// time slab length for a call of n samples (n a multiple of kTile): kSlabTiles tiles, or the divisor of the call's
-// tile count nearest to it (so that no slab is short and every doubtful decision has a window)
+// time slab length for a call of n samples (n a multiple of kTile): kFastSlabTiles tiles, or the divisor of the call's
+// tile count nearest to it (so that no slab is short and every doubtful decision has a window).  A slab is also the
+// warm-up of a verification window: ~1000 samples are dozens of time constants of the filters at the usual baud rates.
 static long fast_slab_len(long n) {
   const long tiles = n / kTile;
-  if (tiles <= kSlabTiles) return tiles * kTile;
-  for (int delta = 0; delta <= kSlabTiles / 2; delta++)
+  if (tiles <= kFastSlabTiles) return tiles * kTile;
+  for (int delta = 0; delta <= kFastSlabTiles / 2; delta++)
     for (int sgn : {-1, 1}) {
-      const long t = kSlabTiles + sgn * delta;
+      const long t = kFastSlabTiles + sgn * delta;
       if (t > 0 && tiles % t == 0) return t * kTile;
     }
-  return (long)kSlabTiles * kTile;
+  return (long)kFastSlabTiles * kTile;
 }
 
 static int fast_prepare_buffers(wam_fsk_batch* b, Group& g, const FastGeom& q, cudaStream_t st) {

@@ -616,6 +616,17 @@ __device__ __forceinline__ int sm_tile_events_fast(FastB& b, uint32_t bits, uint
   return -1;
 }
 
+// Amplitudes inside the doubt band of the silence threshold (rare): our own reading is the plain float32 compare, so
+// that the float64 check of a decision that hinges on one of them usually agrees.  Out of line: the hot loop's
+// registers are all spoken for.
+__device__ __noinline__ uint32_t silent_plain_reading(const float* __restrict__ amp_tile, uint32_t adoubt, uint32_t silent, float thr) {
+  for (uint32_t m = adoubt; m != 0u; m &= m - 1u) {
+    const int k = __ffs((int)m) - 1;
+    if (!(amp_tile[k] < thr)) silent &= ~(1u << k);
+  }
+  return silent;
+}
+
 // Grid: one warp (32 streams) per CTA, TMA-staged tiles, time slabs as in fsk_demod_exact_kernel<.., STAGE_TMA>.
 // Common case only (host: fast path eligibility): rows contiguous and 16-byte aligned, aligned calls (n a multiple of
 // 32 ever since reset), integral sync ring, eod_count > 16, by-value sync template, no write-back / ragged counts.
@@ -770,15 +781,7 @@ __device__ __forceinline__ void fsk_demod_fast_body(const DemodLaunch& L, float 
     // sample 0 of the tile sits in bit 15 of each mask: turn them round
     bits = __brev(bits) >> 16; dmask = __brev(dmask) >> 16; slo = __brev(slo) >> 16; shi = __brev(shi) >> 16;
     uint32_t silent = shi, adoubt = slo ^ shi;
-    if (adoubt != 0u && active) {
-      // amplitudes inside the doubt band of the threshold (rare): our own reading is the plain float32 compare, so that
-      // the float64 check of a decision that hinges on one of them usually agrees
-      const float* ar = ah + t * (kTile / 2);
-      for (uint32_t m = adoubt; m != 0u; m &= m - 1u) {
-        const int k = __ffs((int)m) - 1;
-        if (!(ar[k] < b.sil_thr)) silent &= ~(1u << k);
-      }
-    }
+    if (adoubt != 0u && active) silent = silent_plain_reading(ah + t * (kTile / 2), adoubt, silent, b.sil_thr);
     __syncwarp();  // every lane is done with the input tile
 
     // ---------------- B, with replay of A2 on resetState() ----------------

@@ -344,8 +344,9 @@ static int derive(const wam_fsk_config& c, FskDerived& d) {
 // ------------------------------------------------------------------------------------------
 // Device buffers of the fast path, per configuration group (used by fast_host.inl).
 constexpr int kVerifyClasses = 4;    // verification windows of 1..4 time slabs
+constexpr int kFastSlabTiles = 60;   // time slab of the fast path = the verification windows' grain (halving it buys nothing: measured)
 constexpr int kStageE1 = kVerifyClasses, kStageE2 = kVerifyClasses + 1, kAllClasses = kVerifyClasses + 2;  // two-stage end-of-data check
-constexpr int kSlabStreams = 12;
+constexpr int kSlabStreams = 16;
 constexpr int kVerifyCap = 1024;     // windows per class and call; the excess is re-run over the whole call
 struct FastBuffers {
   // checkpoints 1..S of the per-stream state ([slab][field][stream]); checkpoint 0 is the live state
@@ -1272,19 +1273,23 @@ extern "C" int wam_fsk_batch_fast_stats(wam_fsk_batch* b, wam_fast_stats* out) {
   return WAM_OK;
 }
 
-// Debug: the verification windows of the last fast call of configuration group `group`: per class c (0..3: windows
-// of c + 1 slabs, 4 / 5: the two stages of an end-of-data check) counts[c] items, and for item i of class c
-// items[(c * cap + i) * 3 + {0, 1, 2}] = stream (local index), slab, result (1 = confirmed, else 1 << 30 | what differed).
-// Returns cap (the per-class capacity), negative on error.
-extern "C" int wam_fsk_batch_debug_fast_windows(wam_fsk_batch* b, int group, int32_t* counts6, int32_t* items, long items_cap) {
-  if (!b || group < 0 || group >= (int)b->groups.size() || !counts6) return fail(WAM_E_INVALID, "bad argument");
+// Debug: the verification windows of the last fast call of configuration group `group`.  *n_classes receives the
+// number of window classes C (classes 0..C-3: windows of c + 1 slabs; C-2 / C-1: the two stages of an end-of-data
+// check); counts (nullable, C entries) the items per class; items (nullable, C * cap * 3 entries)
+// items[(c * cap + i) * 3 + {0, 1, 2}] = stream (local index), slab, result (1 = confirmed, else 1 << 30 | what
+// differed).  Returns cap (the per-class capacity), negative on error.
+extern "C" int wam_fsk_batch_debug_fast_windows(wam_fsk_batch* b, int group, int* n_classes, int32_t* counts, int32_t* items,
+                                                long items_cap) {
+  if (!b || group < 0 || group >= (int)b->groups.size() || !n_classes) return fail(WAM_E_INVALID, "bad argument");
+  *n_classes = kAllClasses;
+  if (!counts) return kVerifyCap;
   CUDA_TRY(cudaSetDevice(b->device));
   CUDA_TRY(cudaDeviceSynchronize());
   FastBuffers& fb = b->groups[(size_t)group].fb;
-  for (int c = 0; c < kAllClasses; c++) counts6[c] = 0;
+  for (int c = 0; c < kAllClasses; c++) counts[c] = 0;
   if (!fb.scratch_ready) return kVerifyCap;
-  CUDA_TRY(cudaMemcpy(counts6, fb.item_count, sizeof(int32_t) * kAllClasses, cudaMemcpyDeviceToHost));
-  counts6[kStageE2] = counts6[kStageE1];
+  CUDA_TRY(cudaMemcpy(counts, fb.item_count, sizeof(int32_t) * kAllClasses, cudaMemcpyDeviceToHost));
+  counts[kStageE2] = counts[kStageE1];
   const size_t nv = (size_t)kAllClasses * kVerifyCap;
   if (items && items_cap >= (long)(nv * 3)) {
     std::vector<int32_t> li(nv), sl(nv), rs(nv);

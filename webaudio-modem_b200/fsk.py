@@ -280,17 +280,20 @@ class FSKBatch:
         return out, out_len
 
     def debug_fast_windows(self, group: int = 0):
-        """Verification windows of the last fast call: list of dict(cls, stream, slab, result)."""
-        counts = np.zeros(6, dtype=np.int32)
-        cap = L.check(self._lib.wam_fsk_batch_debug_fast_windows(self._h, group, counts.ctypes.data, None, 0))
-        items = np.zeros(6 * cap * 3, dtype=np.int32)
-        L.check(self._lib.wam_fsk_batch_debug_fast_windows(self._h, group, counts.ctypes.data, items.ctypes.data, items.size))
+        """Verification windows of the last fast call: (n_classes, list of dict(cls, stream, slab, result)); the last two
+        classes are the stages of an end-of-data check."""
+        nc = C.c_int(0)
+        cap = L.check(self._lib.wam_fsk_batch_debug_fast_windows(self._h, group, C.byref(nc), None, None, 0))
+        counts = np.zeros(nc.value, dtype=np.int32)
+        items = np.zeros(nc.value * cap * 3, dtype=np.int32)
+        L.check(self._lib.wam_fsk_batch_debug_fast_windows(self._h, group, C.byref(nc), counts.ctypes.data, items.ctypes.data,
+                                                           items.size))
         out = []
-        for c in range(6):
+        for c in range(nc.value):
             for i in range(min(int(counts[c]), cap)):
                 k = (c * cap + i) * 3
                 out.append(dict(cls=c, stream=int(items[k]), slab=int(items[k + 1]), result=int(items[k + 2])))
-        return out
+        return nc.value, out
 
     def demodulate_pcm16(self, samples: np.ndarray, flags: int = 0):
         """samples int16 [n_streams, n] (16-bit PCM, value / 32768); same result as demodulate(samples / 32768)."""
