@@ -450,10 +450,12 @@ static int launch_exact_selected(wam_fsk_batch* b, DemodLaunch& L, const int32_t
   L.block_begin[0] = 0;
   L.block_begin[1] = (max_streams + 31) / 32;
   const int W = L.block_begin[1];
+  const bool thin = a.thin_margin > 0.0;
   bool pipe = n >= 8 * kTile;
   if (pipe) {
-    auto kern = fsk_demod_pipe_kernel<true>;
-    if (b->pipe_per_sm[1] < 0) {
+    auto kern = thin ? fsk_demod_pipe_kernel<true, true> : fsk_demod_pipe_kernel<true, false>;
+    int& per_sm_cached = thin ? b->pipe_per_sm_thin : b->pipe_per_sm[1];
+    if (per_sm_cached < 0) {
       int ring_words = 0;
       for (auto& g : b->groups) ring_words = std::max(ring_words, g.d.ring_words);
       b->pipe_smem = sizeof(PipeShared) + (size_t)ring_words * 32 * sizeof(uint32_t);
@@ -462,12 +464,13 @@ static int launch_exact_selected(wam_fsk_batch* b, DemodLaunch& L, const int32_t
       int per_sm = 0;
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->pipe_smem));
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPipeThreads, b->pipe_smem));
-      b->pipe_per_sm[1] = per_sm;
+      per_sm_cached = per_sm;
     }
     L.pipe_ring_smem = b->pipe_ring_smem;
-    pipe = b->pipe_per_sm[1] > 0;
+    pipe = per_sm_cached > 0;
     if (pipe) kern<<<W, kPipeThreads, b->pipe_smem, st>>>(L);
   }
+  if (!pipe && thin) return fail(WAM_E_UNSUPPORTED, "thin-compare verification needs the pipeline kernel");
   if (!pipe) fsk_demod_exact_kernel<true, false><<<W, 32, 0, st>>>(L);
   b->launches++;
   CUDA_TRY(cudaGetLastError());

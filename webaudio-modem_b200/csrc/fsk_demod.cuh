@@ -529,7 +529,10 @@ __device__ __forceinline__ bool sm_sample_generic(BState& b, int bit, double amp
 // Event-driven state machine for one tile (integral ring, eod_count > 16).  `bits` holds the hard
 // decisions of decimated samples 0..nk-1 of the tile, amp[k*32] their amplitudes (f64, smem).
 // Returns the decimated index at which resetState() ran, or -1.
-template <bool RING_ARG>
+// THIN (verification launches only): flag silence compares closer than DemodArgs.thin_margin to the threshold.  A
+// compile-time switch: as a run-time test the compiler hoists the sixteen compares of a tile above it, which costs the
+// few-stream pipeline kernel a fifth of its speed.
+template <bool RING_ARG, bool THIN = false>
 __device__ __forceinline__ int sm_tile_events(BState& b, uint32_t bits, const double* __restrict__ amp,
                                               int b_from, int nk, uint32_t pos_t0, uint32_t len_t0, uint32_t slot_t0,
                                               uint32_t alen_t0, const DemodArgs& a, int li, uint8_t* out_row,
@@ -587,7 +590,7 @@ __device__ __forceinline__ int sm_tile_events(BState& b, uint32_t bits, const do
           silent |= (av < thr ? 1u : 0u) << k;
         }
       }
-      if (a.thin_margin > 0.0) {
+      if (THIN) {
         // verification runs whose threshold is exact to ~1e-12: a compare this close to it proves nothing
         const double m = thr * a.thin_margin;
         bool thin = false;

@@ -67,7 +67,7 @@ __device__ __forceinline__ bool pipe_spin(unsigned& spins, PipeShared& sh) {
   return true;
 }
 
-template <bool ALIGNED>
+template <bool ALIGNED, bool THIN = false>
 __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const __grid_constant__ DemodLaunch L) {
   int gi = 0;
 #pragma unroll
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(kPipeThreads, 5) fsk_demod_pipe_kernel(const _
         int k_reset = -1;
         if (lane_busy) {
           const uint32_t bits = sh.bits[t % kPipeDec][lane];
-          k_reset = sm_tile_events<true>(b, bits, sh.amp[t % kPipeDec] + lane, b_from, nk, pos_t0, len_t0, slot_t0,
+          k_reset = sm_tile_events<true, THIN>(b, bits, sh.amp[t % kPipeDec] + lane, b_from, nk, pos_t0, len_t0, slot_t0,
                                          alen_t0, a, li, out_row, ring, rstride);
           if (k_reset < 0 || 2 * (k_reset + 1) >= v_hi) {
             // this lane is done with the tile: end-of-tile ring bookkeeping

@@ -418,6 +418,7 @@ struct wam_fsk_batch {
   size_t stage_nvalid_bytes = 0;
   int fused_per_sm = -1;          // resident CTAs per SM of fsk_demod_exact_kernel<true, false, true>, -1 = not asked yet
   int fast_per_sm = -1;           // the same for fsk_demod_fast_kernel
+  int pipe_per_sm_thin = -1;  // the same for the thin-compare variant of the aligned kernel (verification launches)
   int pipe_per_sm[2] = {-1, -1};  // resident CTAs per SM of fsk_demod_pipe_kernel<unaligned / aligned>, -1 = not asked yet
   size_t pipe_smem = 0;
   int pipe_ring_smem = 0;
