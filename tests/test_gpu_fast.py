@@ -154,6 +154,9 @@ def test_open_readings_are_settled_at_the_next_call(gpu_wam, oracle, scale):
         assert fs["error_flags"] == 0, fs
         if scale > 1.0:
             assert fs["carried_settled"] > 0, fs
+            # the float64 re-reading agrees with the open float32 readings nearly always (a doubtful sample is wrong about
+            # once in 300): the usual outcome is "cleared", not "corrected"
+            assert fs["carried_corrected"] * 20 <= fs["carried_settled"], fs
     # reset() and renew() drop what was carried
     db = DeviceBatch(gpu_wam, cfgs, idx, 160)
     db.b.debug_fast_band(300.0)

@@ -534,8 +534,12 @@ static int fast_prepare_buffers(wam_fsk_batch* b, Group& g, const FastGeom& q, c
 
 static int fast_streams(wam_fsk_batch* b) {
   if (!b->slab_streams[0]) {
+    // the carry save (last stream) runs beside the verification windows and must not get in their way: the windows are
+    // a few latency-bound CTAs on the critical path, the carry save is thousands of copy blocks off it
+    int lo = 0, hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     for (int i = 0; i < kSlabStreams; i++) {
-      CUDA_TRY(cudaStreamCreateWithFlags(&b->slab_streams[i], cudaStreamNonBlocking));
+      CUDA_TRY(cudaStreamCreateWithPriority(&b->slab_streams[i], cudaStreamNonBlocking, i == kSlabStreams - 1 ? lo : hi));
       CUDA_TRY(cudaEventCreateWithFlags(&b->slab_join[i], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaEventCreateWithFlags(&b->slab_fork, cudaEventDisableTiming));
