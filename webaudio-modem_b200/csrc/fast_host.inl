@@ -651,9 +651,13 @@ static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, c
     q.ah_stride = (long)round_up((size_t)q.pa + (size_t)(n / 2), 4);
     q.sync_slabs = (int)((2L * g.d.total_bits + slab_len - 1) / slab_len) + 1;
     {
-      // two-stage end-of-data check: amplitude ring + warm-up before the sync; silent run + one slab + warm-up
-      const int l1 = (int)((2L * g.d.amp_cap + slab_len - 1) / slab_len) + 2;
-      const int l2 = (int)((2L * g.d.eod_count + slab_len - 1) / slab_len) + 2;
+      // two-stage end-of-data check: amplitude ring before the sync / silent run before the decision, each behind a
+      // warm-up.  Amplitudes only pass the full-rate filters (pre-filter, I/Q low-pass): sixteen time constants of the
+      // slower one (the float32 state error of 1e-7 shrinks to 1e-14) are warm-up enough, a whole slab is not needed.
+      const double decay = -std::log(std::sqrt(std::max(std::max(g.d.lp_a2, g.d.pre_a2), 1e-300)));
+      const long warm = decay > 0.0 ? (long)std::ceil(16.0 / decay) : slab_len;
+      const int l1 = (int)((2L * g.d.amp_cap + warm + slab_len - 1) / slab_len) + 1;
+      const int l2 = (int)((2L * g.d.eod_count + warm + slab_len - 1) / slab_len) + 1;
       const bool whole = n == (long)n_slabs * slab_len;
       const bool ok = whole && l1 <= kVerifyClasses && l2 <= kVerifyClasses && l1 <= n_slabs && l2 <= n_slabs;
       q.e1_len = ok ? l1 : 0; q.e2_len = ok ? l2 : 0;
