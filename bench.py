@@ -38,6 +38,10 @@ import time
 
 import numpy as np
 
+# before anything creates a CUDA context: one hardware work queue per stream of the fast path's float64 checks
+# (webaudio-modem_b200/__init__.py says why)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
