@@ -4,7 +4,7 @@ usage: python scripts/soak_config2_seeds.py [--seeds 1000:1016] [--out profiles/
 import argparse, importlib, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import bench
+import bench  # (sets CUDA_DEVICE_MAX_CONNECTIONS before the CUDA context exists)
 import numpy as np
 import torch
 
