@@ -100,11 +100,8 @@ int fir_process_batch_device(const double* d_taps, int ntaps, const float* d_in,
   fa.state = hist > 0 ? d_state : nullptr;
   fa.state_new = (hist > 0 && d_state) ? d_state_new : nullptr;
   const size_t smem = sizeof(double) * (size_t)fir_smem_doubles(ntaps);
-  static size_t smem_set = 48 * 1024;  // opt-in above the default limit, once per size
-  if (smem > smem_set) {
+  if (smem > 48 * 1024)  // opt-in above the default limit (per device: set on every such call, it is cheap)
     CUDA_TRY(cudaFuncSetAttribute(fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
   fir_kernel<<<(unsigned)((size_t)fa.tiles * (size_t)n_streams), kFirThreads, smem, st>>>(fa);
   CUDA_TRY(cudaGetLastError());
   if (fa.state_new)
