@@ -374,7 +374,36 @@ __global__ void fast_compare_kernel(const FastCtx c, int cls) {
     same = __all_sync(0xffffffffu, eq);
     if (!same) why |= 1 << 19;
   }
-  if (lane == 0) c.item_res[si] = same ? 1 : (why | (1 << 30));
+  // ---- local repair.  When the float64 run differs from the fast pass ONLY in what a byte holds — bytes of the window,
+  // or the byte under construction at its end (a data bit voted the other way) — while every counter, position and
+  // timing field agrees, the two trajectories are the same from here on: the data bits of a byte feed nothing but
+  // the byte.  Then the float64 bytes replace the fast ones in place, and a byte still under construction is
+  // corrected where it lands (or in the last checkpoint, if the call ends first).  No re-run.
+  const bool cls_plain = cls < kVerifyClasses;
+  const int only_bytes = 1 << 19, only_current = 1 << 7;
+  if (!same && cls_plain && (why & ~(only_bytes | only_current)) == 0 && o1 <= c.q.out_stride) {
+    // (bytes are only compared when the state agreed; with a differing byte under construction they may differ too)
+    const uint8_t* pa = c.sv_out + si * c.q.out_stride;
+    uint8_t* pb = c.out + fc_row(c, li) * c.q.out_stride + o0;
+    for (int k = lane; k < nb; k += 32) pb[k] = pa[k];
+    if (lane == 0 && (why & only_current)) {
+      const uint32_t diff = c.sv_u32[(size_t)U_CURRENT * nv + si] ^ ue[(size_t)U_CURRENT * ns + li];
+      const uint32_t sd = ue[(size_t)U_SYNC_DET * ns + li];
+      // follow the byte: later checkpoints carry it until it is written (byte count grows) or its frame ends
+      for (int k = wend; k <= c.q.n_slabs; ++k) {
+        uint32_t* uk = (k == 0 ? c.u32 : c.ck_u32 + (size_t)(k - 1) * U32_COUNT * ns);
+        if ((int)uk[(size_t)U_OUT_N * ns + li] > o1) {  // written at index o1 (no other frame can have synced meanwhile)
+          if (o1 < c.q.out_stride) c.out[fc_row(c, li) * c.q.out_stride + o1] ^= (uint8_t)diff;
+          break;
+        }
+        if (!uk[(size_t)U_STARTED * ns + li] || uk[(size_t)U_SYNC_DET * ns + li] != sd) break;  // the frame ended without it
+        uk[(size_t)U_CURRENT * ns + li] ^= diff;  // still under construction at this checkpoint
+      }
+    }
+    same = true;
+    why |= 1 << 29;  // (debug record: repaired in place)
+  }
+  if (lane == 0) c.item_res[si] = (same && !(why & (1 << 29))) ? 1 : (why | (1 << 30));
   if (lane == 0) {
     atomicAdd(c.hard_count + (same ? 1 : 2), 1);
     if (!same) fc_hard(c, li);
@@ -738,16 +767,6 @@ static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, c
   if (guarded) {
     for (int gi = 0; gi < G; gi++) fast_collect_kernel<<<dim3(4, (unsigned)std::min(n_slabs, 64)), 256, 0, st>>>(ctx[gi]);
     CUDA_TRY(cudaEventRecord(b->slab_fork, st));
-    {
-      // beside the checks: keep the last slabs of the streams that end the call with open readings
-      cudaStream_t sc = b->slab_streams[kSlabStreams - 1];
-      CUDA_TRY(cudaStreamWaitEvent(sc, b->slab_fork, 0));
-      const long wcap = wam_fsk_batch_out_capacity(b, (long)kVerifyClasses * slab_len);
-      for (int gi = 0; gi < G; gi++)
-        if ((rc = fast_carry_save(b, *lg[gi], ctx[gi], wcap, sc)) != WAM_OK) return rc;
-      CUDA_TRY(cudaEventRecord(b->slab_join[kSlabStreams - 1], sc));
-      CUDA_TRY(cudaStreamWaitEvent(st, b->slab_join[kSlabStreams - 1], 0));
-    }
     for (int gi = 0; gi < G; gi++) {
       Group& g = *lg[gi];
       FastCtx& c = ctx[gi];
@@ -780,6 +799,17 @@ static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, c
         CUDA_TRY(cudaStreamWaitEvent(st, b->slab_join[sidx], 0));
       }
     }
+    {
+      // behind the checks (they may still correct a byte under construction in the checkpoints), beside the hard list
+      // and the epilogue: keep the last slabs of the streams that end the call with open readings
+      cudaStream_t sc = b->slab_streams[kSlabStreams - 1];
+      CUDA_TRY(cudaEventRecord(b->slab_fork, st));
+      CUDA_TRY(cudaStreamWaitEvent(sc, b->slab_fork, 0));
+      const long wcap = wam_fsk_batch_out_capacity(b, (long)kVerifyClasses * slab_len);
+      for (int gi = 0; gi < G; gi++)
+        if ((rc = fast_carry_save(b, *lg[gi], ctx[gi], wcap, sc)) != WAM_OK) return rc;
+      CUDA_TRY(cudaEventRecord(b->slab_join[kSlabStreams - 1], sc));
+    }
     // whole-call float64 run of the hard lists, on the live state and rings
     for (int gi = 0; gi < G; gi++) {
       Group& g = *lg[gi];
@@ -794,6 +824,7 @@ static int fast_demodulate(wam_fsk_batch* b, DemodLaunch& L, Group* const* lg, c
     }
   }
   for (int gi = 0; gi < G; gi++) fast_epilogue_kernel<<<ctx[gi].q.ns, 128, 0, st>>>(ctx[gi]);
+  if (guarded) CUDA_TRY(cudaStreamWaitEvent(st, b->slab_join[kSlabStreams - 1], 0));  // the carry save
   CUDA_TRY(cudaGetLastError());
   return WAM_OK;
 }
