@@ -275,3 +275,42 @@ def test_time_slabs_next_to_a_foreign_kernel(gpu_wam, oracle):
         if db.b.fast_stats()["error_flags"] & 4:
             continue  # hand-over timed out: reported, not silent
         _check(got, st, want, ost)
+
+
+def test_local_repair_of_a_data_bit_voted_the_other_way(gpu_wam):
+    """BASELINE config 2 at full size, a seed on which the float64 check of a doubtful data-bit vote disagrees with the
+    fast pass while all timing agrees: the byte is corrected in place (no whole-call re-run) and every stream equals the
+    float64 kernels' result."""
+    import os
+    import sys
+
+    import torch
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    L = _lib(gpu_wam)
+    dev = torch.device("cuda", 0)
+    S = 65536
+    x, cfg_index, _, _ = bench.generate_on_device(gpu_wam, torch, dev, S, seed=2043)
+    res = {}
+    for name, fl in (("fast", 0), ("exact", L.WAM_BATCH_EXACT_ONLY)):
+        b = gpu_wam.FSKBatch(S, [bench.CFG_CH1, bench.CFG_CH2], cfg_index)
+        cap = b.out_capacity(bench.N_SAMPLES)
+        d_out = torch.zeros((S, cap), dtype=torch.uint8, device=dev)
+        d_len = torch.zeros(S, dtype=torch.int32, device=dev)
+        b.demodulate_device(x.data_ptr(), bench.N_SAMPLES, bench.N_SAMPLES, d_out.data_ptr(), cap, d_len.data_ptr(), flags=fl)
+        torch.cuda.synchronize()
+        st = b.status()
+        res[name] = (d_out.cpu().numpy(), d_len.cpu().numpy(), [tuple(float(s[k]) for k in KEYS) for s in st])
+        if name == "fast":
+            fs = b.fast_stats()
+            repaired = [w for g in (0, 1) for w in b.debug_fast_windows(g)[1] if w["result"] & (1 << 29)]
+        b.close()
+    fo, fl_, fst = res["fast"]
+    eo, el, est = res["exact"]
+    assert fs["fast_calls"] == 1 and fs["error_flags"] == 0
+    assert (fl_ == el).all() and fst == est
+    assert all(bytes(fo[i, :fl_[i]]) == bytes(eo[i, :el[i]]) for i in range(S))
+    assert repaired, "this seed is known to need a local repair"
+    assert fs["windows_refuted"] == 0 and fs["flagged_last_call"] == 0
