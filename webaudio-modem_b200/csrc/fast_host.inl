@@ -387,17 +387,25 @@ __global__ void fast_compare_kernel(const FastCtx c, int cls) {
     uint8_t* pb = c.out + fc_row(c, li) * c.q.out_stride + o0;
     for (int k = lane; k < nb; k += 32) pb[k] = pa[k];
     if (lane == 0 && (why & only_current)) {
-      const uint32_t diff = c.sv_u32[(size_t)U_CURRENT * nv + si] ^ ue[(size_t)U_CURRENT * ns + li];
+      // the data bits decided so far (bit positions 1 .. bitpos - 1 of the frame sit in bits 7 .. 9 - bitpos of the byte)
+      // take the float64 run's values; SET, not toggled: another window of the same stream may repair the same byte
+      const int bp = (int)ue[(size_t)U_BITPOS * ns + li];
+      const uint32_t mask = (bp >= 1 && bp <= 9) ? (0xffu & ~((1u << (9 - bp)) - 1u)) : 0u;
+      const uint32_t good = c.sv_u32[(size_t)U_CURRENT * nv + si] & mask;
       const uint32_t sd = ue[(size_t)U_SYNC_DET * ns + li];
       // follow the byte: later checkpoints carry it until it is written (byte count grows) or its frame ends
-      for (int k = wend; k <= c.q.n_slabs; ++k) {
+      for (int k = wend; k <= c.q.n_slabs && mask != 0u; ++k) {
         uint32_t* uk = (k == 0 ? c.u32 : c.ck_u32 + (size_t)(k - 1) * U32_COUNT * ns);
         if ((int)uk[(size_t)U_OUT_N * ns + li] > o1) {  // written at index o1 (no other frame can have synced meanwhile)
-          if (o1 < c.q.out_stride) c.out[fc_row(c, li) * c.q.out_stride + o1] ^= (uint8_t)diff;
+          if (o1 < c.q.out_stride) {
+            uint8_t* q8 = c.out + fc_row(c, li) * c.q.out_stride + o1;
+            *q8 = (uint8_t)((*q8 & ~mask) | good);
+          }
           break;
         }
         if (!uk[(size_t)U_STARTED * ns + li] || uk[(size_t)U_SYNC_DET * ns + li] != sd) break;  // the frame ended without it
-        uk[(size_t)U_CURRENT * ns + li] ^= diff;  // still under construction at this checkpoint
+        uint32_t* cur = uk + (size_t)U_CURRENT * ns + li;  // still under construction at this checkpoint
+        *cur = (*cur & ~mask) | good;
       }
     }
     same = true;
