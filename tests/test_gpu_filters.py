@@ -73,3 +73,22 @@ def importlib_filters(wam):
     import importlib
 
     return importlib.import_module("webaudio-modem_b200.filters")
+
+
+def test_more_streams_than_a_grid_dimension(gpu_wam, oracle):
+    """70,000 streams in one call (round 1 stopped at 65,535: streams were a grid's y dimension), IIR with carried state
+    and FIR, spot-checked against the oracle."""
+    filt = importlib_filters(gpu_wam)
+    n_streams, n = 70000, 300
+    rng = np.random.default_rng(70)
+    x = rng.standard_normal((n_streams, n)).astype(np.float32)
+    c = oracle.FilterDesign.butterworthBandpass(1750, 800, 48000)
+    state = np.zeros((n_streams, 4), dtype=np.float64)
+    y1 = filt.iir_process_batch(c["b"], c["a"], np.ascontiguousarray(x[:, :100]), state)
+    y2 = filt.iir_process_batch(c["b"], c["a"], np.ascontiguousarray(x[:, 100:]), state)
+    y = np.concatenate([y1, y2], axis=1)
+    taps = oracle.FilterDesign.sincLowpass(1000, 48000, 51)
+    z = filt.fir_process_batch(taps, x)
+    for s in (0, 1, 32767, 65534, 65535, 65536, 69999):
+        np.testing.assert_allclose(y[s], oracle.IIRFilter(c["b"], c["a"]).processBuffer(x[s]), rtol=TOL, atol=1e-6)
+        np.testing.assert_allclose(z[s], oracle.FIRFilter(taps).processBuffer(x[s]), rtol=TOL, atol=1e-6)

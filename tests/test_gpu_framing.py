@@ -278,3 +278,16 @@ def test_session_mux_send_half_round_trip(gpu_wam):
         rx = gpu_wam.FSKCore()
         rx.configure({})
         assert bytes(rx.demodulateData(sig.copy())) == payloads[s]
+
+
+def test_session_mux_send_half_argument_errors(gpu_wam):
+    mux = gpu_wam.FSKSessionMux(4, {}, max_block=256)
+    with pytest.raises(gpu_wam.WamError):
+        mux.send(4, b"x")  # no such session
+    assert mux.pull(0, 128) is None and not mux.is_modulating(0)
+    mux.modulate()  # nothing queued: a no-op
+    # two configurations: the send half declines (one batched modulate needs one configuration)
+    two = gpu_wam.FSKSessionMux(4, [{}, dict(baudRate=300)], np.array([0, 1, 0, 1], dtype=np.int32), max_block=256)
+    two.send(0, b"AB")
+    with pytest.raises(gpu_wam.WamError):
+        two.modulate()
