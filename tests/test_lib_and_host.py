@@ -150,3 +150,17 @@ def test_napi_addon_is_valid_c_against_the_header_and_binds_what_the_ts_host_cal
     for fn in set(re.findall(r"\b(wam_\w+)\(", c_src)):
         assert re.search(r"\b%s\(" % fn, header), fn
     assert os.path.exists(os.path.join(ROOT, "host", "alias-hook.mjs")) and os.path.exists(os.path.join(ROOT, "host", "alias-hook-impl.mjs"))
+
+
+def test_traffic_record_belongs_to_the_current_kernel_sources():
+    """bench.py reports roofline.traffic from profiles/r02_demod_traffic.json only while it was measured on the sources in
+    the tree (it says "stale" otherwise): the committed record must be the current one."""
+    import json
+    import sys
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    rec = json.load(open(os.path.join(ROOT, "profiles", "r02_demod_traffic.json")))
+    assert rec["source_hash"] == bench.kernel_source_hash()
+    assert rec["algorithmic_bytes_per_step"] == 65536 * 48000 * 4 and rec["bytes_per_step"] > rec["algorithmic_bytes_per_step"]
